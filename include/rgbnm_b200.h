@@ -1,0 +1,143 @@
+/* rgbnm_b200.h -- C ABI of the B200-native DCT-domain ViT hot path.
+ *
+ * Drop-in boundary for the hot path of JeongsooP/RGB-no-more.
+ * Every entry point is `extern "C"`, takes plain pointers and sizes (device pointers
+ * are raw `void*`/typed pointers into HBM, `stream` is a `cudaStream_t` passed as
+ * `void*`), and returns an `rgbnm_status` (0 = OK).  No torch types cross this line.
+ * Reference citations are file:line relative to the reference checkout.
+ *
+ * The shared library is `rgb_no_more_b200/librgbnm_b200.so`, built by
+ * `__graft_entry__.build()` with nvcc for sm_100a only.
+ */
+#ifndef RGBNM_B200_H
+#define RGBNM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    RGBNM_OK = 0,
+    RGBNM_ERR_NOT_JPEG = 1,
+    RGBNM_ERR_CORRUPT = 2,
+    RGBNM_ERR_UNSUPPORTED = 3,
+    RGBNM_ERR_PROGRESSIVE = 4,
+    RGBNM_ERR_BUFFER = 5,
+    RGBNM_ERR_IO = 6,
+    RGBNM_ERR_CUDA = 7,
+    RGBNM_ERR_ARG = 8
+} rgbnm_status;
+
+const char* rgbnm_strerror(int code);
+/* Text of the last CUDA error seen by this thread's calls ("" if none). */
+const char* rgbnm_last_cuda_error(void);
+/* ABI version; bumped whenever a struct below changes. */
+int rgbnm_abi_version(void);
+
+/* ------------------------------------------------------------------------------
+ * (B1) JPEG front end -- host.  Replaces dct_manip.read_coefficients
+ *      (dct_manip/dct_manip.cpp:152-178 -> read_coefficients_using :98-150 ->
+ *      extract_channel :78-96).  Huffman decode stays on the host (north_star).
+ * ---------------------------------------------------------------------------- */
+typedef struct {
+    int32_t width, height, ncomp, progressive;
+    int32_t hb[3], wb[3];       /* height/width in 8x8 blocks per component      */
+    int32_t dsh[3], dsw[3];     /* downsampled height/width (the `dimensions` tensor) */
+    int32_t hsamp[3], vsamp[3];
+} rgbnm_jpeg_info;
+
+int rgbnm_jpeg_info_from_memory(const uint8_t* data, size_t size, rgbnm_jpeg_info* info);
+
+/* One image.  y: hb[0]*wb[0]*64 int16; cbcr: 2*hb[1]*wb[1]*64 int16 (Cb plane then Cr
+ * plane; ignored for grayscale); quant: ncomp*64 int16, natural order; dims: ncomp*2
+ * int32 (may be NULL); clamp_flag: set to 1 iff some dequantised coefficient leaves
+ * [-1024, 1016], i.e. the clamp of datasets.py:288-290 is live (may be NULL). */
+int rgbnm_jpeg_read_coefficients(const uint8_t* data, size_t size, int16_t* y, size_t y_capacity,
+                                 int16_t* cbcr, size_t c_capacity, int16_t* quant, int32_t* dims,
+                                 int32_t* clamp_flag);
+
+/* Batch decode on `nthreads` host threads (0 = all cores) straight into the batch
+ * layout the fused kernel reads: y [n][hb][wb][64], cbcr [n][2][hb/2][wb/2][64],
+ * quant [n][3][64].  Every image must be hb x wb blocks, 4:2:0 or grayscale.
+ * Replaces DataLoader workers + default collate (datasets.py:542-556). */
+int rgbnm_jpeg_decode_batch(const uint8_t* const* data, const size_t* sizes, int n, int hb, int wb,
+                            int16_t* y, int16_t* cbcr, int16_t* quant, uint8_t* clamp_flags,
+                            int32_t* status, int nthreads);
+
+int rgbnm_jpeg_read_file(const char* path, uint8_t** out, size_t* size);
+void rgbnm_free(void* p);
+
+/* Coefficient writer for fixtures: mirror of write_coefficients (dct_manip.cpp:265-313).
+ * Luma sampling chroma_h x chroma_v (1 or 2), chroma 1x1; standard Annex-K tables. */
+int rgbnm_jpeg_write_coefficients(int width, int height, int ncomp, int chroma_h, int chroma_v,
+                                  const int16_t* y, const int16_t* cbcr, const int16_t* quant,
+                                  uint8_t** out, size_t* out_size);
+
+/* ------------------------------------------------------------------------------
+ * (K0) Fused DCT-domain data path -- device.  One launch replaces, per image:
+ *   dequantise+clamp (datasets.py:288-293) -> crop (dct_ops.py:584-599) ->
+ *   resize (dct_ops.py:529-580) -> RandomFlip_DCT (custom_transforms.py:913-942) ->
+ *   RandAugment_dct ops (custom_transforms.py:944-1127) -> ToRange (:406-466) ->
+ *   grouped-embedding rearrange + sub-block conversion + collapse
+ *   (models/plainvit.py:200-216)
+ * and writes the (B, 196, 384) input of the patch-projection Linear.
+ * ---------------------------------------------------------------------------- */
+enum rgbnm_op {
+    RGBNM_OP_NOP = 0, RGBNM_OP_TRANSLATE_X = 1, RGBNM_OP_TRANSLATE_Y = 2, RGBNM_OP_ROT90 = 3,
+    RGBNM_OP_CUTOUT = 4, RGBNM_OP_BRIGHTNESS = 5, RGBNM_OP_CONTRAST = 6, RGBNM_OP_COLOR = 7,
+    RGBNM_OP_AUTOCONTRAST = 8, RGBNM_OP_AUTOSATURATION = 9, RGBNM_OP_POSTERIZE = 10,
+    RGBNM_OP_SHARPNESS = 11, RGBNM_OP_MIDFREQ = 12, RGBNM_OP_GRAYSCALE = 13,
+    RGBNM_OP_CHROMADROP = 14, RGBNM_OP_SOLARIZE_ADD = 15, RGBNM_OP_INVERT = 16
+};
+#define RGBNM_MAX_OPS 4
+#define RGBNM_FILTER_SLOTS 48
+
+typedef struct {
+    int16_t code;      /* enum rgbnm_op */
+    int16_t p[8];      /* integer parameters (see rgb_no_more_b200/plan.py:resolve_op) */
+    int16_t pad;
+    float f;           /* float parameter, fp32-exact */
+} rgbnm_plan_op;       /* 24 bytes */
+
+typedef struct {
+    int16_t crop_i, crop_j, crop_size;  /* luma crop window in blocks (chroma = /2) */
+    int16_t flip;                       /* RandomFlip_DCT applied */
+    int16_t n_ops;
+    int16_t clamp_in;                   /* 1: apply the dequant clamp (0 only if the decoder proved it idle) */
+    int16_t needs_stats;                /* plan holds Brightness / AutoContrast / AutoSaturation */
+    int16_t train;                      /* RandAugment stage present (entry clamp) */
+    rgbnm_plan_op ops[RGBNM_MAX_OPS];
+} rgbnm_plan;          /* 112 bytes */
+
+/* Per-launch constant tables (device pointers). */
+typedef struct {
+    const float* filters;        /* [RGBNM_FILTER_SLOTS][64] multiplicative 8x8 filters */
+    const int16_t* posterize_lut;/* [6][2048] */
+    const float* up_mats;        /* [23][64]: upsample matrices P_l for factors 2, 7, 14 */
+    const float* a16;            /* [16][16] reference-exact conversion matrix (strict paths) */
+} rgbnm_k0_tables;
+
+#define RGBNM_K0_OUT_F32 0
+#define RGBNM_K0_OUT_BF16 1
+#define RGBNM_K0_OUT_INT16_PLANES 2   /* debug/parity: int16 planes handed to ToRange */
+
+/* stats: float [n][RGBNM_MAX_OPS][2] scratch written by rgbnm_k0_dcstats and read by
+ * rgbnm_k0_fused (Brightness: mean|dc|*m; AutoContrast/AutoSaturation: min, max).
+ * y/cbcr/quant: quantised int16 coefficients in the batch layout above (hb x wb luma
+ * blocks).  out: [n][196][384] (f32 or bf16) or, in INT16_PLANES mode,
+ * [n][(28*28 + 2*14*14)*64] int16. */
+int rgbnm_k0_dcstats(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans,
+                     const rgbnm_k0_tables* tables, float* stats, int n, int hb, int wb, void* stream);
+int rgbnm_k0_fused(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans,
+                   const rgbnm_k0_tables* tables, const float* stats, void* out, int out_mode, int n,
+                   int hb, int wb, void* stream);
+/* Number of kernels the two calls above launch for one batch (for gpu_launches accounting). */
+int rgbnm_k0_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGBNM_B200_H */

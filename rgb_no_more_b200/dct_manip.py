@@ -1,0 +1,103 @@
+"""Drop-in for the reference's `dct_manip` extension module (boundary B1).
+
+`read_coefficients(path)` has the reference's return contract
+(/root/reference/dct_manip/dct_manip.cpp:152-178, bound at :578-606):
+    (dimensions int32 (C,2), quantization int16 (C,8,8), Y int16 (1,Hb,Wb,8,8),
+     CbCr int16 (2,Hb/2,Wb/2,8,8) or None)
+Errors surface as RuntimeError, like the pybind11-translated C++ exceptions of the
+reference (file open failure :155-159, libjpeg error_exit :24-41).
+
+To use it from the reference's datasets.py (`import dct_manip as dm`, datasets.py:10) put
+a one-line shim module named `dct_manip` on sys.path -- see INTEGRATION.md.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+
+
+def _info(buf: bytes) -> _lib.JpegInfo:
+    L = _lib.load()
+    info = _lib.JpegInfo()
+    rc = L.rgbnm_jpeg_info_from_memory(buf, len(buf), C.byref(info))
+    if rc != 0:
+        raise RuntimeError(L.rgbnm_strerror(rc).decode())
+    return info
+
+
+def read_coefficients_from_bytes(buf: bytes, return_clamp_flag: bool = False):
+    L = _lib.load()
+    info = _info(buf)
+    hb, wb = info.hb[0], info.wb[0]
+    y = torch.empty((1, hb, wb, 8, 8), dtype=torch.int16)
+    quant = torch.empty((info.ncomp, 8, 8), dtype=torch.int16)
+    dims = torch.empty((info.ncomp, 2), dtype=torch.int32)
+    cbcr = None
+    c_ptr, c_cap = None, 0
+    if info.ncomp > 1:
+        cbcr = torch.empty((2, info.hb[1], info.wb[1], 8, 8), dtype=torch.int16)
+        c_ptr, c_cap = cbcr.data_ptr(), cbcr.numel()
+    flag = C.c_int32(1)
+    rc = L.rgbnm_jpeg_read_coefficients(buf, len(buf), y.data_ptr(), y.numel(), c_ptr, c_cap,
+                                        quant.data_ptr(), dims.data_ptr(), C.addressof(flag))
+    if rc != 0:
+        raise RuntimeError(L.rgbnm_strerror(rc).decode())
+    if return_clamp_flag:
+        return dims, quant, y, cbcr, bool(flag.value)
+    return dims, quant, y, cbcr
+
+
+def read_coefficients(path: str):
+    """dct_manip.read_coefficients(path) -> (dimensions, quantization, Y, CbCr|None)."""
+    try:
+        with open(path, "rb") as f:
+            buf = f.read()
+    except OSError:
+        raise RuntimeError(f"Unable to open file for reading: {path}")
+    return read_coefficients_from_bytes(buf)
+
+
+def decode_batch(jpegs: Sequence[bytes], hb: int = 64, wb: int = 64, nthreads: int = 0, pin: bool = False):
+    """Multithreaded batch decode into the layout the fused kernel reads.
+    Returns (y [n,hb,wb,64], cbcr [n,2,hb/2,wb/2,64], quant [n,3,64], clamp_flags uint8 [n])."""
+    L = _lib.load()
+    n = len(jpegs)
+    pin = pin and torch.cuda.is_available()
+    y = torch.empty((n, hb, wb, 64), dtype=torch.int16, pin_memory=pin)
+    c = torch.empty((n, 2, hb // 2, wb // 2, 64), dtype=torch.int16, pin_memory=pin)
+    q = torch.empty((n, 3, 64), dtype=torch.int16, pin_memory=pin)
+    flags = torch.empty((n,), dtype=torch.uint8)
+    status = torch.zeros((n,), dtype=torch.int32)
+    ptrs = (C.c_char_p * n)(*jpegs)
+    sizes = (C.c_size_t * n)(*[len(j) for j in jpegs])
+    rc = L.rgbnm_jpeg_decode_batch(C.cast(ptrs, C.c_void_p), C.cast(sizes, C.c_void_p), n, hb, wb, y.data_ptr(),
+                                   c.data_ptr(), q.data_ptr(), flags.data_ptr(), status.data_ptr(), nthreads)
+    if rc != 0:
+        bad = int(torch.nonzero(status)[0]) if status.any() else -1
+        raise RuntimeError(f"image {bad}: {L.rgbnm_strerror(rc).decode()}")
+    return y, c, q, flags
+
+
+def write_coefficients(width: int, height: int, y: torch.Tensor, cbcr: Optional[torch.Tensor],
+                       quant: torch.Tensor, chroma: Tuple[int, int] = (2, 2)) -> bytes:
+    """Baseline JPEG bytes from quantised coefficient planes (fixture writer)."""
+    L = _lib.load()
+    out = C.c_void_p()
+    size = C.c_size_t()
+    ncomp = 1 if cbcr is None else 3
+    y = y.contiguous()
+    quant = quant.contiguous()
+    cb = cbcr.contiguous() if cbcr is not None else None
+    rc = L.rgbnm_jpeg_write_coefficients(width, height, ncomp, chroma[0], chroma[1], y.data_ptr(),
+                                         cb.data_ptr() if cb is not None else None, quant.data_ptr(),
+                                         C.byref(out), C.byref(size))
+    if rc != 0:
+        raise RuntimeError(L.rgbnm_strerror(rc).decode())
+    data = C.string_at(out, size.value)
+    L.rgbnm_free(out)
+    return data

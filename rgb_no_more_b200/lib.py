@@ -1,0 +1,77 @@
+"""ctypes binding of librgbnm_b200.so (the C-ABI declared in include/rgbnm_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing, or a CUDA
+entry point is called without a GPU, the call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librgbnm_b200.so")
+_lib = None
+
+
+class RgbnmError(RuntimeError):
+    pass
+
+
+class JpegInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("ncomp", C.c_int32), ("progressive", C.c_int32),
+                ("hb", C.c_int32 * 3), ("wb", C.c_int32 * 3), ("dsh", C.c_int32 * 3), ("dsw", C.c_int32 * 3),
+                ("hsamp", C.c_int32 * 3), ("vsamp", C.c_int32 * 3)]
+
+
+class K0Tables(C.Structure):
+    _fields_ = [("filters", C.c_void_p), ("posterize_lut", C.c_void_p), ("up_mats", C.c_void_p),
+                ("a16", C.c_void_p)]
+
+
+# name -> (restype, argtypes); must list every symbol include/rgbnm_b200.h declares.
+_vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
+SIGNATURES = {
+    "rgbnm_strerror": (C.c_char_p, [_i]),
+    "rgbnm_last_cuda_error": (C.c_char_p, []),
+    "rgbnm_abi_version": (_i, []),
+    "rgbnm_jpeg_info_from_memory": (_i, [_vp, _sz, C.POINTER(JpegInfo)]),
+    "rgbnm_jpeg_read_coefficients": (_i, [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp]),
+    "rgbnm_jpeg_decode_batch": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i]),
+    "rgbnm_jpeg_read_file": (_i, [C.c_char_p, C.POINTER(_vp), C.POINTER(_sz)]),
+    "rgbnm_free": (None, [_vp]),
+    "rgbnm_jpeg_write_coefficients": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_sz)]),
+    "rgbnm_k0_dcstats": (_i, [_vp, _vp, _vp, _vp, C.POINTER(K0Tables), _vp, _i, _i, _i, _vp]),
+    "rgbnm_k0_fused": (_i, [_vp, _vp, _vp, _vp, C.POINTER(K0Tables), _vp, _vp, _i, _i, _i, _i, _vp]),
+    "rgbnm_k0_launch_count": (_i, []),
+}
+
+
+def load():
+    """Load the shared library (once) and type every entry point."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RgbnmError(f"{LIB_PATH} is missing: run `python __graft_entry__.py` (build()) first; "
+                         "there is no CPU fallback for the B200 path")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        lib = load()
+        msg = lib.rgbnm_strerror(rc).decode()
+        if rc == 7:
+            msg += ": " + lib.rgbnm_last_cuda_error().decode()
+        raise RgbnmError(f"{what}: {msg}" if what else msg)
+
+
+def stream_ptr():
+    """Raw cudaStream_t of torch's current stream."""
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,406 @@
+"""Host-side augmentation-plan sampler for the fused DCT kernel (K0).
+
+The reference draws every random augmentation parameter on the CPU, inside the
+transform modules, from the torch *global* CPU generator.  The B200 path keeps
+exactly that contract: this module replays the reference's RNG call sequence
+(SURVEY.md section 8a "RNG contract") and resolves every draw into a fixed-size
+per-image POD record -- the *plan*.  The CUDA kernel is then a pure function of
+(quantised coefficients, quantisation tables, plan).
+
+Reference call sites mirrored here (file:line in /root/reference):
+  * RandomResizedCrop_DCT.get_params          utils/custom_transforms.py:557-629
+  * ResizedCenterCrop_DCT.get_params          utils/custom_transforms.py:850-882
+  * RandomFlip_DCT.forward                    utils/custom_transforms.py:926-942
+  * RandAugment_dct.forward / _augmentation_space   :1066-1127
+  * _apply_op_dct (parameter resolution only) :944-1021
+  * cutout_dct centre draws                   utils/dct_ops.py:791-799
+  * filters of sharpblur_dct / midfreqaug_dct utils/dct_ops.py:696-698,728-737
+  * posterize_dct quantisation table          utils/dct_ops.py:903-912
+
+Nothing here touches the oracle; the module is product code and is covered by
+CPU tests against golden plans dumped from the reference itself.
+"""
+from __future__ import annotations
+
+import itertools
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+# --------------------------------------------------------------------------
+# Op codes shared with include/rgbnm_b200.h (enum rgbnm_op) -- keep in sync.
+# --------------------------------------------------------------------------
+OP_NOP = 0
+OP_TRANSLATE_X = 1
+OP_TRANSLATE_Y = 2
+OP_ROT90 = 3
+OP_CUTOUT = 4
+OP_BRIGHTNESS = 5
+OP_CONTRAST = 6
+OP_COLOR = 7
+OP_AUTOCONTRAST = 8
+OP_AUTOSATURATION = 9
+OP_POSTERIZE = 10
+OP_SHARPNESS = 11
+OP_MIDFREQ = 12
+OP_GRAYSCALE = 13
+OP_CHROMADROP = 14
+OP_SOLARIZE_ADD = 15
+OP_INVERT = 16
+
+OP_NAMES = {
+    "Identity": OP_NOP, "TranslateX": OP_TRANSLATE_X, "TranslateY": OP_TRANSLATE_Y,
+    "Rotate90": OP_ROT90, "Cutout": OP_CUTOUT, "Brightness": OP_BRIGHTNESS,
+    "Contrast": OP_CONTRAST, "Color": OP_COLOR, "AutoContrast": OP_AUTOCONTRAST,
+    "AutoSaturation": OP_AUTOSATURATION, "Posterize": OP_POSTERIZE,
+    "Sharpness": OP_SHARPNESS, "MidfreqAug": OP_MIDFREQ, "Grayscale": OP_GRAYSCALE,
+    "ChromaDrop": OP_CHROMADROP, "SolarizeAdd": OP_SOLARIZE_ADD, "Invert": OP_INVERT,
+}
+# Dispatchable in the reference but outside every default DCT AUGLIST
+# (utils/configs.py:29,93): arbitrary-angle DCT->DFT warps and histogram ops.
+UNSUPPORTED_OPS = ("Rotate", "ShearX", "ShearY", "Equalize", "Solarize", "FreqEnhance")
+
+MAX_OPS = 4          # plan slots per image (reference default num_ops = 2)
+N_FILTER_SLOTS = 48  # distinct 8x8 multiplicative filters per launch
+CLAMP_MIN = -1024
+CLAMP_MAX = 1016
+
+# Default DCT op lists (utils/configs.py:29 and :93).
+AUGLIST_VITS = ("AutoContrast,Posterize,Color,Contrast,Brightness,Sharpness,Cutout,TranslateX,"
+                "TranslateY,Rotate90,AutoSaturation,Grayscale,MidfreqAug,ChromaDrop").split(",")
+AUGLIST_VITTI = ("AutoContrast,Posterize,SolarizeAdd,Color,Contrast,Brightness,MidfreqAug,Cutout,"
+                 "TranslateX,TranslateY,Rotate90,AutoSaturation,Grayscale,ChromaDrop").split(",")
+
+# numpy mirror of `struct rgbnm_plan` (include/rgbnm_b200.h); 96 bytes, 16-byte aligned.
+PLAN_OP_DTYPE = np.dtype([("code", np.int16), ("p", np.int16, (8,)), ("pad", np.int16),
+                          ("f", np.float32)], align=False)          # 2+16+2+4 = 24 B? -> see assert
+PLAN_DTYPE = np.dtype([
+    ("crop_i", np.int16), ("crop_j", np.int16), ("crop_size", np.int16),
+    ("flip", np.int16), ("n_ops", np.int16), ("clamp_in", np.int16),
+    ("needs_stats", np.int16), ("train", np.int16),
+    ("ops", PLAN_OP_DTYPE, (MAX_OPS,)),
+])
+assert PLAN_OP_DTYPE.itemsize == 24, PLAN_OP_DTYPE.itemsize
+assert PLAN_DTYPE.itemsize == 16 + 24 * MAX_OPS, PLAN_DTYPE.itemsize
+
+
+@dataclass
+class PlanOp:
+    code: int
+    p: List[int] = field(default_factory=lambda: [0] * 8)   # integer parameters
+    f: float = 0.0                                          # float parameter (fp32 exact)
+    name: str = ""
+
+
+@dataclass
+class Plan:
+    """Resolved per-image plan.  Crop geometry is in Y blocks; chroma uses //2."""
+    crop_i: int
+    crop_j: int
+    crop_size: int
+    flip: bool = False
+    train: bool = False          # RandAugment stage present -> entry clamp applies
+    ops: List[PlanOp] = field(default_factory=list)
+
+    @property
+    def needs_stats(self) -> bool:
+        return any(o.code in (OP_BRIGHTNESS, OP_AUTOCONTRAST, OP_AUTOSATURATION) for o in self.ops)
+
+
+# --------------------------------------------------------------------------
+# Filter / LUT tables (computed with the reference's own torch/scipy calls so
+# that the constants are bit-identical).
+# --------------------------------------------------------------------------
+class FilterBank:
+    """De-duplicating store of 8x8 multiplicative filters used by Sharpness and
+    MidfreqAug.  Slot 0 is the all-ones filter."""
+
+    def __init__(self, slots: int = N_FILTER_SLOTS):
+        self.table = np.ones((slots, 8, 8), dtype=np.float32)
+        self._index = {}
+        self._n = 1
+
+    def _put(self, key, mat: torch.Tensor) -> int:
+        if key in self._index:
+            return self._index[key]
+        if self._n >= self.table.shape[0]:
+            raise RuntimeError("rgbnm: FilterBank full (too many distinct filter magnitudes)")
+        self.table[self._n] = mat.numpy()
+        self._index[key] = self._n
+        self._n += 1
+        return self._index[key]
+
+    def sharpness(self, intensity: float) -> int:
+        # dct_ops.py:696-698 -- outer product of two clamped linspace ramps.
+        f_h = torch.linspace(1, (1 + 2 * intensity), 8, dtype=torch.float32).unsqueeze(1).clamp(min=0)
+        f_w = torch.linspace(1, (1 + 2 * intensity), 8, dtype=torch.float32).unsqueeze(0).clamp(min=0)
+        return self._put(("sharp", float(intensity)), f_h.mm(f_w))
+
+    def midfreq(self, intensity: float) -> int:
+        # dct_ops.py:725-741 -- gaussian window applied in block-shifted coordinates;
+        # blockshift(x)[i] = x[(i-4) % 8], so in unshifted coordinates the filter is
+        # F[(i+4)%8][(j+4)%8].
+        import scipy.signal
+        sig = 8 // 2 - (8 // 8 * 2.2) * abs(intensity)
+        f_h = torch.tensor(scipy.signal.windows.gaussian(8, sig), dtype=torch.float32).unsqueeze(1)
+        f_w = torch.tensor(scipy.signal.windows.gaussian(8, sig), dtype=torch.float32).unsqueeze(0)
+        mat = f_h.mm(f_w)
+        if intensity >= 0:
+            mat = 1 / mat
+        mat = torch.roll(mat, shifts=(4, 4), dims=(0, 1))
+        return self._put(("mid", float(intensity)), mat)
+
+
+def posterize_lut() -> np.ndarray:
+    """int16 LUT [6][2048]: DC value (index = dc + 1024) -> posterised DC, for
+    bit offsets 0..5 (dct_ops.py:903-912, evaluated with the same torch ops)."""
+    lut = np.zeros((6, 2048), dtype=np.int16)
+    dc = torch.arange(CLAMP_MIN, CLAMP_MAX + 1, dtype=torch.int16).to(torch.float32)
+    for b in range(6):
+        x = dc - CLAMP_MIN
+        x = x / 2 ** b
+        idx = torch.round(x).to(torch.int64)
+        table = torch.linspace(CLAMP_MIN, CLAMP_MAX, round((CLAMP_MAX - CLAMP_MIN) / (2 ** b)) + 1)
+        out = torch.round(table[idx]).to(torch.int16)
+        lut[b, : out.numel()] = out.numpy()
+    return lut
+
+
+# --------------------------------------------------------------------------
+# Crop geometry
+# --------------------------------------------------------------------------
+def _factors(n: int) -> List[int]:
+    return list(itertools.chain.from_iterable((i, n // i) for i in range(1, int(n ** 0.5) + 1) if n % i == 0))
+
+
+def _even_choices(size: int) -> torch.Tensor:
+    choices, _ = torch.tensor(_factors(size)).sort()
+    even, _ = torch.tensor([c for c in choices if c % 2 == 0]).sort()
+    return even
+
+
+def _choose_closest(val, choices: torch.Tensor, maxval: int):
+    # custom_transforms.py:571-578 / :860-867
+    if val <= choices[-1]:
+        closest = choices[torch.argmin(torch.abs(choices - val))]
+    else:
+        closest = torch.round(val / choices[-1]).item() * choices[-1]
+        if closest > maxval:
+            closest -= choices[-1]
+    return closest
+
+
+def eval_crop(height: int, width: int, size_resize: int = 32, size_crop: int = 28) -> Tuple[int, int, int, int]:
+    """ResizedCenterCrop_DCT.get_params for the luma plane (custom_transforms.py:850-882)."""
+    choices = _even_choices(size_crop)
+    ratio = size_crop / size_resize
+    w = round(ratio * width)
+    h = round(ratio * height)
+    w = _choose_closest(w, choices, width)
+    h = _choose_closest(h, choices, height)
+    i = int(torch.div((height - h), 2, rounding_mode="floor"))
+    j = int(torch.div((width - w), 2, rounding_mode="floor"))
+    i = i // 2 * 2
+    j = j // 2 * 2
+    return i, j, int(max(1, h)), int(max(1, w))
+
+
+def train_crop(height: int, width: int, size: int = 28, scale=(0.05, 1.0)) -> Tuple[int, int, int, int]:
+    """RandomResizedCrop_DCT.get_params with ratio=(1,1) (custom_transforms.py:580-629).
+    Issues the same torch global-RNG calls in the same order."""
+    choices = _even_choices(size)
+    area = height * width
+    for _ in range(10):
+        target_area = area * torch.empty(1).uniform_(scale[0], scale[1]).item()
+        w = int(round(math.sqrt(target_area)))
+        w = _choose_closest(w, choices, width)
+        h = w
+        w = int(max(2, w))
+        h = int(max(2, h))
+        if w <= width and h <= height:
+            i = int(torch.randint(0, height - h + 1, size=(1,)).item() // 2 * 2)
+            j = int(torch.randint(0, width - w + 1, size=(1,)).item() // 2 * 2)
+            return i, j, h, w
+    # central-crop fallback (:612-629); ratio == (1, 1)
+    in_ratio = float(width) / float(height)
+    if in_ratio < 1:
+        w = width
+        h = int(round(w / 1))
+    elif in_ratio > 1:
+        h = height
+        w = int(round(h * 1))
+    else:
+        w, h = width, height
+    h = _choose_closest(h, choices, height)
+    w = _choose_closest(w, choices, width)
+    i = int(torch.div((height - h), 2, rounding_mode="floor").div(2, rounding_mode="floor") * 2)
+    j = int(torch.div((width - w), 2, rounding_mode="floor").div(2, rounding_mode="floor") * 2)
+    return i, j, int(max(1, h)), int(max(1, w))
+
+
+# --------------------------------------------------------------------------
+# RandAugment parameter resolution
+# --------------------------------------------------------------------------
+def _augmentation_space(num_bins: int, image_size: Tuple[int, int]):
+    # custom_transforms.py:1066-1092 (only magnitudes + signedness are needed)
+    return {
+        "Identity": (torch.tensor(0.0), False),
+        "AutoContrast": (torch.tensor(0.0), False),
+        "Equalize": (torch.tensor(0.0), False),
+        "Invert": (torch.tensor(0.0), False),
+        "Rotate": (torch.linspace(0.0, 30.0, num_bins), True),
+        "Posterize": (torch.linspace(0.0, 5.0, num_bins).round().int(), False),
+        "Solarize": (torch.linspace(818, -818, num_bins), False),
+        "SolarizeAdd": (torch.linspace(0, 883, num_bins), False),
+        "Color": (torch.linspace(0.0, 0.9, num_bins), True),
+        "Contrast": (torch.linspace(0.0, 0.9, num_bins), True),
+        "Brightness": (torch.linspace(0.0, 0.9, num_bins), True),
+        "Sharpness": (torch.linspace(0.0, 0.9, num_bins), True),
+        "ShearX": (torch.linspace(0.0, 17.0, num_bins), True),
+        "ShearY": (torch.linspace(0.0, 17.0, num_bins), True),
+        "Cutout": (torch.linspace(0, 6, num_bins), False),
+        "TranslateX": (torch.linspace(0.0, 150.0 / 336.0 * image_size[1], num_bins), True),
+        "TranslateY": (torch.linspace(0.0, 150.0 / 336.0 * image_size[0], num_bins), True),
+        "Rotate90": (torch.tensor(1), True),
+        "AutoSaturation": (torch.tensor(0.0), False),
+        "Grayscale": (torch.tensor(0.0), False),
+        "MidfreqAug": (torch.linspace(0.0, 0.9, num_bins), True),
+        "FreqEnhance": (torch.linspace(0.0, 0.9, num_bins), True),
+        "ChromaDrop": (torch.tensor(0.0), False),
+    }
+
+
+def cutout_rect(size: int, centre_h: int, centre_w: int, H: int, W: int) -> Tuple[int, int, int, int]:
+    """Zeroed block rectangle rows [r0, r1) x cols [c0, c1) of cutout_dct
+    (dct_ops.py:796-807).  Note the rows are mirrored about the image: the mask is
+    built with F.pad((left, right, upper, lower)) where `upper` = H - centre - pad."""
+    lower_pad = max(0, centre_h - size)
+    upper_pad = max(0, H - centre_h - size)
+    left_pad = max(0, centre_w - size)
+    right_pad = max(0, W - centre_w - size)
+    return upper_pad, H - lower_pad, left_pad, W - right_pad
+
+
+def resolve_op(op_name: str, magnitude: float, grid: int, bank: FilterBank) -> PlanOp:
+    """Turn (op name, signed magnitude) into a resolved PlanOp, drawing the
+    op-internal random numbers exactly where _apply_op_dct would
+    (custom_transforms.py:944-1021)."""
+    if op_name in UNSUPPORTED_OPS:
+        raise NotImplementedError(
+            f"rgbnm: DCT op '{op_name}' is outside the B200 hot path (SURVEY.md 8a row a21); "
+            f"it is not in any default DCT AUGLIST")
+    if op_name not in OP_NAMES:
+        raise ValueError(f"The provided operator {op_name} is not recognized.")
+    code = OP_NAMES[op_name]
+    op = PlanOp(code=code, name=op_name)
+    H = W = grid
+    if code in (OP_TRANSLATE_X, OP_TRANSLATE_Y):
+        t = int(magnitude - (magnitude % 2))           # python float %, :958
+        op.p[0] = t
+        op.p[1] = t // 2
+    elif code == OP_ROT90:
+        # rotate_dct_90deg(rotate=magnitude), magnitude = +-1 (dct_ops.py:111-128)
+        op.p[0] = 1 if magnitude > 0 else -1
+    elif code == OP_CUTOUT:
+        size = round(magnitude)
+        size = int(size - (size % 2))
+        ch = (torch.randint(low=0, high=H, size=(1,)).item()) // 2 * 2
+        cw = (torch.randint(low=0, high=W, size=(1,)).item()) // 2 * 2
+        op.p[0:4] = list(cutout_rect(size, ch, cw, H, W))
+        op.p[4:8] = list(cutout_rect(size // 2, ch // 2, cw // 2, H // 2, W // 2))
+    elif code == OP_BRIGHTNESS:
+        # coeff_dc += mean(|dc|) * ((1 + m) - 1)   (dct_ops.py:832); (1+m)-1 == m in double
+        op.f = float(np.float32((1.0 + magnitude) - 1.0))
+    elif code in (OP_CONTRAST, OP_COLOR):
+        op.f = float(np.float32(1.0 + magnitude))     # fp32 scalar multiply (dct_ops.py:856)
+    elif code == OP_POSTERIZE:
+        op.p[0] = int(magnitude)
+    elif code == OP_SHARPNESS:
+        op.p[0] = bank.sharpness(magnitude)
+    elif code == OP_MIDFREQ:
+        op.p[0] = bank.midfreq(magnitude)
+    elif code == OP_CHROMADROP:
+        op.p[0] = 0 if torch.rand(1).item() > 0.5 else 1   # >0.5 drops Cb, else Cr (:1012-1015)
+    elif code == OP_SOLARIZE_ADD:
+        op.p[0] = int(magnitude)
+    return op
+
+
+def sample_randaugment(ops_list: Sequence[str], num_ops: int, magnitude_bin: int, grid: int,
+                       bank: FilterBank, num_bins: int = 11) -> List[PlanOp]:
+    """RandAugment_dct.forward's draw sequence (custom_transforms.py:1109-1124)."""
+    if len(ops_list) == 0:
+        return []
+    ops_list = list(ops_list).copy()
+    op_meta = _augmentation_space(num_bins, (grid, grid))
+    chromas = {"Grayscale", "Color", "AutoSaturation", "ChromaDrop"}
+    out: List[PlanOp] = []
+    for _ in range(num_ops):
+        op_index = int(torch.randint(len(ops_list), (1,)).item())
+        op_name = ops_list[op_index]
+        if op_name in chromas:
+            # NB: list(set(..)) ordering is hash dependent, exactly as in the reference.
+            if op_name == "Grayscale":
+                ops_list = list(set(ops_list).difference(chromas))
+            else:
+                ops_list = list(set(ops_list).difference({"Grayscale"}))
+        magnitudes, signed = op_meta[op_name]
+        magnitude = float(magnitudes[magnitude_bin].item()) if magnitudes.ndim > 0 else magnitudes.item()
+        if signed and torch.randint(2, (1,)):
+            magnitude *= -1.0
+        out.append(resolve_op(op_name, magnitude, grid, bank))
+    return out
+
+
+def sample_train_plan(height: int, width: int, ops_list: Optional[Sequence[str]], num_ops: int,
+                      magnitude_bin: int, bank: FilterBank, size: int = 28) -> Plan:
+    """One image's worth of `get_transform('imagenet_dct','train')` draws
+    (datasets.py:355-361): RandomResizedCrop_DCT -> RandomFlip_DCT -> RandAugment_dct."""
+    if len(ops_list if ops_list is not None else AUGLIST_VITS) > 0 and num_ops > MAX_OPS:
+        raise ValueError(f"rgbnm: num_ops={num_ops} exceeds plan capacity {MAX_OPS}")
+    i, j, h, w = train_crop(height, width, size)
+    if h != w:
+        raise NotImplementedError("rgbnm: non-square DCT crops are outside the hot path")
+    flip = not (torch.rand(1) > 0.5)                  # custom_transforms.py:934
+    if ops_list is None:
+        ops_list = ["AutoContrast", "Equalize", "Invert", "Rotate", "Posterize", "Solarize", "SolarizeAdd",
+                    "Color", "Contrast", "Brightness", "Sharpness", "ShearX", "ShearY", "Cutout",
+                    "TranslateX", "TranslateY"]
+    ops = sample_randaugment(ops_list, num_ops, magnitude_bin, size, bank)
+    return Plan(crop_i=i, crop_j=j, crop_size=h, flip=bool(flip), train=len(ops_list) > 0, ops=ops)
+
+
+def eval_plan(height: int, width: int, size_resize: int = 32, size_crop: int = 28) -> Plan:
+    """`get_transform('imagenet_dct','test')` (datasets.py:362-366): deterministic."""
+    i, j, h, w = eval_crop(height, width, size_resize, size_crop)
+    if h != w:
+        raise NotImplementedError("rgbnm: non-square DCT crops are outside the hot path")
+    return Plan(crop_i=i, crop_j=j, crop_size=h, flip=False, train=False, ops=[])
+
+
+SUPPORTED_CROPS = {28: (2, 4, 14, 28, 56)}
+
+
+def pack_plans(plans: Sequence[Plan], clamp_in: Optional[Sequence[bool]] = None, out_size: int = 28) -> np.ndarray:
+    """Pack plans into the `struct rgbnm_plan` array the C-ABI takes."""
+    arr = np.zeros(len(plans), dtype=PLAN_DTYPE)
+    for n, pl in enumerate(plans):
+        if pl.crop_size not in SUPPORTED_CROPS[out_size]:
+            raise ValueError(f"rgbnm: unsupported crop size {pl.crop_size} -> {out_size} blocks")
+        if len(pl.ops) > MAX_OPS:
+            raise ValueError("rgbnm: too many ops in plan")
+        a = arr[n]
+        a["crop_i"], a["crop_j"], a["crop_size"] = pl.crop_i, pl.crop_j, pl.crop_size
+        a["flip"] = int(pl.flip)
+        a["n_ops"] = len(pl.ops)
+        a["clamp_in"] = 1 if clamp_in is None else int(bool(clamp_in[n]))
+        a["needs_stats"] = int(pl.needs_stats)
+        a["train"] = int(pl.train)
+        for k, op in enumerate(pl.ops):
+            a["ops"][k]["code"] = op.code
+            a["ops"][k]["p"][:] = op.p
+            a["ops"][k]["f"] = op.f
+    return arr

@@ -1,0 +1,51 @@
+"""Shared test helpers: golden loading and plan (de)serialisation."""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+from rgb_no_more_b200 import plan as P  # noqa: E402
+
+CODE_TO_NAME = {v: k for k, v in P.OP_NAMES.items()}
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def unpack_plans(arr):
+    """numpy PLAN_DTYPE array -> list[Plan] (names restored from op codes)."""
+    out = []
+    for a in arr:
+        ops = []
+        for k in range(int(a["n_ops"])):
+            o = a["ops"][k]
+            ops.append(P.PlanOp(code=int(o["code"]), p=[int(v) for v in o["p"]], f=float(o["f"]),
+                                name=CODE_TO_NAME[int(o["code"])]))
+        out.append(P.Plan(crop_i=int(a["crop_i"]), crop_j=int(a["crop_j"]), crop_size=int(a["crop_size"]),
+                          flip=bool(a["flip"]), train=bool(a["train"]), ops=ops))
+    return out
+
+
+def lsb_report(a, b):
+    """(max |diff|, fraction of entries that differ) for two integer arrays."""
+    d = np.abs(a.astype(np.int64) - b.astype(np.int64))
+    return int(d.max()), float((d != 0).mean())
+
+
+def reference_available():
+    return os.path.isdir("/root/reference/utils")
+
+
+def import_reference():
+    if "/root/reference" not in sys.path:
+        sys.path.insert(1, "/root/reference")
+    sys.modules.setdefault("dct_manip", types.ModuleType("dct_manip"))
+    import utils.custom_transforms as ctrans
+    import utils.dct_ops as dops
+    return ctrans, dops

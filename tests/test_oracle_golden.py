@@ -1,0 +1,97 @@
+"""Pin the CPU oracle (oracle/dct_oracle.py) against vectors produced by the reference
+itself (tools/make_golden.py).  CPU-only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dct_oracle as O
+from rgb_no_more_b200 import plan as P
+from tests.helpers import load, unpack_plans, lsb_report
+
+torch.set_num_threads(1)
+
+
+def test_conversion_matrices_bit_equal():
+    g = load("resize.npz")
+    assert np.array_equal(O.conversion_matrix(2).numpy(), g["A16"])
+    assert np.array_equal(O.conversion_matrix(7).numpy(), g["A7"])
+    A = O.conversion_matrix(2)
+    assert float((A @ A.T - torch.eye(16)).abs().max()) < 2e-6          # orthonormal
+    # even rows are 2-sparse up to fp32 noise: A16[2m] = (e_m | (-1)^m e_m)/sqrt(2)
+    for m in range(8):
+        row = A[2 * m].clone()
+        assert abs(float(row[m]) - 2 ** -0.5) < 1e-6 and abs(float(row[8 + m]) - (-1) ** m * 2 ** -0.5) < 1e-6
+        row[m] = 0
+        row[8 + m] = 0
+        assert float(row.abs().max()) < 3e-6
+
+
+@pytest.mark.parametrize("side", [2, 4, 14, 28, 56])
+def test_resize_matches_reference(side):
+    g = load("resize.npz")
+    out = O.resize_blocks(torch.from_numpy(g[f"in_{side}"]), 28).numpy()
+    mx, frac = lsb_report(out, g[f"out_{side}"])
+    assert mx <= 1 and frac < 2e-3, (mx, frac)
+    outc = O.resize_blocks(torch.from_numpy(g[f"cin_{side}"]), 14).numpy()
+    mx, frac = lsb_report(outc, g[f"cout_{side}"])
+    assert mx <= 1 and frac < 2e-3, (mx, frac)
+
+
+def _resolve(name, mag, seed, bank):
+    if seed is not None:
+        torch.manual_seed(seed)
+    return P.resolve_op(name, mag, 8, bank)
+
+
+def test_every_op_bit_exact_on_small_grid():
+    g = load("ops_small.npz")
+    y, c = torch.from_numpy(g["y"]), torch.from_numpy(g["c"])
+    bank = P.FilterBank()
+    for k, (name, mag) in enumerate(zip(g["case_names"], g["case_mags"])):
+        name = str(name)
+        key = f"{name}_{k}"
+        seed = int(g[key + "_seed"]) if key + "_seed" in g.files else None
+        op = _resolve(name, float(mag), seed, bank)
+        oy, oc = O.apply_op(y.clone(), c.clone(), op, bank.table)
+        assert np.array_equal(oy.numpy(), g[key + "_y"]), (name, mag)
+        assert np.array_equal(oc.numpy(), g[key + "_c"]), (name, mag)
+
+
+def test_full_pipeline_matches_reference():
+    g = load("pipeline.npz")
+    plans = unpack_plans(g["plans"])
+    filters = g["filters"]
+    worst = 0.0
+    for k, (img, seed, mag) in enumerate(g["cases"]):
+        yq = torch.from_numpy(g[f"img{img}_y"])
+        cq = torch.from_numpy(g[f"img{img}_c"])
+        q = torch.from_numpy(g[f"img{img}_q"])
+        oy, oc = O.transform_int16(yq, cq, q, plans[k], filters)
+        my, fy = lsb_report(oy.numpy(), g[f"case{k}_y"])
+        mc, fc = lsb_report(oc.numpy(), g[f"case{k}_c"])
+        # same machine + same torch ops => identical; allow resize ties on other CPUs
+        assert my <= 1 and mc <= 1, (k, my, mc)
+        assert fy < 5e-3 and fc < 5e-3, (k, fy, fc)
+        worst = max(worst, fy, fc)
+    print("worst mismatch fraction", worst)
+
+
+def test_to_range_formula():
+    x = torch.arange(-1100, 1100, dtype=torch.int16)
+    z = O.to_range(x)
+    assert z.dtype == torch.float32
+    assert float(z[x == -1024]) == -1.0 and float(z[x == 1016]) == 1.0
+    ref = -1 + 2 * ((x.double() + 1024) / 2040)
+    assert float((z.double() - ref).abs().max()) < 2e-7
+
+
+def test_embed_input_bit_exact_permutation():
+    g = load("embed_vit.npz")
+    gen = torch.Generator().manual_seed(int(g["input_seed"]))
+    yf = torch.rand((2, 1, 28, 28, 8, 8), generator=gen) * 2 - 1
+    cf = torch.rand((2, 2, 14, 14, 8, 8), generator=gen) * 2 - 1
+    e = O.embed_input(yf, cf)[0].numpy()
+    ref = g["embed_in"]
+    # chroma part is a pure permutation -> bit exact; luma part goes through A16 X A16^T
+    assert np.array_equal(e[..., 256:], ref[..., 256:])
+    assert np.abs(e[..., :256] - ref[..., :256]).max() < 1e-5
