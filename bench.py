@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Benchmark of the DCT-domain ViT hot path on B200 (contract: see the task's bench section).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5            # our arm
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1   # reference CPU path (oracle port)
+    torchrun ... bench.py --gpus N ...                        # one rank per GPU, weak scaling
+
+A "step" is one pass of the hot path over one batch of 256 synthetic 512x512 4:2:0 images per
+GPU whose Huffman-decoded int16 coefficients are the input: fused DCT-aug+embed kernel (K0)
+-> ViT forward/backward/optimizer when `--stage train` (default once the model is built).
+`value` times the step with inputs resident in HBM; `e2e` includes the pinned-host -> device
+copy of the coefficients + plans and a device -> host read of the step result.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "images/sec (512x512 JPEG, ViT-S DCT) at 1/2/4/8 B200; DCT-aug+embed HBM GB/s"
+UNIT = "images/s"
+N_POOL = 4          # distinct input batches cycled through (4 x 201 MB >> 126 MB L2)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# Workload construction
+# ----------------------------------------------------------------------------------------------
+def build_inputs(batch: int, rank: int, from_jpeg: int = 8):
+    """N_POOL synthetic coefficient batches in pinned host memory.  The first `from_jpeg` images of
+    batch 0 are real PIL-encoded JPEGs run through our Huffman decoder; the rest use the
+    JPEG-statistics generator (encoding 1024 JPEGs with PIL would take minutes of setup)."""
+    from rgb_no_more_b200 import dct_manip as dm, synth
+    pool = []
+    for k in range(N_POOL):
+        y, c, q = synth.synth_coefficients(batch, 64, 64, seed=synth.SEED + 1000 * rank + k)
+        y, c, q = torch.from_numpy(y), torch.from_numpy(c), torch.from_numpy(q)
+        if k == 0 and from_jpeg:
+            jy, jc, jq, _ = dm.decode_batch(synth.synth_jpeg_set(from_jpeg), 64, 64, nthreads=0)
+            y[:from_jpeg], c[:from_jpeg], q[:from_jpeg] = jy, jc, jq
+        pool.append(tuple(t.pin_memory() for t in (y, c, q)))
+    return pool
+
+
+def algorithmic_bytes(plans, out_bytes: int) -> int:
+    """int16 coefficients inside the crop window + 384 B tables + plan, + output."""
+    total = 0
+    for pl in plans:
+        s = pl.crop_size
+        total += s * s * 128 + 2 * (s // 2) * (s // 2) * 128 + 384 + 112 + 196 * 384 * out_bytes
+    return total
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from rgb_no_more_b200 import plan as P, transforms as TF
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    out_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    tf = TF.FusedDCT(dev, "train", P.AUGLIST_VITS, 2, 9, out_dtype=out_dtype)
+    tf_eval = TF.FusedDCT(dev, "test", out_dtype=out_dtype)
+    host_pool = build_inputs(B, rank)
+    torch.manual_seed(11997733 + rank)
+    plan_pool = [tf.sample_plans(B) for _ in range(N_POOL)]
+    packed_pool = [torch.from_numpy(P.pack_plans(p).view(np.uint8).reshape(B, -1).copy()).pin_memory() for p in plan_pool]
+    dev_pool = [tuple(t.to(dev) for t in hp) for hp in host_pool]
+    dev_plans = [p.to(dev) for p in packed_pool]
+    stage = None
+    if args.stage == "train":
+        from rgb_no_more_b200 import train_step as TS
+        stage = TS.TrainStage(dev, arch=args.arch, batch=B, dtype=args.dtype, world=world)
+    out_buf = torch.empty((B, 196, 384), dtype=out_dtype, device=dev)
+    labels_pool = [torch.randint(0, 1000, (B,), device=dev) for _ in range(N_POOL)]
+
+    k0_ms = []
+
+    def step_device(i, timed=False):
+        k = i % N_POOL
+        y, c, q = dev_pool[k]
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        x = tf.run(y, c, q, None, plans_dev=dev_plans[k], out=out_buf)
+        if timed:
+            e1.record()
+            k0_ms.append((e0, e1))
+        if stage is not None:
+            return stage.step(x, labels_pool[k])
+        return x
+
+    h2d_stream = torch.cuda.Stream(device=dev)
+    stage_bufs = [tuple(torch.empty_like(t, device=dev) for t in host_pool[0]) for _ in range(2)]
+    stage_plans = [torch.empty_like(packed_pool[0], device=dev) for _ in range(2)]
+    result_host = torch.empty((1,), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        k = i % N_POOL
+        s = i % 2
+        for dst, src in zip(stage_bufs[s], host_pool[k]):
+            dst.copy_(src, non_blocking=True)
+        stage_plans[s].copy_(packed_pool[k], non_blocking=True)
+        x = tf.run(*stage_bufs[s], None, plans_dev=stage_plans[s], out=out_buf)
+        if stage is not None:
+            res = stage.step(x, labels_pool[k])
+        else:
+            res = x[:, 0, :8].float().sum().reshape(1)     # a scalar that depends on the step's output
+        result_host.copy_(res.reshape(-1)[:1].float(), non_blocking=True)
+
+    def timed_loop(fn, steps, warmup, **kw):
+        for i in range(warmup):
+            fn(i, **kw) if kw else fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i, **kw) if kw else fn(warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed_loop(step_device, args.steps, args.warmup, timed=True)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed_loop(step_e2e, args.steps, args.warmup)
+
+    # K0 kernel(s) alone: average over the timed region (events on the launching stream)
+    k0_avg_ms = float(np.mean([a.elapsed_time(b) for a, b in k0_ms[-args.steps:]]))
+    out_bytes = 2 if out_dtype == torch.bfloat16 else 4
+    alg = float(np.mean([algorithmic_bytes(p, out_bytes) for p in plan_pool]))
+    pk, pk_src = peaks()
+    # canonical eval geometry side measurement
+    eplans = torch.from_numpy(P.pack_plans(tf_eval.sample_plans(B)).view(np.uint8).reshape(B, -1).copy()).to(dev)
+
+    def step_eval(i):
+        y, c, q = dev_pool[i % N_POOL]
+        tf_eval.run(y, c, q, None, plans_dev=eplans, out=out_buf)
+    ms_eval = timed_loop(step_eval, max(args.steps, 20), max(args.warmup, 3)) / max(args.steps, 20)
+    alg_eval = algorithmic_bytes(tf_eval.sample_plans(B), out_bytes)
+
+    if rank != 0:
+        return
+    ms_step = ms_total / args.steps
+    value = B * world / (ms_step * 1e-3)
+    e2e_val = B * world / (ms_e2e / args.steps * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in host_pool[0]) + packed_pool[0].numel()
+    launches = 2 + (stage.launches_per_step if stage is not None else 0)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": (f"{args.arch} DCT train step (K0 fused DCT-aug+embed -> ViT fwd/bwd/AdamW)" if stage is not None
+                                else "K0 fused DCT-aug+embed only (ViT stage not built yet)") +
+                               f", batch {B}/GPU, 512x512 4:2:0 coefficients, RandAugment num_ops=2 magnitude=9",
+                   "l2_policy": f"{N_POOL} distinct input batches x 201 MB cycled (> 126 MB L2)", "batch_per_gpu": B},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
+        "gpu_launches": launches * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k0_dcstats + k0_fused (train mix)", "achieved": alg / (k0_avg_ms * 1e-3) / 1e9,
+                     "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s",
+                     "frac": alg / (k0_avg_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                     "algorithmic_bytes_per_launch": alg, "kernel_ms": k0_avg_ms},
+        "roofline_eval_geometry": {"bound": "hbm", "achieved": alg_eval / (ms_eval * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                                   "unit": "GB/s", "frac": alg_eval / (ms_eval * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                   "algorithmic_bytes_per_launch": alg_eval, "kernel_ms": ms_eval,
+                                   "images_per_s": B / (ms_eval * 1e-3)},
+    }
+    if world == 1:
+        line["cpu_baseline"] = cpu_baseline(args, sample_images=16, threads=1)
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs (oracle port of the reference path) -- the only place bench.py touches oracle/
+# ----------------------------------------------------------------------------------------------
+def _cpu_transform_worker(job):
+    from oracle import dct_oracle as O
+    torch.set_num_threads(1)
+    y, c, q, plan, filters = job
+    return O.transform_embed(y, c, q, plan, filters)
+
+
+_POOL = {}
+
+
+def _cpu_jobs(n_images: int):
+    from rgb_no_more_b200 import plan as P, synth
+    bank = P.FilterBank()
+    torch.manual_seed(11997733)
+    y, c, q = synth.synth_coefficients(n_images, 64, 64, seed=synth.SEED)
+    jobs = []
+    for b in range(n_images):
+        pl = P.sample_train_plan(64, 64, P.AUGLIST_VITS, 2, 9, bank)
+        jobs.append((torch.from_numpy(y[b]).reshape(1, 64, 64, 8, 8), torch.from_numpy(c[b]).reshape(2, 32, 32, 8, 8),
+                     torch.from_numpy(q[b]).reshape(3, 8, 8), pl, bank.table))
+    return jobs
+
+
+def _cpu_chunk(jobs):
+    torch.set_num_threads(1)
+    acc = 0.0
+    for j in jobs:
+        acc += float(_cpu_transform_worker(j)[0, 0])     # keep the result alive; return a scalar, like a loss
+    return acc
+
+
+def cpu_path_images_per_s(args, n_images: int, threads: int):
+    """Reference CPU data path (oracle restatement) on `n_images` images with `threads` persistent worker
+    processes (the reference's DataLoader-worker model, datasets.py:542-556, one torch thread each)."""
+    jobs = _cpu_jobs(n_images)
+    if threads <= 1:
+        _cpu_chunk(jobs[:2])
+        t0 = time.perf_counter()
+        _cpu_chunk(jobs)
+        return n_images / (time.perf_counter() - t0), None
+    import multiprocessing as mp
+    if threads not in _POOL:
+        _POOL[threads] = mp.get_context("fork").Pool(threads)
+    pool = _POOL[threads]
+    chunks = [jobs[i::threads] for i in range(threads)]
+    pool.map(_cpu_chunk, [ch[:1] for ch in chunks])         # warm the workers
+    t0 = time.perf_counter()
+    pool.map(_cpu_chunk, chunks)
+    return n_images / (time.perf_counter() - t0), None
+
+
+def cpu_baseline(args, sample_images: int, threads: int):
+    ips, _ = cpu_path_images_per_s(args, sample_images, threads)
+    return {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{sample_images} images of the same workload through oracle/dct_oracle.py "
+                      f"(dequant->crop->resize->flip->RandAugment->ToRange->embed input), {threads} thread(s)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = max(cores * 16, 64)
+    times = []
+    for s in range(args.warmup + args.steps):
+        ips, _ = cpu_path_images_per_s(args, n, cores)
+        if s >= args.warmup:
+            times.append(n / ips)
+    sec = float(np.mean(times))
+    val = n / sec
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"reference CPU data path (oracle port), bounded sample of {n} images/step of the same "
+                                   f"workload (batch {args.batch}, RandAugment num_ops=2 magnitude=9)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{n} images per step"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--arch", default="vits")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--stage", default="auto", choices=["auto", "k0", "train"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.stage == "auto":
+        args.stage = "train" if os.path.exists(os.path.join(ROOT, "rgb_no_more_b200", "train_step.py")) else "k0"
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        for pool in _POOL.values():
+            pool.close()
+            pool.join()
+        _POOL.clear()
+
+
+if __name__ == "__main__":
+    main()

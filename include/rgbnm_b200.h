@@ -116,8 +116,6 @@ typedef struct {
 typedef struct {
     const float* filters;        /* [RGBNM_FILTER_SLOTS][64] multiplicative 8x8 filters */
     const int16_t* posterize_lut;/* [6][2048] */
-    const float* up_mats;        /* [23][64]: upsample matrices P_l for factors 2, 7, 14 */
-    const float* a16;            /* [16][16] reference-exact conversion matrix (strict paths) */
 } rgbnm_k0_tables;
 
 #define RGBNM_K0_OUT_F32 0

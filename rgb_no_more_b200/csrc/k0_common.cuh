@@ -1,0 +1,180 @@
+// Device helpers shared by the fused DCT kernel (k0_fused.cu) and its DC-statistics
+// pre-pass (k0_dcstats.cu).  Both translation units must evaluate the *same* IEEE
+// operation sequences for a resized block's DC term, so the 1-D transforms live here and
+// the library is compiled with --fmad=false (FMA only where written as fmaf()).
+//
+// Math (reference utils/dct_ops.py:150-208, 436-527):
+//   A16 = D16 . blockdiag(D8, D8)^T is the orthonormal 16x16 "conversion matrix".
+//   Structure exploited here (verified in tests/test_k0_math.py):
+//     A16[k][8+j] = (-1)^(k+j) A16[k][j]                     (mirror symmetry)
+//     A16[2m][j]  = delta(j, m) / sqrt(2)                    (even rows are 2-sparse)
+//     A16[2m+1][j] = kB[m][j], a dense 8x8 block             (odd rows)
+//   so a 16-point product costs 8 mul + 64 fma + 16 add instead of 256 fma, and the
+//   8-output (downsample) form 4 mul + 32 fma + 12 add instead of 128.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rgbnm_b200.h"
+
+namespace k0 {
+
+constexpr float KE = 0.707106781f;
+constexpr float CLAMP_LO = -1024.0f;
+constexpr float CLAMP_HI = 1016.0f;
+constexpr int GRID_Y = 28;   // luma blocks per side after resize
+constexpr int GRID_C = 14;
+constexpr int TOKENS = 196;
+constexpr int FEAT = 384;
+constexpr int PLANE_ELEMS = (GRID_Y * GRID_Y + 2 * GRID_C * GRID_C) * 64;
+
+enum Mode { MODE_DOWN2 = 0, MODE_IDENT = 1, MODE_UP2 = 2, MODE_BAD = 3 };
+
+__device__ __forceinline__ int mode_of(int crop_size) {
+    return crop_size == 56 ? MODE_DOWN2 : crop_size == 28 ? MODE_IDENT : crop_size == 14 ? MODE_UP2 : MODE_BAD;
+}
+
+#define K0_KB_TABLE                                                                                               \
+    {                                                                                                             \
+        {0.637643577f, 0.298637845f, -0.0584927049f, 0.0240878632f, -0.0124921762f, 0.00706026221f,               \
+         -0.00392845722f, 0.00177477869f},                                                                        \
+        {-0.215305887f, 0.544633646f, 0.381218413f, -0.0950727443f, 0.0436403016f, -0.0234808956f,                \
+         0.0127634981f, -0.00570323591f},                                                                         \
+        {0.132584711f, -0.221907938f, 0.508053606f, 0.400770851f, -0.106061464f, 0.0493435375f, -0.0252556743f,   \
+         0.0109887194f},                                                                                          \
+        {-0.0985193279f, 0.150923057f, -0.202355499f, 0.497064887f, 0.406474087f, -0.107836242f, 0.0475687588f,   \
+         -0.0195524384f},                                                                                         \
+        {0.0808527229f, -0.119774931f, 0.139934337f, -0.196652263f, 0.495290108f, 0.404699308f, -0.102133006f,    \
+         0.0365800394f},                                                                                          \
+        {-0.0708680044f, 0.103354298f, -0.114071695f, 0.138159559f, -0.198427042f, 0.500993344f, 0.393710589f,    \
+         -0.0825805681f},                                                                                         \
+        {0.0653123269f, -0.094519257f, 0.101579519f, -0.115846474f, 0.143862794f, -0.209415762f, 0.520545782f,    \
+         0.357130549f},                                                                                           \
+        {-0.0628024108f, 0.0905907998f, -0.0962940357f, 0.107282755f, -0.126835194f, 0.163415233f,                \
+         -0.245995801f, 0.60312635f},                                                                             \
+    }
+
+// o[k] = SCALE * sum_j (A16[k][j] xl[j] + A16[k][8+j] xr[j]),  k = 0..7  (downsample-by-2 half)
+template <int SCALE_NUM, int SCALE_DEN>
+__device__ __forceinline__ void down2_1d(const float (&xl)[8], const float (&xr)[8], float (&o)[8]) {
+    constexpr float B[8][8] = K0_KB_TABLE;
+    constexpr float s = float(SCALE_NUM) / float(SCALE_DEN);
+    o[0] = (KE * s) * (xl[0] + xr[0]);
+    o[2] = (KE * s) * (xl[1] - xr[1]);
+    o[4] = (KE * s) * (xl[2] + xr[2]);
+    o[6] = (KE * s) * (xl[3] - xr[3]);
+    float u[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] = (j & 1) ? (xl[j] + xr[j]) : (xl[j] - xr[j]);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        float acc = (B[m][0] * s) * u[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) acc = fmaf(B[m][j] * s, u[j], acc);
+        o[2 * m + 1] = acc;
+    }
+}
+
+// o[k] = sum_j (A16[k][j] xl[j] + A16[k][8+j] xr[j]),  k = 0..15  (sub-block conversion)
+__device__ __forceinline__ void a16_1d(const float (&xl)[8], const float (&xr)[8], float (&o)[16]) {
+    constexpr float B[8][8] = K0_KB_TABLE;
+    float u[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float sm = xl[j] + xr[j], df = xl[j] - xr[j];
+        o[2 * j] = KE * ((j & 1) ? df : sm);
+        u[j] = (j & 1) ? sm : df;
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        float acc = B[m][0] * u[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) acc = fmaf(B[m][j], u[j], acc);
+        o[2 * m + 1] = acc;
+    }
+}
+
+// o[a] = SCALE * sum_b x[b] A16[b][8*child + a],  a = 0..7  (upsample-by-2, one child half)
+template <int SCALE>
+__device__ __forceinline__ void up2_1d(const float (&x)[8], int child, float (&o)[8]) {
+    constexpr float B[8][8] = K0_KB_TABLE;
+    constexpr float s = float(SCALE);
+    const float cs = child ? -1.0f : 1.0f;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        float w = (B[0][a] * s) * x[1];
+        w = fmaf(B[1][a] * s, x[3], w);
+        w = fmaf(B[2][a] * s, x[5], w);
+        w = fmaf(B[3][a] * s, x[7], w);
+        const float v = (a < 4) ? (KE * s) * x[2 * a] : 0.0f;
+        float r = fmaf(cs, w, v);
+        if (a & 1) r = child ? -r : r;
+        o[a] = r;
+    }
+}
+
+__device__ __forceinline__ float rint_magic(float x) {
+    // round-half-even for |x| < 2^22 (torch.round semantics), two full-rate FADDs
+    return (x + 12582912.0f) - 12582912.0f;
+}
+__device__ __forceinline__ float clampf(float x) { return fminf(fmaxf(x, CLAMP_LO), CLAMP_HI); }
+
+// dequantise 8 int16 packed in an int4 with the fp32 table row q[8]; optional clamp
+template <bool CLAMP>
+__device__ __forceinline__ void dequant8(const int4& raw, const float* __restrict__ q, float (&x)[8]) {
+    const int w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const float lo = float(int(short(w[p] & 0xffff)));
+        const float hi = float(w[p] >> 16);
+        x[2 * p] = lo * q[2 * p];
+        x[2 * p + 1] = hi * q[2 * p + 1];
+        if (CLAMP) {
+            x[2 * p] = clampf(x[2 * p]);
+            x[2 * p + 1] = clampf(x[2 * p + 1]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Geometry: where does the block at final-grid position (r, c) of plane `comp` come from?
+// Walks the op list backwards (RandAugment ops, then RandomFlip_DCT).  Returns the stage
+// after which the block is identically zero (-1: never) and the post-resize position.
+// ---------------------------------------------------------------------------------------
+struct Trace {
+    int r, c;     // position in the post-resize grid
+    int zero;     // -1, or index of the op that zeroed the block
+};
+
+__device__ __forceinline__ Trace trace_back(const rgbnm_plan& pl, int comp, int r, int c) {
+    const int G = comp == 0 ? GRID_Y : GRID_C;
+    Trace t{r, c, -1};
+    for (int k = pl.n_ops - 1; k >= 0; --k) {
+        const rgbnm_plan_op& op = pl.ops[k];
+        const int code = op.code;
+        if (code == RGBNM_OP_TRANSLATE_X) {
+            const int nc = t.c - op.p[comp == 0 ? 0 : 1];
+            if (nc < 0 || nc >= G) { t.zero = k; return t; }
+            t.c = nc;
+        } else if (code == RGBNM_OP_TRANSLATE_Y) {
+            const int nr = t.r - op.p[comp == 0 ? 0 : 1];
+            if (nr < 0 || nr >= G) { t.zero = k; return t; }
+            t.r = nr;
+        } else if (code == RGBNM_OP_ROT90) {
+            const int rr = t.r, cc = t.c;
+            if (op.p[0] > 0) { t.r = cc; t.c = G - 1 - rr; }   // torch.rot90(k=+1): out[i][j] = in[j][G-1-i]
+            else             { t.r = G - 1 - cc; t.c = rr; }   // k=-1: out[i][j] = in[G-1-j][i]
+        } else if (code == RGBNM_OP_CUTOUT) {
+            const int o = comp == 0 ? 0 : 4;
+            if (t.r >= op.p[o] && t.r < op.p[o + 1] && t.c >= op.p[o + 2] && t.c < op.p[o + 3]) { t.zero = k; return t; }
+        } else if (code == RGBNM_OP_GRAYSCALE) {
+            if (comp != 0) { t.zero = k; return t; }
+        } else if (code == RGBNM_OP_CHROMADROP) {
+            if (comp == 1 + op.p[0]) { t.zero = k; return t; }
+        }
+    }
+    if (pl.flip) t.c = G - 1 - t.c;
+    return t;
+}
+
+}  // namespace k0

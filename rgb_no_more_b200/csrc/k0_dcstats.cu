@@ -1,0 +1,203 @@
+// K0 pre-pass: per-image DC statistics for the three RandAugment ops that need a
+// whole-image reduction (SURVEY.md 7 "hard part 3"):
+//   Brightness      mean(|DC_Y|) * m          utils/dct_ops.py:831-832
+//   AutoContrast    min / max of DC_Y         utils/dct_ops.py:875-882
+//   AutoSaturation  min / max of DC_CbCr (joint over both chroma planes)
+// The reduction must see the DC plane *as it is when the op runs*, i.e. after the resize,
+// the flip and every earlier op (translate / cutout zero blocks, posterize moves DCs, ...).
+// Only the DC term of each block (1/64 of the data) is involved, so one small CTA per
+// flagged image replays the plan on the 28x28 + 2x14x14 DC planes in shared memory and
+// writes the resolved scalars to `stats`; the fused kernel then stays a pure per-block
+// function.  Images whose plan has none of the three ops exit immediately.
+#include <cuda_runtime.h>
+
+#include "../../include/rgbnm_b200.h"
+#include "common.cuh"
+#include "k0_common.cuh"
+
+namespace k0 {
+
+constexpr int NY = GRID_Y * GRID_Y;       // 784
+constexpr int NC = 2 * GRID_C * GRID_C;   // 392
+constexpr int NDC = NY + NC;
+constexpr int STATS_THREADS = 256;
+
+// DC of the resized block at post-resize position (r, c) of plane `comp`, computed with the
+// exact operation sequence of the fused kernel's row pass + column pass.
+__device__ float resized_dc(const int16_t* __restrict__ plane, int W, const float* __restrict__ q, int mode,
+                            bool clamp_in, int ci, int cj, int r, int c) {
+    auto ld = [&](int brow, int bcol, int row, float (&x)[8]) {
+        const int4 raw = __ldg(reinterpret_cast<const int4*>(plane + (size_t(brow) * W + bcol) * 64 + row * 8));
+        if (clamp_in) dequant8<true>(raw, q + row * 8, x);
+        else dequant8<false>(raw, q + row * 8, x);
+    };
+    if (mode == MODE_IDENT) {
+        float x[8];
+        ld(ci + r, cj + c, 0, x);
+        return x[0];
+    }
+    if (mode == MODE_DOWN2) {
+        // column 0 of R needs rows 0 and 8 of the 16x16 tile: first row of the top / bottom block pair
+        float xl[8], xr[8], o[8], col_l[8], col_r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) col_l[i] = col_r[i] = 0.0f;
+        ld(ci + 2 * r, cj + 2 * c, 0, xl);
+        ld(ci + 2 * r, cj + 2 * c + 1, 0, xr);
+        down2_1d<1, 1>(xl, xr, o);
+        col_l[0] = o[0];
+        ld(ci + 2 * r + 1, cj + 2 * c, 0, xl);
+        ld(ci + 2 * r + 1, cj + 2 * c + 1, 0, xr);
+        down2_1d<1, 1>(xl, xr, o);
+        col_r[0] = o[0];
+        float v[8];
+        down2_1d<1, 2>(col_l, col_r, v);   // v[0] depends only on col_l[0], col_r[0]
+        return rint_magic(v[0]);
+    }
+    // MODE_UP2
+    float col[8], x[8], o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        ld(ci + (r >> 1), cj + (c >> 1), i, x);
+        up2_1d<1>(x, c & 1, o);
+        col[i] = o[0];
+    }
+    float v[8];
+    up2_1d<2>(col, r & 1, v);
+    return rint_magic(v[0]);
+}
+
+__device__ __forceinline__ float block_reduce(float v, int op, float* scratch) {
+    // op: 0 sum, 1 min, 2 max
+    for (int o = 16; o > 0; o >>= 1) {
+        const float t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = op == 0 ? v + t : op == 1 ? fminf(v, t) : fmaxf(v, t);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = scratch[0];
+    for (int w = 1; w < STATS_THREADS / 32; ++w) r = op == 0 ? r + scratch[w] : op == 1 ? fminf(r, scratch[w]) : fmaxf(r, scratch[w]);
+    return r;
+}
+
+__global__ void __launch_bounds__(STATS_THREADS)
+k0_dcstats_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, const int16_t* __restrict__ quant,
+                  const rgbnm_plan* __restrict__ plans, rgbnm_k0_tables tb, float* __restrict__ stats_all, int hb, int wb) {
+    const int img = blockIdx.x;
+    __shared__ rgbnm_plan pl;
+    __shared__ float qf[192];
+    __shared__ float dc[2][NDC];
+    __shared__ float scratch[STATS_THREADS / 32];
+    if (threadIdx.x < int(sizeof(rgbnm_plan) / 4))
+        reinterpret_cast<int*>(&pl)[threadIdx.x] = __ldg(reinterpret_cast<const int*>(plans + img) + threadIdx.x);
+    __syncthreads();
+    if (!pl.needs_stats) return;
+    for (int k = threadIdx.x; k < 192; k += STATS_THREADS) qf[k] = float(__ldg(quant + size_t(img) * 192 + k));
+    __syncthreads();
+
+    const int hc = hb >> 1, wc = wb >> 1;
+    const int mode = mode_of(pl.crop_size);
+    float* stats = stats_all + size_t(img) * RGBNM_MAX_OPS * 2;
+
+    // post-resize, post-flip DC planes (flip only moves blocks: the DC term keeps its sign)
+    for (int e = threadIdx.x; e < NDC; e += STATS_THREADS) {
+        int comp, r, c;
+        if (e < NY) { comp = 0; r = e / GRID_Y; c = e - r * GRID_Y; }
+        else { const int f = e - NY; comp = 1 + f / (GRID_C * GRID_C); const int g = f % (GRID_C * GRID_C); r = g / GRID_C; c = g - r * GRID_C; }
+        const int G = comp == 0 ? GRID_Y : GRID_C;
+        const int sc = pl.flip ? G - 1 - c : c;
+        const int16_t* plane = comp == 0 ? y + size_t(img) * hb * wb * 64
+                                         : cbcr + (size_t(img) * 2 + (comp - 1)) * hc * wc * 64;
+        float v = resized_dc(plane, comp == 0 ? wb : wc, qf + comp * 64, mode, pl.clamp_in != 0,
+                             comp == 0 ? pl.crop_i : pl.crop_i >> 1, comp == 0 ? pl.crop_j : pl.crop_j >> 1, r, sc);
+        if (pl.train) v = clampf(v);
+        dc[0][e] = v;
+    }
+    __syncthreads();
+
+    int cur = 0;
+    for (int k = 0; k < pl.n_ops; ++k) {
+        const rgbnm_plan_op op = pl.ops[k];
+        const int code = op.code;
+        float* src = dc[cur];
+        float* dst = dc[cur ^ 1];
+        // ---- reductions first (they read the plane as it stands before op k) ----
+        float s0 = 0.0f, s1 = 0.0f;
+        if (code == RGBNM_OP_BRIGHTNESS) {
+            float a = 0.0f;
+            for (int e = threadIdx.x; e < NY; e += STATS_THREADS) a += fabsf(src[e]);
+            // integer-valued partial sums < 2^24: exact in fp32 whatever the order
+            const float sum = block_reduce(a, 0, scratch);
+            s0 = __fdiv_rn(sum, float(NY)) * op.f;      // torch.mean(|dc|) * m
+        } else if (code == RGBNM_OP_AUTOCONTRAST || code == RGBNM_OP_AUTOSATURATION) {
+            const int lo_e = code == RGBNM_OP_AUTOCONTRAST ? 0 : NY, hi_e = code == RGBNM_OP_AUTOCONTRAST ? NY : NDC;
+            float mn = 3.0e38f, mx = -3.0e38f;
+            for (int e = lo_e + threadIdx.x; e < hi_e; e += STATS_THREADS) { mn = fminf(mn, src[e]); mx = fmaxf(mx, src[e]); }
+            s0 = block_reduce(mn, 1, scratch);
+            s1 = block_reduce(mx, 2, scratch);
+        }
+        if (threadIdx.x == 0) { stats[2 * k] = s0; stats[2 * k + 1] = s1; }
+        // ---- then apply op k to the DC planes ----
+        for (int e = threadIdx.x; e < NDC; e += STATS_THREADS) {
+            int comp, r, c;
+            if (e < NY) { comp = 0; r = e / GRID_Y; c = e - r * GRID_Y; }
+            else { const int f = e - NY; comp = 1 + f / (GRID_C * GRID_C); const int g = f % (GRID_C * GRID_C); r = g / GRID_C; c = g - r * GRID_C; }
+            const int G = comp == 0 ? GRID_Y : GRID_C;
+            const int base = comp == 0 ? 0 : NY + (comp - 1) * GRID_C * GRID_C;
+            float v = src[e];
+            if (code == RGBNM_OP_TRANSLATE_X) {
+                const int nc = c - op.p[comp == 0 ? 0 : 1];
+                v = (nc < 0 || nc >= G) ? 0.0f : src[base + r * G + nc];
+            } else if (code == RGBNM_OP_TRANSLATE_Y) {
+                const int nr = r - op.p[comp == 0 ? 0 : 1];
+                v = (nr < 0 || nr >= G) ? 0.0f : src[base + nr * G + c];
+            } else if (code == RGBNM_OP_ROT90) {
+                const int sr = op.p[0] > 0 ? c : G - 1 - c, sc = op.p[0] > 0 ? G - 1 - r : r;
+                v = src[base + sr * G + sc];
+            } else if (code == RGBNM_OP_CUTOUT) {
+                const int o = comp == 0 ? 0 : 4;
+                if (r >= op.p[o] && r < op.p[o + 1] && c >= op.p[o + 2] && c < op.p[o + 3]) v = 0.0f;
+            } else if (code == RGBNM_OP_GRAYSCALE) {
+                if (comp != 0) v = 0.0f;
+            } else if (code == RGBNM_OP_CHROMADROP) {
+                if (comp == 1 + op.p[0]) v = 0.0f;
+            } else if (code == RGBNM_OP_BRIGHTNESS) {
+                if (comp == 0) v = rint_magic(v + s0);
+            } else if (code == RGBNM_OP_CONTRAST) {
+                if (comp == 0) v = rint_magic(v * op.f);
+            } else if (code == RGBNM_OP_COLOR) {
+                if (comp != 0) v = rint_magic(v * op.f);
+            } else if (code == RGBNM_OP_AUTOCONTRAST || code == RGBNM_OP_AUTOSATURATION) {
+                const bool mine = (code == RGBNM_OP_AUTOCONTRAST) ? (comp == 0) : (comp != 0);
+                if (mine && s0 != s1) {
+                    const float z = __fdiv_rn(v - s0, s1 - s0);
+                    v = rint_magic(CLAMP_LO + z * (CLAMP_HI - CLAMP_LO));
+                }
+            } else if (code == RGBNM_OP_POSTERIZE) {
+                v = float(tb.posterize_lut[op.p[0] * 2048 + int(v) + 1024]);
+            } else if (code == RGBNM_OP_SHARPNESS || code == RGBNM_OP_MIDFREQ) {
+                if (comp == 0) v = rint_magic(clampf(v * __ldg(tb.filters + op.p[0] * 64)));
+            } else if (code == RGBNM_OP_SOLARIZE_ADD) {
+                if (comp == 0 && v < 0.0f) v += float(op.p[0]);
+            } else if (code == RGBNM_OP_INVERT) {
+                v = -v;
+            }
+            dst[e] = clampf(v);
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+}
+
+}  // namespace k0
+
+extern "C" int rgbnm_k0_dcstats(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans,
+                                const rgbnm_k0_tables* tables, float* stats, int n, int hb, int wb, void* stream) {
+    using namespace k0;
+    if (!y || !cbcr || !quant || !plans || !tables || !stats || n < 0) return RGBNM_ERR_ARG;
+    if (hb < 2 || wb < 2 || hb > 255 || wb > 255 || (hb & 1) || (wb & 1)) return RGBNM_ERR_ARG;
+    if (n == 0) return RGBNM_OK;
+    k0_dcstats_kernel<<<n, STATS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(y, cbcr, quant, plans, *tables, stats, hb, wb);
+    RGBNM_CUDA_CHECK(cudaGetLastError());
+    return RGBNM_OK;
+}

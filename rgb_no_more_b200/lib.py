@@ -23,8 +23,7 @@ class JpegInfo(C.Structure):
 
 
 class K0Tables(C.Structure):
-    _fields_ = [("filters", C.c_void_p), ("posterize_lut", C.c_void_p), ("up_mats", C.c_void_p),
-                ("a16", C.c_void_p)]
+    _fields_ = [("filters", C.c_void_p), ("posterize_lut", C.c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol include/rgbnm_b200.h declares.

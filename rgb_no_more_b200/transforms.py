@@ -1,0 +1,137 @@
+"""Host side of the fused DCT data path (K0) -- the `get_transform` seam (boundary B2).
+
+The reference builds a per-image `transforms.Compose` that runs on CPU DataLoader workers
+(/root/reference/datasets.py:305-390).  Here the same `dataset`/`type`/`ops_list`/`num_ops`/
+`ops_magnitude` arguments configure a *batch* transform: the host only draws the
+augmentation plan (rgb_no_more_b200/plan.py, same RNG call sequence), everything else runs
+in one fused CUDA kernel through the C-ABI (include/rgbnm_b200.h: rgbnm_k0_dcstats +
+rgbnm_k0_fused).  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from . import plan as P
+
+OUT_F32, OUT_BF16, OUT_INT16_PLANES = 0, 1, 2
+PLANE_ELEMS = (28 * 28 + 2 * 14 * 14) * 64
+
+
+class FusedDCT:
+    """Batch DCT transform on one GPU.
+
+    >>> tf = FusedDCT(device, kind="train", ops_list=plan.AUGLIST_VITS, num_ops=2, ops_magnitude=9)
+    >>> x = tf(y_q, c_q, quant)            # (B,196,384) operand of the patch-projection Linear
+    """
+
+    def __init__(self, device, kind: str = "test", ops_list: Optional[Sequence[str]] = None, num_ops: int = 2,
+                 ops_magnitude: int = 10, out_dtype: torch.dtype = torch.float32, out_size: int = 28):
+        if out_size != 28:
+            raise NotImplementedError("rgbnm: only the 28-block (patch 16, 224 px) geometry is on the hot path")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.RgbnmError("rgbnm: FusedDCT needs a CUDA device; there is no CPU fallback")
+        self.kind = kind
+        self.ops_list = list(ops_list) if ops_list is not None else None
+        self.num_ops = num_ops
+        self.ops_magnitude = ops_magnitude
+        self.out_dtype = out_dtype
+        self.bank = P.FilterBank()
+        self._lib = _lib.load()
+        self._filters_dev = None
+        self._filters_n = -1
+        self._lut = torch.from_numpy(P.posterize_lut()).to(self.device)
+        self._tables = _lib.K0Tables()
+        self._sync_tables()
+
+    # -- tables ---------------------------------------------------------------------------
+    def _sync_tables(self):
+        if self._filters_n != self.bank._n:
+            self._filters_dev = torch.from_numpy(self.bank.table.reshape(-1, 64).copy()).to(self.device)
+            self._filters_n = self.bank._n
+        self._tables.filters = self._filters_dev.data_ptr()
+        self._tables.posterize_lut = self._lut.data_ptr()
+
+    # -- plans ----------------------------------------------------------------------------
+    def sample_plans(self, n: int, hb: int = 64, wb: int = 64) -> List[P.Plan]:
+        """Draw n plans from the torch global CPU RNG in the reference's call order."""
+        if self.kind == "train":
+            return [P.sample_train_plan(hb, wb, self.ops_list, self.num_ops, self.ops_magnitude, self.bank)
+                    for _ in range(n)]
+        return [P.eval_plan(hb, wb)] * n
+
+    # -- launch ---------------------------------------------------------------------------
+    def run(self, y_q: torch.Tensor, c_q: torch.Tensor, quant: torch.Tensor, plans, clamp_in=None,
+            out_mode: Optional[int] = None, out: Optional[torch.Tensor] = None,
+            plans_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """y_q int16 [B,hb,wb,64] (or [B,1,hb,wb,8,8]), c_q int16 [B,2,hb/2,wb/2,64], quant int16 [B,3,64],
+        all on `device`.  `plans`: list[Plan] or packed numpy array (or pass `plans_dev`)."""
+        B = y_q.shape[0]
+        if y_q.dim() == 6:
+            hb, wb = y_q.shape[2], y_q.shape[3]
+        else:
+            hb, wb = y_q.shape[1], y_q.shape[2]
+        for t in (y_q, c_q, quant):
+            if t.device != self.device or t.dtype != torch.int16 or not t.is_contiguous():
+                raise ValueError("rgbnm: coefficient tensors must be contiguous int16 on the transform's device")
+        if c_q.numel() != B * 2 * (hb // 2) * (wb // 2) * 64 or quant.numel() != B * 192:
+            raise ValueError("rgbnm: coefficient batch shapes are inconsistent (4:2:0 layout expected)")
+        if plans_dev is None:
+            if not isinstance(plans, np.ndarray):
+                for pl in plans:
+                    if pl.crop_i + pl.crop_size > hb or pl.crop_j + pl.crop_size > wb or pl.crop_i < 0 or pl.crop_j < 0:
+                        raise ValueError("rgbnm: crop window outside the image")
+                plans = P.pack_plans(plans, clamp_in)
+            if len(plans) != B:
+                raise ValueError("rgbnm: one plan per image required")
+            plans_dev = torch.from_numpy(plans.view(np.uint8).reshape(B, -1)).to(self.device, non_blocking=True)
+        self._sync_tables()
+        if out_mode is None:
+            out_mode = OUT_BF16 if self.out_dtype == torch.bfloat16 else OUT_F32
+        if out is None:
+            if out_mode == OUT_INT16_PLANES:
+                out = torch.empty((B, PLANE_ELEMS), dtype=torch.int16, device=self.device)
+            else:
+                out = torch.empty((B, 196, 384), dtype=torch.bfloat16 if out_mode == OUT_BF16 else torch.float32,
+                                  device=self.device)
+        stats = torch.zeros((B, P.MAX_OPS, 2), dtype=torch.float32, device=self.device)
+        st = _lib.stream_ptr()
+        L = self._lib
+        _lib.check(L.rgbnm_k0_dcstats(y_q.data_ptr(), c_q.data_ptr(), quant.data_ptr(), plans_dev.data_ptr(),
+                                      C.byref(self._tables), stats.data_ptr(), B, hb, wb, st), "rgbnm_k0_dcstats")
+        _lib.check(L.rgbnm_k0_fused(y_q.data_ptr(), c_q.data_ptr(), quant.data_ptr(), plans_dev.data_ptr(),
+                                    C.byref(self._tables), stats.data_ptr(), out.data_ptr(), out_mode, B, hb, wb, st),
+                   "rgbnm_k0_fused")
+        self.last_stats = stats
+        return out
+
+    def __call__(self, y_q, c_q, quant, clamp_in=None):
+        plans = self.sample_plans(y_q.shape[0], *(y_q.shape[2:4] if y_q.dim() == 6 else y_q.shape[1:3]))
+        return self.run(y_q, c_q, quant, plans, clamp_in)
+
+
+def split_planes(planes: torch.Tensor):
+    """INT16_PLANES output -> (Y [B,1,28,28,8,8], CbCr [B,2,14,14,8,8]) in the reference layout."""
+    B = planes.shape[0]
+    y = planes[:, : 784 * 64].reshape(B, 1, 28, 28, 8, 8)
+    c = planes[:, 784 * 64:].reshape(B, 2, 14, 14, 8, 8)
+    return y, c
+
+
+def get_transform(dataset: str = "imagenet_dct", type: str = "train", ops_list=None, num_ops: int = 2,
+                  ops_magnitude: int = 10, dtype=torch.float32, device="cuda"):
+    """Same selector as the reference's datasets.get_transform (datasets.py:305-390) for the
+    DCT datasets; returns a batch transform bound to `device`."""
+    if dataset != "imagenet_dct":
+        raise NotImplementedError(f"rgbnm: dataset '{dataset}' is outside the B200 hot path (SURVEY.md 8f)")
+    if type == "train":
+        return FusedDCT(device, "train", ops_list, num_ops, ops_magnitude, dtype)
+    if type in ("val", "test"):
+        return FusedDCT(device, "test", None, 0, 0, dtype)
+    print("Unrecognized dataset type! Returning 'None' transform")
+    return None
