@@ -286,14 +286,73 @@ def apply_op(y: torch.Tensor, c: torch.Tensor, op, filters: np.ndarray):
     return _clamp(y).contiguous(), _clamp(c).contiguous()
 
 
-def transform_int16(y_q, c_q, quant, plan, filters, out_size: int = 28):
-    """dequantise -> crop -> resize -> flip -> RandAugment ops; returns the int16
-    planes the reference hands to ToRange: Y (1,S,S,8,8), CbCr (2,S/2,S/2,8,8)."""
+def resized_planes(y_q, c_q, quant, plan, out_size: int = 28):
+    """dequantise -> crop -> resize: the int16 planes RandomFlip_DCT receives."""
     y, c = dequantize(y_q, c_q, quant)
     s = plan.crop_size
     y = resize_blocks(crop_blocks(y, plan.crop_i, plan.crop_j, s, s), out_size)
     c = resize_blocks(crop_blocks(c, plan.crop_i // 2, plan.crop_j // 2, max(1, s // 2), max(1, s // 2)),
                       math.ceil(out_size / 2))
+    return y, c
+
+
+def resized_planes_exact(y_q, c_q, quant, plan, out_size: int = 28):
+    """The same resize evaluated in float64 with float64 basis matrices and NOT rounded.
+    Used by the parity tests to decide whether an int16 mismatch sits on an exact .5 tie
+    of the real-valued result (where the reference's own answer depends on the BLAS
+    summation order, SURVEY.md 7 hard part 2)."""
+    def basis64(n):
+        h = torch.arange(n, dtype=torch.float64).unsqueeze(1)
+        w = torch.arange(n, dtype=torch.float64).unsqueeze(0) + 0.5
+        b = (h @ w * math.pi / n).cos()
+        b[0] *= 1 / math.sqrt(2)
+        return b * math.sqrt(2 / n)
+
+    def conv64(mult):
+        return basis64(8 * mult) @ torch.block_diag(*[basis64(8)] * mult).T
+
+    def resize64(x, size):
+        _, H, _, _, _ = x.shape
+        g = math.gcd(H, size)
+        up, down = size // g, H // g
+        z = x.to(torch.float64)
+        if up > 1:
+            A = conv64(up)
+            c, h, w = z.shape[:3]
+            big = torch.zeros((c, h, w, 8 * up, 8 * up), dtype=torch.float64)
+            big[..., :8, :8] = z * up
+            big = A.T @ big @ A
+            z = big.reshape(c, h, w, up, 8, up, 8).permute(0, 1, 3, 2, 5, 4, 6).reshape(c, h * up, w * up, 8, 8)
+        if down > 1:
+            A = conv64(down)
+            c, H2, W2 = z.shape[:3]
+            z = z.reshape(c, H2 // down, down, W2 // down, down, 8, 8).permute(0, 1, 3, 2, 5, 4, 6)
+            z = z.reshape(c, H2 // down, W2 // down, 8 * down, 8 * down)
+            z = (A @ z @ A.T)[..., :8, :8] / down
+        return z
+
+    y, c = dequantize(y_q, c_q, quant)
+    s = plan.crop_size
+    return (resize64(crop_blocks(y, plan.crop_i, plan.crop_j, s, s), out_size),
+            resize64(crop_blocks(c, plan.crop_i // 2, plan.crop_j // 2, max(1, s // 2), max(1, s // 2)),
+                     math.ceil(out_size / 2)))
+
+
+def transform_from_resized(y, c, plan, filters):
+    """flip -> RandAugment ops on already-resized int16 planes (integer / DC arithmetic only)."""
+    if plan.flip:
+        y, c = flip_blocks(y), flip_blocks(c)
+    if plan.train:
+        y, c = _clamp(y), _clamp(c)                    # custom_transforms.py:1107-1108
+        for op in plan.ops:
+            y, c = apply_op(y, c, op, filters)
+    return y, c
+
+
+def transform_int16(y_q, c_q, quant, plan, filters, out_size: int = 28):
+    """dequantise -> crop -> resize -> flip -> RandAugment ops; returns the int16
+    planes the reference hands to ToRange: Y (1,S,S,8,8), CbCr (2,S/2,S/2,8,8)."""
+    y, c = resized_planes(y_q, c_q, quant, plan, out_size)
     if plan.flip:
         y, c = flip_blocks(y), flip_blocks(c)
     if plan.train:

@@ -1,8 +1,16 @@
 """GPU parity tests for the fused DCT kernel (K0), called through the C-ABI.
-Bit-exact where the reference is integer arithmetic (dequant, crop, flip, translate, rot90,
-cutout, chroma drop, DC ops on an un-resized crop); <= 1 int16 LSB on a small fraction of
-coefficients where a resize is involved (fp32 summation order at exact .5 ties -- the
-reference itself is not reproducible across BLAS builds there, SURVEY.md 7 hard part 2)."""
+
+Parity is asserted stage by stage, because the reference rounds to int16 between stages:
+  (1) dequantise + crop + resize: bit-exact when no resize happens (crop 28); for the x2 up /
+      x2 down resizes the CUDA int16 planes may differ from the oracle by one LSB and ONLY where
+      the real-valued (float64) result sits on a .5 tie -- ~8 % of the down-sampled coefficients
+      are exact ties ((a+b+c+d)/4), and there the reference's own answer is decided by fp32 noise
+      of its BLAS, i.e. it is not reproducible across machines (SURVEY.md 7 hard part 2);
+  (2) flip + RandAugment ops: BIT-EXACT given the resized planes (integer / DC arithmetic) --
+      K0(full plan) == oracle ops applied to K0(resize only);
+  (3) ToRange + rearrange + sub-block conversion (fp32): |diff| <= F32_TOL against the oracle fed
+      with K0's own int16 planes; the chroma part is a pure permutation and must be bit-exact.
+"""
 import numpy as np
 import pytest
 import torch
@@ -11,13 +19,12 @@ from oracle import dct_oracle as O
 from rgb_no_more_b200 import plan as P
 from rgb_no_more_b200 import synth
 from rgb_no_more_b200 import transforms as TF
-from tests.helpers import load, unpack_plans, lsb_report
+from tests.helpers import load, unpack_plans, lsb_report, assert_only_tie_mismatches
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-LSB_FRAC = 1e-2       # max fraction of coefficients allowed to differ by one LSB after a resize
-F32_TOL = 2e-5        # |K0 fp32 - oracle| where no LSB flip occurred (embed-input units, range [-1,1])
-LSB_STEP = 2.0 / 2040  # one int16 LSB after ToRange
+F32_TOL = 2e-5        # |K0 fp32 - oracle fp32| in embed-input units (range [-1,1]); fp32 summation order only
+BF16_TOL = 2 ** -8    # bf16 output: half an ulp at |x| <= 1.6 (orthonormal A16 keeps |x| <= 16 in theory; data << that)
 
 
 def _run_planes(tf, y, c, q, plans):
@@ -26,7 +33,37 @@ def _run_planes(tf, y, c, q, plans):
     return TF.split_planes(out.cpu())
 
 
+def _views(y, c, q, b):
+    return y[b].reshape(1, 64, 64, 8, 8), c[b].reshape(2, 32, 32, 8, 8), q[b].reshape(3, 8, 8)
+
+
+def _resize_only(pl):
+    return P.Plan(crop_i=pl.crop_i, crop_j=pl.crop_j, crop_size=pl.crop_size, flip=False, train=False, ops=[])
+
+
+def _check_stagewise(tf, y, c, q, plans):
+    """Stages (1) and (2) of the module docstring for a batch; returns the tie-mismatch fractions."""
+    oy, oc = _run_planes(tf, y, c, q, plans)
+    ry, rc = _run_planes(tf, y, c, q, [_resize_only(p) for p in plans])
+    fracs = []
+    for b, pl in enumerate(plans):
+        yq, cq, qq = _views(y, c, q, b)
+        ey, ec = O.resized_planes(yq, cq, qq, pl)
+        desc = (b, pl.crop_size, [o.name for o in pl.ops])
+        if pl.crop_size == 28:
+            assert torch.equal(ry[b], ey) and torch.equal(rc[b], ec), desc
+        else:
+            xy, xc = O.resized_planes_exact(yq, cq, qq, pl)
+            fracs.append(assert_only_tie_mismatches(ry[b].numpy(), ey.numpy(), xy.numpy(), desc))
+            fracs.append(assert_only_tie_mismatches(rc[b].numpy(), ec.numpy(), xc.numpy(), desc))
+        fy, fc = O.transform_from_resized(ry[b].clone(), rc[b].clone(), pl, tf.bank.table)
+        assert torch.equal(oy[b], fy), (desc, lsb_report(oy[b].numpy(), fy.numpy()))
+        assert torch.equal(oc[b], fc), (desc, lsb_report(oc[b].numpy(), fc.numpy()))
+    return fracs
+
+
 def test_golden_pipeline_cases():
+    """Cases produced by the reference's own transform classes (tools/make_golden.py)."""
     g = load("pipeline.npz")
     plans = unpack_plans(g["plans"])
     tf = TF.FusedDCT(DEV, "train", P.AUGLIST_VITS, 2, 9)
@@ -37,15 +74,16 @@ def test_golden_pipeline_cases():
         y = torch.from_numpy(g[f"img{img}_y"]).reshape(1, 64, 64, 64)
         c = torch.from_numpy(g[f"img{img}_c"]).reshape(1, 2, 32, 32, 64)
         q = torch.from_numpy(g[f"img{img}_q"]).reshape(1, 3, 64)
+        _check_stagewise(tf, y, c, q, [plans[k]])
         oy, oc = _run_planes(tf, y, c, q, [plans[k]])
-        my, fy = lsb_report(oy[0].numpy(), g[f"case{k}_y"])
-        mc, fc = lsb_report(oc[0].numpy(), g[f"case{k}_c"])
         names = str(g["plan_op_names"][k])
         if plans[k].crop_size == 28:
-            assert my == 0 and mc == 0, (k, names, my, mc)          # no resize: bit exact
+            # no resize: bit exact against the reference's own output
+            assert np.array_equal(oy[0].numpy(), g[f"case{k}_y"]) and np.array_equal(oc[0].numpy(), g[f"case{k}_c"]), (k, names)
         else:
-            assert my <= 1 and mc <= 1, (k, names, my, mc)
-            assert fy < LSB_FRAC and fc < LSB_FRAC, (k, names, fy, fc)
+            # direct comparison: everything except tie flips (and what a DC op makes of them) is identical
+            assert float((oy[0].numpy() != g[f"case{k}_y"]).mean()) < 0.12, (k, names)
+            assert float((oc[0].numpy() != g[f"case{k}_c"]).mean()) < 0.12, (k, names)
 
 
 def _random_batch(B, seed, dense):
@@ -61,23 +99,21 @@ def test_random_plans_vs_oracle(dense, mag, ops):
     tf = TF.FusedDCT(DEV, "train", ops, 2, mag)
     torch.manual_seed(1234 + mag + int(dense))
     plans = tf.sample_plans(B)
-    oy, oc = _run_planes(tf, y, c, q, plans)
-    n_exact = 0
-    for b in range(B):
-        ry, rc = O.transform_int16(y[b].reshape(1, 64, 64, 8, 8), c[b].reshape(2, 32, 32, 8, 8),
-                                   q[b].reshape(3, 8, 8), plans[b], tf.bank.table)
-        my, fy = lsb_report(oy[b].numpy(), ry.numpy())
-        mc, fc = lsb_report(oc[b].numpy(), rc.numpy())
-        desc = (b, plans[b].crop_size, [o.name for o in plans[b].ops], my, fy, mc, fc)
-        if plans[b].crop_size == 28:
-            assert my == 0 and mc == 0, desc
-            n_exact += 1
-        else:
-            assert my <= 1 and mc <= 1, desc
-            # a DC tie flip can move a min/max and with it every AutoContrast output by 1 LSB
-            lim = 0.05 if plans[b].needs_stats else LSB_FRAC
-            assert fy < lim and fc < lim, desc
-    assert n_exact > 0
+    assert len({p.crop_size for p in plans}) >= 2
+    fracs = _check_stagewise(tf, y, c, q, plans)
+    assert fracs and max(fracs) < 0.15
+
+
+def test_real_jpeg_batch_stagewise():
+    """PIL-encoded synthetic JPEGs through our Huffman decoder, then the same stage-wise parity."""
+    from rgb_no_more_b200 import dct_manip as dm
+    B = 6
+    y, c, q, flags = dm.decode_batch(synth.synth_jpeg_set(B), 64, 64, nthreads=2)
+    tf = TF.FusedDCT(DEV, "train", P.AUGLIST_VITS, 2, 9)
+    torch.manual_seed(77)
+    plans = tf.sample_plans(B) + []
+    plans[0] = P.eval_plan(64, 64)
+    _check_stagewise(tf, y, c, q, plans)
 
 
 @pytest.mark.parametrize("crop", [14, 28, 56])
@@ -88,18 +124,31 @@ def test_embed_input_f32_and_bf16(crop):
     tf = TF.FusedDCT(DEV, "test")
     out = tf.run(y.to(DEV), c.to(DEV), q.to(DEV), plans, out_mode=TF.OUT_F32).cpu()
     outb = tf.run(y.to(DEV), c.to(DEV), q.to(DEV), plans, out_mode=TF.OUT_BF16).float().cpu()
+    py, pc = _run_planes(tf, y, c, q, plans)
     for b in range(B):
-        ref = O.transform_embed(y[b].reshape(1, 64, 64, 8, 8), c[b].reshape(2, 32, 32, 8, 8), q[b].reshape(3, 8, 8),
-                                plans[b], tf.bank.table)
+        # stage (3): oracle ToRange + rearrange + A16 conversion fed with K0's own int16 planes
+        ref = O.embed_input(O.to_range(py[b]).unsqueeze(0), O.to_range(pc[b]).unsqueeze(0)).reshape(196, 384)
         d = (out[b] - ref).abs()
-        if crop == 28:
-            assert float(d.max()) < F32_TOL, float(d.max())
-            assert torch.equal(out[b][:, 256:], ref[:, 256:])       # chroma: pure permutation + ToRange -> bit exact
-        else:
-            # an LSB flip of one coefficient moves <= 1 LSB_STEP of energy into its token
-            assert float(d.max()) < 1.5 * LSB_STEP
-            assert float((d > F32_TOL).float().mean()) < 0.2
-        assert float((outb[b] - ref).abs().max()) < 1.5 * LSB_STEP + 2 ** -8
+        assert float(d.max()) < F32_TOL, float(d.max())
+        assert torch.equal(out[b][:, 256:], ref[:, 256:])       # chroma: pure permutation + ToRange -> bit exact
+        assert float((outb[b] - ref).abs().max()) < BF16_TOL + F32_TOL
+
+
+def test_to_range_bit_exact_all_values():
+    """Every representable input of ToRange (-1024..1016) through the chroma path, bit-exact."""
+    vals = torch.arange(-1024, 1017, dtype=torch.int16)
+    c = torch.zeros((1, 2, 32, 32, 64), dtype=torch.int16)
+    c[0, 0, :14, :14, :] = vals.repeat(7)[: 14 * 14 * 64].reshape(14, 14, 64)     # all 2041 values inside the crop
+    y = torch.zeros((1, 64, 64, 64), dtype=torch.int16)
+    q = torch.ones((1, 3, 64), dtype=torch.int16)
+    tf = TF.FusedDCT(DEV, "test")
+    plans = [P.Plan(0, 0, 28)]
+    out = tf.run(y.to(DEV), c.to(DEV), q.to(DEV), plans, out_mode=TF.OUT_F32).cpu()
+    pc = c[0].reshape(2, 32, 32, 8, 8)[:, :14, :14]
+    ref = O.embed_input(O.to_range(torch.zeros((1, 1, 28, 28, 8, 8), dtype=torch.int16)),
+                        O.to_range(pc).unsqueeze(0)).reshape(196, 384)
+    assert torch.equal(out[0][:, 256:], ref[:, 256:])
+    assert len(torch.unique(pc)) > 1000
 
 
 def test_eval_geometry_matches_reference_crop():
