@@ -135,6 +135,40 @@ int rgbnm_k0_fused(const int16_t* y, const int16_t* cbcr, const int16_t* quant, 
 /* Number of kernels the two calls above launch for one batch (for gpu_launches accounting). */
 int rgbnm_k0_launch_count(void);
 
+
+/* ------------------------------------------------------------------------------
+ * (K1,K3,K5,K6,K8) Dense bf16 contractions of models/plainvit.py on tcgen05 tensor cores.
+ * Logical problem: C[M,N] = sum_k A[m,k] * B[n,k]  (fp32 accumulation in TMEM).
+ *   nn.Linear forward  (plainvit.py:194,441,443,485-490): A = activations [M,K], B = weight [N,K]
+ *   dgrad              : A = dY [M,N'], B = transposed bf16 weight copy
+ *   wgrad (RGBNM_EPI_WGRAD_ATOMIC): A and B are stored [K][M] and [K][N] (reduction index = token
+ *                        = slowest), out_f32[M][N] += alpha * C, split over `splits` CTAs
+ * All device pointers; bf16 operands; leading dimensions in elements, multiples of 8.
+ * ---------------------------------------------------------------------------- */
+enum rgbnm_epilogue {
+    RGBNM_EPI_STORE = 0,        /* C = acc (+ bias)                          bf16 */
+    RGBNM_EPI_RESIDUAL = 1,     /* C = acc + bias + aux                      plainvit.py:475-479 */
+    RGBNM_EPI_GELU = 2,         /* C = acc + bias, C2 = gelu_erf(C)          plainvit.py:485-487 */
+    RGBNM_EPI_DGELU = 3,        /* C = acc * gelu_erf'(aux)                  backward of the above */
+    RGBNM_EPI_POSEMB = 4,       /* C = acc + bias + posemb[row % period]     plainvit.py:194-198, 97-121 */
+    RGBNM_EPI_WGRAD_ATOMIC = 5, /* out_f32 += alpha * acc                    fp32 red.add */
+    RGBNM_EPI_F32 = 6           /* out_f32 = acc + bias                      fp32 (logits) */
+};
+
+typedef struct {
+    const void* A; const void* B;
+    void* C; void* C2; const void* aux;
+    const float* bias; const float* posemb; float* out_f32;
+    long long lda, ldb, ldc, ldaux, ldo;
+    int M, N, K;
+    int epilogue;               /* enum rgbnm_epilogue */
+    int pos_period;
+    int splits;
+    float alpha;
+} rgbnm_gemm_args;
+
+int rgbnm_gemm_bf16(const rgbnm_gemm_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,22 +119,45 @@ __device__ __forceinline__ float rint_magic(float x) {
 }
 __device__ __forceinline__ float clampf(float x) { return fminf(fmaxf(x, CLAMP_LO), CLAMP_HI); }
 
-// dequantise 8 int16 packed in an int4 with the fp32 table row q[8]; optional clamp
-template <bool CLAMP>
-__device__ __forceinline__ void dequant8(const int4& raw, const float* __restrict__ q, float (&x)[8]) {
-    const int w[4] = {raw.x, raw.y, raw.z, raw.w};
+// dequantise 8 int16 packed in an int4: x[j] = float(v[j]) * q[j], exactly, without I2F.
+// The biased 16-bit pattern (v ^ 0x8000) is dropped into the mantissa of 2^23 with one PRMT,
+// giving m = 2^23 + 32768 + v; then x = fma(m, q, cq) with cq = -(2^23 + 32768) * q, which is
+// exact: cq = -2^15 * 257 * q is representable for q <= 255 and |v * q| < 2^24.
+// q8 / cq8: 8 consecutive fp32 table entries (16-byte aligned, shared memory).
+__device__ __forceinline__ void dequant8_regs(const int4& raw, const float (&q)[8], const float (&cq)[8], bool clamp,
+                                              float (&x)[8]) {
+    const unsigned w[4] = {unsigned(raw.x) ^ 0x80008000u, unsigned(raw.y) ^ 0x80008000u,
+                           unsigned(raw.z) ^ 0x80008000u, unsigned(raw.w) ^ 0x80008000u};
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-        const float lo = float(int(short(w[p] & 0xffff)));
-        const float hi = float(w[p] >> 16);
-        x[2 * p] = lo * q[2 * p];
-        x[2 * p + 1] = hi * q[2 * p + 1];
-        if (CLAMP) {
-            x[2 * p] = clampf(x[2 * p]);
-            x[2 * p + 1] = clampf(x[2 * p + 1]);
-        }
+        const float lo = __uint_as_float(__byte_perm(w[p], 0x4B000000u, 0x7610));
+        const float hi = __uint_as_float(__byte_perm(w[p], 0x4B000000u, 0x7632));
+        x[2 * p] = fmaf(lo, q[2 * p], cq[2 * p]);
+        x[2 * p + 1] = fmaf(hi, q[2 * p + 1], cq[2 * p + 1]);
+    }
+    if (clamp) {     // datasets.py:288-290; the decoder proves it idle for ordinary JPEGs (plan.clamp_in = 0)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = clampf(x[j]);
     }
 }
+#define K0_LOAD_Q(q8, cq8)                                                                                          \
+    const float4 qa = *reinterpret_cast<const float4*>(q8), qb = *reinterpret_cast<const float4*>((q8) + 4);        \
+    const float4 ca = *reinterpret_cast<const float4*>(cq8), cb = *reinterpret_cast<const float4*>((cq8) + 4);      \
+    const float q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};                                            \
+    const float cq[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w}
+__device__ __forceinline__ void dequant8(const int4& raw, const float* __restrict__ q8, const float* __restrict__ cq8,
+                                         bool clamp, float (&x)[8]) {
+    K0_LOAD_Q(q8, cq8);
+    dequant8_regs(raw, q, cq, clamp, x);
+}
+// two horizontally adjacent blocks share the table row
+__device__ __forceinline__ void dequant8x2(const int4& ra, const int4& rb, const float* __restrict__ q8,
+                                           const float* __restrict__ cq8, bool clamp, float (&xl)[8], float (&xr)[8]) {
+    K0_LOAD_Q(q8, cq8);
+    dequant8_regs(ra, q, cq, clamp, xl);
+    dequant8_regs(rb, q, cq, clamp, xr);
+}
+constexpr float DEQ_BIAS = 8421376.0f;   // 2^23 + 2^15
 
 // ---------------------------------------------------------------------------------------
 // Geometry: where does the block at final-grid position (r, c) of plane `comp` come from?

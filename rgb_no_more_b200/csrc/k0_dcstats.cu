@@ -24,12 +24,11 @@ constexpr int STATS_THREADS = 256;
 
 // DC of the resized block at post-resize position (r, c) of plane `comp`, computed with the
 // exact operation sequence of the fused kernel's row pass + column pass.
-__device__ float resized_dc(const int16_t* __restrict__ plane, int W, const float* __restrict__ q, int mode,
-                            bool clamp_in, int ci, int cj, int r, int c) {
+__device__ float resized_dc(const int16_t* __restrict__ plane, int W, const float* __restrict__ q,
+                            const float* __restrict__ cq, int mode, bool clamp_in, int ci, int cj, int r, int c) {
     auto ld = [&](int brow, int bcol, int row, float (&x)[8]) {
         const int4 raw = __ldg(reinterpret_cast<const int4*>(plane + (size_t(brow) * W + bcol) * 64 + row * 8));
-        if (clamp_in) dequant8<true>(raw, q + row * 8, x);
-        else dequant8<false>(raw, q + row * 8, x);
+        dequant8(raw, q + row * 8, cq + row * 8, clamp_in, x);
     };
     if (mode == MODE_IDENT) {
         float x[8];
@@ -85,14 +84,18 @@ k0_dcstats_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbc
                   const rgbnm_plan* __restrict__ plans, rgbnm_k0_tables tb, float* __restrict__ stats_all, int hb, int wb) {
     const int img = blockIdx.x;
     __shared__ rgbnm_plan pl;
-    __shared__ float qf[192];
+    __shared__ __align__(16) float qf[192];
+    __shared__ __align__(16) float cqf[192];
     __shared__ float dc[2][NDC];
     __shared__ float scratch[STATS_THREADS / 32];
     if (threadIdx.x < int(sizeof(rgbnm_plan) / 4))
         reinterpret_cast<int*>(&pl)[threadIdx.x] = __ldg(reinterpret_cast<const int*>(plans + img) + threadIdx.x);
     __syncthreads();
     if (!pl.needs_stats) return;
-    for (int k = threadIdx.x; k < 192; k += STATS_THREADS) qf[k] = float(__ldg(quant + size_t(img) * 192 + k));
+    for (int k = threadIdx.x; k < 192; k += STATS_THREADS) {
+        qf[k] = float(__ldg(quant + size_t(img) * 192 + k));
+        cqf[k] = -DEQ_BIAS * qf[k];
+    }
     __syncthreads();
 
     const int hc = hb >> 1, wc = wb >> 1;
@@ -108,7 +111,7 @@ k0_dcstats_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbc
         const int sc = pl.flip ? G - 1 - c : c;
         const int16_t* plane = comp == 0 ? y + size_t(img) * hb * wb * 64
                                          : cbcr + (size_t(img) * 2 + (comp - 1)) * hc * wc * 64;
-        float v = resized_dc(plane, comp == 0 ? wb : wc, qf + comp * 64, mode, pl.clamp_in != 0,
+        float v = resized_dc(plane, comp == 0 ? wb : wc, qf + comp * 64, cqf + comp * 64, mode, pl.clamp_in != 0,
                              comp == 0 ? pl.crop_i : pl.crop_i >> 1, comp == 0 ? pl.crop_j : pl.crop_j >> 1, r, sc);
         if (pl.train) v = clampf(v);
         dc[0][e] = v;
