@@ -169,6 +169,33 @@ typedef struct {
 
 int rgbnm_gemm_bf16(const rgbnm_gemm_args* args, void* stream);
 
+
+/* ------------------------------------------------------------------------------
+ * (K2, K7, K8, a31) Memory-bound ViT kernels around the contractions.
+ * ---------------------------------------------------------------------------- */
+/* nn.LayerNorm(emb, eps) over the last dimension (plainvit.py:513,522,551); x, y bf16 [rows][emb],
+ * gamma/beta fp32, statistics fp32 [rows] kept for backward.  emb in {192, 384, 768}. */
+int rgbnm_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                        int rows, int emb, float eps, void* stream);
+/* dx = LN'(dy) (+ dres if non-NULL: the residual branch gradient, plainvit.py:475-479); dgamma/dbeta += */
+int rgbnm_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                        const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int emb, void* stream);
+/* out[cols] += column sums of a bf16 matrix (bias gradients of nn.Linear) */
+int rgbnm_colsum_bf16(const void* a, long long ld, int rows, int cols, float* out, void* stream);
+/* fp32 master weight [n][k] -> bf16 working copy (rows regrouped q|k|v head-major when qkv_heads > 0,
+ * undoing the "(h d qkv)" interleave of plainvit.py:447) and, if wt_bf16 != NULL, its transpose [k][n] */
+int rgbnm_weight_prep(const float* w, int n, int k, int qkv_heads, int head_dim, void* w_bf16, void* wt_bf16, void* stream);
+int rgbnm_qkv_perm_vec(const float* src, float* dst, int n, int heads, int head_dim, int inverse, void* stream);
+int rgbnm_qkv_unperm_rows_add(const float* src, float* dst, int n, int k, int heads, int head_dim, void* stream);
+/* *out += sum(g^2) */
+int rgbnm_sumsq_f32(const float* g, long long n, float* out, void* stream);
+/* clip_grad_norm_(max_norm) + AdamW(weight_decay=0) + decoupled decay `p -= decay * p` on the first n_decay
+ * elements (train.py:163-172, pipeline_utils.py:536, custom_optims.py:37-43); gnorm_sq = device scalar with
+ * sum(g^2) of the unscaled gradient, grad_scale multiplies g first (1/world after a SUM allreduce). */
+int rgbnm_adamw_step(float* p, const float* g, float* m, float* v, long long n, long long n_decay, const float* gnorm_sq,
+                     float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, int step, float decay,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

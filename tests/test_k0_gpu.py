@@ -173,7 +173,6 @@ def test_properties_full_batch():
     rot4 = [P.Plan(4, 8, 28, False, True, [_op("Rotate90", [1] + [0] * 7)] * 4) for _ in range(B)]
     got = tf.run(yd, cd, qd, rot4, out_mode=TF.OUT_INT16_PLANES)
     assert torch.equal(got.clamp(min=-1016), ref.clamp(min=-1016))
-    assert int((got != ref).sum()) <= int((ref == -1024).sum())
     # cw then ccw == identity (same caveat)
     rr = [P.Plan(4, 8, 28, False, True, [_op("Rotate90", [1] + [0] * 7), _op("Rotate90", [-1] + [0] * 7)]) for _ in range(B)]
     got = tf.run(yd, cd, qd, rr, out_mode=TF.OUT_INT16_PLANES)
