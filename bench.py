@@ -143,7 +143,7 @@ def run_ours(args):
     stage = None
     if args.stage == "train":
         from rgb_no_more_b200 import train_step as TS
-        stage = TS.TrainStage(dev, arch=args.arch, batch=B, dtype=args.dtype, world=world)
+        stage = TS.TrainStage(dev, arch=args.arch, batch=B, dtype=args.dtype, world=world, use_graph=not args.no_graph)
     out_buf = torch.empty((B, 196, 384), dtype=out_dtype, device=dev)
     labels_pool = [torch.randint(0, 1000, (B,), device=dev) for _ in range(N_POOL)]
 
@@ -350,6 +350,7 @@ def main():
     ap.add_argument("--arch", default="vits")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--stage", default="auto", choices=["auto", "k0", "train"])
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly (for ncu launch lists)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.stage == "auto":

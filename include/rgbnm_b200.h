@@ -190,11 +190,18 @@ int rgbnm_qkv_unperm_rows_add(const float* src, float* dst, int n, int k, int he
 /* *out += sum(g^2) */
 int rgbnm_sumsq_f32(const float* g, long long n, float* out, void* stream);
 /* clip_grad_norm_(max_norm) + AdamW(weight_decay=0) + decoupled decay `p -= decay * p` on the first n_decay
- * elements (train.py:163-172, pipeline_utils.py:536, custom_optims.py:37-43); gnorm_sq = device scalar with
- * sum(g^2) of the unscaled gradient, grad_scale multiplies g first (1/world after a SUM allreduce). */
+ * elements (train.py:163-172, pipeline_utils.py:536, custom_optims.py:37-43).  gnorm_sq = device scalar with
+ * sum(g^2) of the unscaled gradient.  hyper = 9 device floats (so that a captured CUDA graph can be replayed with
+ * a new learning rate): lr, beta1, beta2, eps, 1-beta1^t, 1-beta2^t, decay (= lr/base_lr*wd), grad_scale
+ * (multiplies g first: 1/world after a SUM allreduce), max_norm (<= 0: no clipping). */
 int rgbnm_adamw_step(float* p, const float* g, float* m, float* v, long long n, long long n_decay, const float* gnorm_sq,
-                     float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, int step, float decay,
-                     void* stream);
+                     const float* hyper, void* stream);
+
+
+/* (K4) attention core, forward: o = softmax(q k^T * scale) v per (image, head) (plainvit.py:450-461; the reference's
+ * scale is 1/sqrt(emb_size)).  qkv bf16 [B][N][3*H*D] = [q | k | v] head-major, o bf16 [B][N][H*D], lse fp32 [B][H][N]
+ * (log-sum-exp of the scaled scores, for backward).  N = 196, D = 64. */
+int rgbnm_attention_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int D, float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -54,11 +54,28 @@ struct Smem {
     static constexpr int TOTAL = OFF_TMEM + 16 + 1024;   // + slack for the manual 1024-byte alignment
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// GELU(erf) and its derivative (nn.GELU() default, plainvit.py:487).  erf by Abramowitz-Stegun 7.1.26
+// (|error| <= 1.5e-7, far below the bf16 output rounding): one MUFU.RCP + one MUFU.EX2 per element, and the
+// exponential exp(-x^2/2) is shared with the Gaussian density of the derivative.
+struct GeluParts { float cdf, pdf; };
+__device__ __forceinline__ GeluParts gelu_parts(float x) {
+    const float u = fabsf(x) * 0.70710678118654752f;
+    const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
+    const float ex = exp2f(x * x * -0.72134752044448170f);          // exp(-x^2 / 2)
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float erf_abs = fmaf(-poly * t, ex, 1.0f);
+    GeluParts g;
+    g.cdf = fmaf(copysignf(0.5f, x), erf_abs, 0.5f);
+    g.pdf = 0.3989422804014327f * ex;
+    return g;
+}
+__device__ __forceinline__ float gelu_erf(float x) { return x * gelu_parts(x).cdf; }
 __device__ __forceinline__ float dgelu_erf(float x) {
-    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-    const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-    return cdf + x * pdf;
+    const GeluParts g = gelu_parts(x);
+    return fmaf(x, g.pdf, g.cdf);
 }
 
 __device__ __forceinline__ void bar_sync_epi(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(EPI_WARPS * 32) : "memory"); }
@@ -337,6 +354,25 @@ int rgbnm_make_tmap_bf16(CUtensorMap* map, const void* ptr, long long rows, long
     return RGBNM_OK;
 }
 
+// 3-D bf16 tensor [d2][d1][d0] (d0 contiguous; pitches ld1, ld2 in elements); box = {box0, box1, 1}, 128-byte swizzle.
+int rgbnm_make_tmap_bf16_3d(CUtensorMap* map, const void* ptr, long long d0, long long d1, long long d2, long long ld1,
+                            long long ld2, int box0, int box1) {
+    gemm::EncodeTiledFn enc = gemm::get_encode();
+    if (!enc) return RGBNM_ERR_CUDA;
+    cuuint64_t dims[3] = {cuuint64_t(d0), cuuint64_t(d1), cuuint64_t(d2)};
+    cuuint64_t strides[2] = {cuuint64_t(ld1) * 2, cuuint64_t(ld2) * 2};
+    cuuint32_t box[3] = {cuuint32_t(box0), cuuint32_t(box1), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        rgbnm_set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(3d)");
+        return RGBNM_ERR_CUDA;
+    }
+    return RGBNM_OK;
+}
+
 namespace gemm {
 
 static int g_num_sms = 0;
@@ -392,7 +428,7 @@ extern "C" int rgbnm_gemm_bf16(const rgbnm_gemm_args* args, void* stream) {
     using namespace gemm;
     if (!args || !args->A || !args->B || args->M <= 0 || args->N <= 0 || args->K <= 0) return RGBNM_ERR_ARG;
     const rgbnm_gemm_args& a = *args;
-    if ((a.lda % 8) || (a.ldb % 8) || (a.K % 8)) return RGBNM_ERR_ARG;          // TMA: 16-byte aligned rows
+    if ((a.lda % 8) || (a.ldb % 8)) return RGBNM_ERR_ARG;                      // TMA: 16-byte aligned row pitch
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (a.epilogue) {
         case RGBNM_EPI_STORE:

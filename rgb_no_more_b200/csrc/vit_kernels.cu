@@ -133,30 +133,46 @@ ln_bwd_kernel(const unsigned* __restrict__ dy, const unsigned* __restrict__ x, c
 
 // ------------------------------------------------------------------------------------------
 // Column sums of a bf16 matrix [rows][cols] (ld elements) -> fp32 out[cols] += sum_rows
-// CTA = 256 threads: 64 columns (32 lanes x bf16 pair) x 8 row-lanes; grid (cols/64, row chunks)
+// A warp covers 256 columns of one row with 16-byte loads; 4 independent rows in flight per thread.
+// CTA = 8 warps on 8 interleaved row streams; grid (ceil(cols/256), row chunks).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ a, long long ld, int rows, int cols, float* __restrict__ out) {
-    __shared__ float red[8][64];
+    __shared__ float red[8][256 + 8];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int c0 = blockIdx.x * 64 + 2 * lane;
-    float sx = 0.0f, sy = 0.0f;
+    const int c0 = blockIdx.x * 256 + 8 * lane;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
     if (c0 < cols) {
-        for (int r = blockIdx.y * 8 + w; r < rows; r += gridDim.y * 8) {
-            const float2 v = bf2_to_f2(__ldg(reinterpret_cast<const unsigned*>(a + size_t(r) * ld + c0)));
-            sx += v.x; sy += v.y;
+        const int stride = gridDim.y * 8;
+        int r = blockIdx.y * 8 + w;
+        for (; r + 3 * stride < rows; r += 4 * stride) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(a + size_t(r + u * stride) * ld + c0));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned wd[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float2 f = bf2_to_f2(wd[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+            }
+        }
+        for (; r < rows; r += stride) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(a + size_t(r) * ld + c0));
+            const unsigned wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 f = bf2_to_f2(wd[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
         }
     }
-    red[w][2 * lane] = sx;
-    red[w][2 * lane + 1] = sy;
-    __syncthreads();
-    if (threadIdx.x < 64) {
-        float s = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
-        const int c = blockIdx.x * 64 + threadIdx.x;
-        if (c < cols) atomicAdd(out + c, s);
-    }
+    for (int j = 0; j < 8; ++j) red[w][8 * lane + j] = acc[j];
+    __syncthreads();
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < cols) atomicAdd(out + c, s);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -245,10 +261,13 @@ sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
 // AdamW with weight_decay = 0 (pipeline_utils.py:536), preceded by clip_grad_norm_(max_norm) (train.py:163)
 // and followed by the reference's separate decoupled decay p -= (lr / base_lr) * wd * p on the first
 // `n_decay` elements of the flat buffer (custom_optims.py:37-43; Linear weights are laid out first).
+// hyper (device, so a captured CUDA graph sees new values every replay):
+//   [0] lr  [1] beta1  [2] beta2  [3] eps  [4] 1-beta1^t  [5] 1-beta2^t  [6] decay = lr/base_lr*wd  [7] grad_scale  [8] max_norm
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
-             size_t n_decay, const float* __restrict__ gnorm_sq, float grad_scale, float max_norm, float lr, float beta1,
-             float beta2, float eps, float bc1, float bc2, float decay) {
+             size_t n_decay, const float* __restrict__ gnorm_sq, const float* __restrict__ hyper) {
+    const float lr = hyper[0], beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3], bc1 = hyper[4], bc2 = hyper[5];
+    const float decay = hyper[6], grad_scale = hyper[7], max_norm = hyper[8];
     float clip = 1.0f;
     if (max_norm > 0.0f) {
         const float total = sqrtf(*gnorm_sq) * grad_scale;
@@ -319,10 +338,10 @@ int rgbnm_layernorm_bwd(const void* dy, const void* x, const float* mean, const 
 }
 
 int rgbnm_colsum_bf16(const void* a, long long ld, int rows, int cols, float* out, void* stream) {
-    if (!a || !out || rows < 0 || cols <= 0 || (ld & 1) || (cols & 1)) return RGBNM_ERR_ARG;
+    if (!a || !out || rows < 0 || cols <= 0 || (ld & 7) || (cols & 7)) return RGBNM_ERR_ARG;
     if (rows == 0) return RGBNM_OK;
-    const int gx = (cols + 63) / 64;
-    int gy = (vitk::sms() * 8 + gx - 1) / gx;
+    const int gx = (cols + 255) / 256;
+    int gy = (vitk::sms() * 4 + gx - 1) / gx;
     if (gy > (rows + 7) / 8) gy = (rows + 7) / 8;
     vitk::colsum_kernel<<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(a), ld, rows, cols, out);
@@ -365,15 +384,12 @@ int rgbnm_sumsq_f32(const float* g, long long n, float* out, void* stream) {
 }
 
 int rgbnm_adamw_step(float* p, const float* g, float* m, float* v, long long n, long long n_decay, const float* gnorm_sq,
-                     float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, int step, float decay,
-                     void* stream) {
-    if (!p || !g || !m || !v || n < 0 || step < 1 || (max_norm > 0.0f && !gnorm_sq)) return RGBNM_ERR_ARG;
+                     const float* hyper, void* stream) {
+    if (!p || !g || !m || !v || n < 0 || !hyper || !gnorm_sq) return RGBNM_ERR_ARG;
     if (n == 0) return RGBNM_OK;
-    const float bc1 = 1.0f - powf(beta1, float(step)), bc2 = 1.0f - powf(beta2, float(step));
     long long blocks = (n + 255) / 256;
     const int grid = int(blocks > vitk::sms() * 16 ? vitk::sms() * 16 : blocks);
-    vitk::adamw_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, size_t(n), size_t(n_decay), gnorm_sq,
-                                                                            grad_scale, max_norm, lr, beta1, beta2, eps, bc1, bc2, decay);
+    vitk::adamw_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, size_t(n), size_t(n_decay), gnorm_sq, hyper);
     RGBNM_CUDA_CHECK(cudaGetLastError());
     return RGBNM_OK;
 }

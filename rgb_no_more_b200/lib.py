@@ -42,6 +42,7 @@ SIGNATURES = {
     "rgbnm_k0_fused": (_i, [_vp, _vp, _vp, _vp, C.POINTER(K0Tables), _vp, _vp, _i, _i, _i, _i, _vp]),
     "rgbnm_k0_launch_count": (_i, []),
     "rgbnm_gemm_bf16": (_i, [_vp, _vp]),
+    "rgbnm_attention_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_float, _vp]),
     "rgbnm_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.c_float, _vp]),
     "rgbnm_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "rgbnm_colsum_bf16": (_i, [_vp, C.c_longlong, _i, _i, _vp, _vp]),
@@ -49,8 +50,7 @@ SIGNATURES = {
     "rgbnm_qkv_perm_vec": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rgbnm_qkv_unperm_rows_add": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rgbnm_sumsq_f32": (_i, [_vp, C.c_longlong, _vp, _vp]),
-    "rgbnm_adamw_step": (_i, [_vp, _vp, _vp, _vp, C.c_longlong, C.c_longlong, _vp, C.c_float, C.c_float, C.c_float,
-                              C.c_float, C.c_float, C.c_float, _i, C.c_float, _vp]),
+    "rgbnm_adamw_step": (_i, [_vp, _vp, _vp, _vp, C.c_longlong, C.c_longlong, _vp, _vp, _vp]),
 }
 
 

@@ -1,0 +1,143 @@
+"""One training step of the DCT ViT on one B200 (SURVEY.md 3.1 hot loop, train.py:146-176):
+
+    mixup (cls_transforms.py:135-182, on the embed input -- mixup is a convex combination and the embed tail is
+    affine, so it commutes) -> ViT forward -> soft-label cross entropy -> backward into ONE flat fp32 gradient
+    buffer -> [single NCCL allreduce of that buffer over NVLink, train.py:137's DDP buckets collapsed into one]
+    -> clip_grad_norm_(1.0) + AdamW + decoupled WeightDecay in one fused kernel (train.py:163-172) -> bf16 weight refresh.
+
+The forward/backward part and the optimiser part are captured in CUDA graphs (launch-bound otherwise: ~600 kernel
+launches per step); the learning rate and the mixup lambda live in device memory so replays see fresh values."""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import ops as K
+from . import vit as V
+
+ARCHS = {"vitti": dict(emb_size=192, depth=12, num_heads=3, wd=1e-4), "vits": dict(emb_size=384, depth=12, num_heads=6, wd=3e-4),
+         "vitb": dict(emb_size=768, depth=12, num_heads=12, wd=3e-4)}
+
+
+class TrainStage:
+    def __init__(self, device, arch: str = "vits", batch: int = 256, dtype: str = "bf16", world: int = 1, lr: float = 3e-3,
+                 warmup_steps: int = 10000, total_steps: int = 112590, mixup_alpha: float = 0.2, use_graph: bool = True,
+                 seed: int = 11997733, attention: str = "auto"):
+        if dtype != "bf16":
+            raise NotImplementedError("rgbnm TrainStage: the tcgen05 path computes in bf16 (fp32 accumulation)")
+        cfg = ARCHS[arch]
+        self.dev = torch.device(device)
+        self.B, self.world = batch, world
+        torch.manual_seed(seed)            # same seed on every rank: identical initial replicas, like DDP's broadcast
+        self.model = V.ViT(patch_size=16, emb_size=cfg["emb_size"], depth=cfg["depth"], n_classes=1000, drop_p=0.0,
+                           pixel_space="DCT", ver=1, use_subblock=True, device=self.dev, num_heads=cfg["num_heads"],
+                           head_size=64, attention=attention)
+        self.eng = self.model.prepare(self.dev)
+        self.base_lr, self.wd = lr, cfg["wd"]
+        self.warmup_steps, self.total_steps = warmup_steps, total_steps
+        self.m = torch.zeros_like(self.eng.flat)
+        self.v = torch.zeros_like(self.eng.flat)
+        self.gnorm = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.hyper_host = torch.zeros(9, dtype=torch.float32).pin_memory()
+        self.hyper = torch.zeros(9, dtype=torch.float32, device=self.dev)
+        self.lam_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.lam = torch.zeros(2, dtype=torch.float32, device=self.dev)
+        self.mixup_alpha = mixup_alpha
+        self.step_no = 0
+        self.use_graph = use_graph
+        self.g_fb: Optional[torch.cuda.CUDAGraph] = None
+        self.g_opt: Optional[torch.cuda.CUDAGraph] = None
+        self.x_static = torch.zeros((batch, V.TOKENS, V.IN_FEAT), dtype=torch.bfloat16, device=self.dev)
+        self.y_static = torch.zeros((batch,), dtype=torch.int64, device=self.dev)
+        self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
+        self.launches_per_step = 0
+        self._rng = torch.Generator().manual_seed(seed + 17)
+
+    # ---- pieces ---------------------------------------------------------------------------------------------
+    def _lr(self, it: int) -> float:
+        # linear warm-up (train.py:150-152) then per-iteration cosine annealing (pipeline_utils.py:538)
+        if it < self.warmup_steps:
+            return self.base_lr * (it + 1) / self.warmup_steps
+        t = (it - self.warmup_steps) / max(1, self.total_steps - self.warmup_steps)
+        return 0.5 * self.base_lr * (1.0 + math.cos(math.pi * min(1.0, t)))
+
+    def _fwd_bwd(self):
+        x, y, lam = self.x_static, self.y_static, self.lam
+        # RandomMixup_DCT: batch rolled by one, lambda from a sorted Dirichlet(alpha, alpha) draw
+        xm = (x.float() * lam[0] + x.roll(1, 0).float() * lam[1]).to(torch.bfloat16)
+        onehot = torch.nn.functional.one_hot(y, 1000).float()
+        soft = onehot * lam[0] + onehot.roll(1, 0) * lam[1]
+        logits = self.eng.forward(xm)
+        logp = torch.log_softmax(logits, dim=1)
+        self.loss.copy_(-(soft * logp).sum(1).mean())
+        dlogits = (torch.exp(logp) * soft.sum(1, keepdim=True) - soft) / self.B
+        self.eng.backward(dlogits)
+
+    def _opt(self):
+        self.gnorm.zero_()
+        K.sumsq(self.eng.flat_grad, self.gnorm)
+        K.adamw_step(self.eng.flat, self.eng.flat_grad, self.m, self.v, self.eng.n_decay, self.gnorm, self.hyper)
+        self.eng.refresh_weights()
+
+    def _set_hyper(self):
+        t = self.step_no + 1
+        lr = self._lr(self.step_no)
+        h = self.hyper_host
+        h[0], h[1], h[2], h[3] = lr, 0.9, 0.999, 1e-8
+        h[4], h[5] = 1.0 - 0.9 ** t, 1.0 - 0.999 ** t
+        h[6] = lr / self.base_lr * self.wd
+        # sumsq runs after the SUM allreduce, so the norm and the gradient both carry the factor `world`
+        h[7], h[8] = 1.0 / self.world, 1.0
+        self.hyper.copy_(h, non_blocking=True)
+        lam = torch._sample_dirichlet(torch.tensor([self.mixup_alpha, self.mixup_alpha]), generator=self._rng) \
+            if self.mixup_alpha > 0 else torch.tensor([1.0, 0.0])
+        lam, _ = lam.sort(descending=True)
+        self.lam_host.copy_(lam)
+        self.lam.copy_(self.lam_host, non_blocking=True)
+
+    # ---- public ---------------------------------------------------------------------------------------------
+    def step(self, x: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """x: (B,196,384) bf16 from FusedDCT, labels (B,) int64.  Returns the device scalar loss of this step."""
+        self._set_hyper()
+        self.x_static.copy_(x, non_blocking=True)
+        self.y_static.copy_(labels, non_blocking=True)
+        if not self.use_graph:
+            l0 = self.eng.launches
+            self._fwd_bwd()
+            self._allreduce()
+            self._opt()
+            self.launches_per_step = self.eng.launches - l0 + 2
+        else:
+            if self.g_fb is None:
+                self._capture()
+            self.g_fb.replay()
+            self._allreduce()
+            self.g_opt.replay()
+        self.step_no += 1
+        return self.loss
+
+    def _allreduce(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.eng.flat_grad)          # one flat SUM allreduce; 1/world folded into the optimiser kernel
+
+    def _capture(self):
+        # warm up on a side stream (lazy allocations, cuTensorMap encodes, cuBLAS handles of the tiny head ops)
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._fwd_bwd()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        l0 = self.eng.launches
+        self.g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fb):
+            self._fwd_bwd()
+        l1 = self.eng.launches
+        self.g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_opt):
+            self._opt()
+        self.launches_per_step = (l1 - l0) + (self.eng.launches - l1) + 2

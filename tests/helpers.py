@@ -70,3 +70,24 @@ def assert_only_tie_mismatches(got, ref, exact, what=""):
     # and the CUDA value is always one of the two nearest integers of the exact result
     assert np.all(np.abs(got - exact) <= 0.5 + TIE_EPS), what
     return float((d != 0).mean())
+
+
+def seeded_state_dict(model, seed=11997733):
+    """The weight recipe tools/make_golden.py used for the reference ViT: per key, seeded normal."""
+    sd = {}
+    for k, v in sorted(model.state_dict().items()):
+        g = torch.Generator().manual_seed(seed + sum(ord(ch) * (i + 1) for i, ch in enumerate(k)) % 1000003)
+        if k.endswith("weight") and v.ndim == 2:
+            sd[k] = torch.randn(v.shape, generator=g) * (0.5 / v.shape[1] ** 0.5)
+        elif k.endswith("weight"):
+            sd[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=g)
+        else:
+            sd[k] = 0.05 * torch.randn(v.shape, generator=g)
+    return sd
+
+
+def golden_vit_inputs(seed):
+    g = torch.Generator().manual_seed(int(seed))
+    yf = torch.rand((2, 1, 28, 28, 8, 8), generator=g) * 2 - 1
+    cf = torch.rand((2, 2, 14, 14, 8, 8), generator=g) * 2 - 1
+    return yf, cf

@@ -1,0 +1,204 @@
+"""GPU parity tests of the ViT path (tcgen05 GEMMs, LayerNorm, attention, optimiser) through the C-ABI.
+
+Oracle for the model = outputs of the reference's own `models.plainvit.ViT` (fp32, CPU) committed in
+tests/golden/embed_vit.npz by tools/make_golden.py.  Our path computes in bf16 with fp32 accumulation (the
+reference's `--amp 1 --ampdtype bf16` regime), so tolerances are bf16-sized and written next to each check."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from rgb_no_more_b200 import gemm as G
+from rgb_no_more_b200 import ops as K
+from rgb_no_more_b200 import vit as V
+from tests.helpers import load, seeded_state_dict, golden_vit_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _bf(*shape, scale=1.0):
+    return (torch.randn(*shape, device=DEV) * scale).to(torch.bfloat16)
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).abs().max()) / (float(b.float().abs().max()) + 1e-12)
+
+
+# ---- kernels against plain PyTorch fp32 references of the same op -------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 192, 64), (1000, 1000, 384), (392, 384, 1536)])
+def test_gemm_epilogues(M, N, K):
+    torch.manual_seed(M + N + K)
+    a, w, bias = _bf(M, K), _bf(N, K, scale=K ** -0.5), torch.randn(N, device=DEV)
+    ref = a.float() @ w.float().t()
+    tol = 1e-2                                   # bf16 output rounding (2^-8 relative) on O(1) values
+    assert _rel(G.gemm(a, w, G.EPI_STORE, bias=bias), ref + bias) < tol
+    res = _bf(M, N)
+    assert _rel(G.gemm(a, w, G.EPI_RESIDUAL, bias=bias, aux=res), ref + bias + res.float()) < tol
+    u, f = G.gemm(a, w, G.EPI_GELU, bias=bias)
+    assert _rel(u, ref + bias) < tol and _rel(f, F.gelu(ref + bias)) < tol
+    pre = _bf(M, N)
+    x = pre.float().requires_grad_(True)
+    F.gelu(x).sum().backward()
+    assert _rel(G.gemm(a, w, G.EPI_DGELU, aux=pre), ref * x.grad) < tol
+    assert _rel(G.gemm(a, w, G.EPI_F32, bias=bias), ref + bias) < 1e-5      # fp32 out: accumulation order only
+    if N % 32 == 0:
+        pos = torch.randn(196, N, device=DEV)
+        rows = torch.arange(M, device=DEV) % 196
+        assert _rel(G.gemm(a, w, G.EPI_POSEMB, bias=bias, posemb=pos), ref + bias + pos[rows]) < tol
+
+
+@pytest.mark.parametrize("T,M,N,splits", [(64, 128, 192, 1), (1024, 200, 104, 4), (50176, 384, 384, 16)])
+def test_gemm_wgrad_atomic(T, M, N, splits):
+    torch.manual_seed(T)
+    dy, x = _bf(T, M), _bf(T, N)
+    ref = dy.float().t() @ x.float()
+    out = torch.zeros(M, N, device=DEV)
+    G.gemm(dy, x, G.EPI_WGRAD_ATOMIC, out_f32=out, splits=splits)
+    assert _rel(out, ref) < 1e-4                                             # fp32 accumulate, order differs
+    G.gemm(dy, x, G.EPI_WGRAD_ATOMIC, out_f32=out, splits=splits, alpha=0.5)
+    assert _rel(out, 1.5 * ref) < 1e-4
+
+
+def test_gemm_bad_arguments():
+    a, w = _bf(128, 60), _bf(192, 60)
+    with pytest.raises(Exception):
+        G.gemm(a, w)                                  # K not a multiple of 8: TMA row pitch
+    with pytest.raises(ValueError):
+        G.gemm(a.float(), w)
+
+
+@pytest.mark.parametrize("E", [192, 384, 768])
+def test_layernorm_fwd_bwd(E):
+    torch.manual_seed(E)
+    rows = 1000
+    x = _bf(rows, E, scale=2.0) + 0.5
+    g, b = torch.randn(E, device=DEV), torch.randn(E, device=DEV)
+    y = torch.empty_like(x)
+    mean, rstd = torch.empty(rows, device=DEV), torch.empty(rows, device=DEV)
+    K.layernorm_fwd(x, g, b, y, mean, rstd)
+    xr = x.float().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (E,), gr, br, 1e-5)
+    assert _rel(y, ref) < 1e-2
+    assert float((mean - xr.mean(1)).abs().max()) < 1e-5
+    dy, dres = _bf(rows, E), _bf(rows, E)
+    (ref * dy.float()).sum().backward()
+    dx = torch.empty_like(x)
+    dg, db = torch.zeros(E, device=DEV), torch.zeros(E, device=DEV)
+    K.layernorm_bwd(dy, x, mean, rstd, g, dres, dx, dg, db)
+    assert _rel(dx, xr.grad + dres.float()) < 1e-2
+    assert _rel(dg, gr.grad) < 1e-4 and _rel(db, br.grad) < 1e-4
+
+
+def test_colsum_weightprep_adamw():
+    torch.manual_seed(3)
+    a = _bf(5000, 1152)
+    out = torch.zeros(1152, device=DEV)
+    K.colsum(a, out)
+    assert _rel(out, a.float().sum(0)) < 1e-5
+    # weight prep: plain and qkv-regrouped
+    H, D, E = 6, 64, 384
+    w = torch.randn(3 * H * D, E, device=DEV)
+    wb, wt = torch.empty(3 * H * D, E, dtype=torch.bfloat16, device=DEV), torch.empty(E, 3 * H * D, dtype=torch.bfloat16, device=DEV)
+    K.weight_prep(w, wb, wt, H, D)
+    # reference regrouping: "b n (h d qkv) -> qkv h d" (plainvit.py:447)
+    perm = w.view(H, D, 3, E).permute(2, 0, 1, 3).reshape(3 * H * D, E)
+    assert torch.equal(wb, perm.to(torch.bfloat16)) and torch.equal(wt, perm.to(torch.bfloat16).t().contiguous())
+    wb2, wt2 = torch.empty_like(wb), torch.empty_like(wt)
+    K.weight_prep(w, wb2, wt2)
+    assert torch.equal(wb2, w.to(torch.bfloat16)) and torch.equal(wt2, w.to(torch.bfloat16).t().contiguous())
+    # fused clip + AdamW + decoupled decay against torch (train.py:163-172, custom_optims.py:37-43)
+    n, n_decay = 10000, 6000
+    p0, g0 = torch.randn(n, device=DEV), torch.randn(n, device=DEV) * 0.1
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([p_ref], lr=3e-3, eps=1e-8, weight_decay=0.0)
+    p, m, v = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    gn = torch.zeros(1, device=DEV)
+    for t in range(1, 4):
+        lr = 3e-3 * t / 3
+        for gparam in opt.param_groups:
+            gparam["lr"] = lr
+        p_ref.grad = g0.clone() * t
+        torch.nn.utils.clip_grad_norm_([p_ref], 1.0)
+        opt.step()
+        with torch.no_grad():
+            p_ref[:n_decay] -= (lr / 3e-3) * 1e-4 * p_ref[:n_decay]
+        gn.zero_()
+        K.sumsq(g0 * t, gn)
+        hyper = torch.tensor([lr, 0.9, 0.999, 1e-8, 1 - 0.9 ** t, 1 - 0.999 ** t, lr / 3e-3 * 1e-4, 1.0, 1.0], device=DEV)
+        K.adamw_step(p, g0 * t, m, v, n_decay, gn, hyper)
+    assert float((p - p_ref.detach()).abs().max()) < 1e-5
+
+
+# ---- the model against the reference's own outputs -----------------------------------------------------------
+def _golden_model(attention="auto"):
+    m = V.ViT(patch_size=16, emb_size=192, depth=12, n_classes=1000, drop_p=0.0, num_heads=3, head_size=64,
+              pixel_space="DCT", ver=1, use_subblock=True, attention=attention)
+    m.load_state_dict(seeded_state_dict(m))
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize("attention", ["auto", "torch"])
+def test_vitti_logits_match_reference(attention):
+    g = load("embed_vit.npz")
+    yf, cf = golden_vit_inputs(g["input_seed"])
+    m = _golden_model(attention).eval()
+    with torch.no_grad():
+        logits = m(yf.to(DEV), cf.to(DEV)).cpu()
+    ref = torch.from_numpy(g["logits_vitti"])
+    # bf16 GEMM inputs / activations over 12 layers vs the fp32 reference: <= 2e-2 of the logit range
+    assert logits.shape == ref.shape
+    assert float((logits - ref).abs().max()) < 2e-2 * float(ref.abs().max()), (float((logits - ref).abs().max()), float(ref.abs().max()))
+    assert torch.equal(logits.argmax(1), ref.argmax(1))
+
+
+def test_vitti_training_gradients_match_reference():
+    g = load("embed_vit.npz")
+    yf, cf = golden_vit_inputs(g["input_seed"])
+    m = _golden_model().train()
+    labels = torch.zeros((2, 1000), device=DEV)
+    labels[0, 3], labels[0, 7], labels[1, 999] = 0.7, 0.3, 1.0
+    loss = torch.nn.CrossEntropyLoss()(m(yf.to(DEV), cf.to(DEV)), labels)
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 2e-2 * abs(float(g["loss"]))
+    sd = dict(m.named_parameters())
+    for k in ("patchembed.projection.0.weight", "encoder.0.0.fn.eb_mha.qkv.weight", "encoder.11.1.fn.eb_ffb.3.bias",
+              "classhead.ch_linear2.weight", "encoder.5.0.fn.eb_lrnorm1.weight"):
+        got = sd[k].grad.reshape(-1).float().cpu()
+        ref = torch.from_numpy(g["grad:" + k])
+        n = ref.numel()
+        cos = float(F.cosine_similarity(got[:n], ref, dim=0))
+        # bf16 activations/gradients through 12 layers: direction within 1e-2, norm within 5 %
+        assert cos > 0.99, (k, cos)
+        assert abs(float(sd[k].grad.norm()) - float(g["gradnorm:" + k])) < 5e-2 * float(g["gradnorm:" + k]), k
+
+
+def test_state_dict_roundtrip_and_autograd_surface():
+    m = _golden_model()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randn(3, 196, 384, device=DEV).to(torch.bfloat16)
+    y1 = m(x)
+    m2 = _golden_model()
+    m2.load_state_dict(sd)
+    assert torch.equal(m2(x), y1)
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    y1.square().mean().backward()
+    torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+    opt.step()
+    opt.zero_grad()
+    y2 = m(x)                                  # weights changed -> bf16 copies refreshed
+    assert not torch.equal(y1, y2)
+
+
+def test_train_stage_loss_decreases():
+    from rgb_no_more_b200 import train_step as TS
+    st = TS.TrainStage(DEV, arch="vitti", batch=16, warmup_steps=1, total_steps=1000, mixup_alpha=0.0, use_graph=True)
+    torch.manual_seed(0)
+    x = (torch.randn(16, 196, 384, device=DEV) * 0.3).to(torch.bfloat16)
+    y = torch.arange(16, device=DEV) % 4
+    losses = [float(st.step(x, y)) for _ in range(30)]
+    assert losses[-1] < 0.5 * losses[0], losses[::5]
+    assert all(math.isfinite(v) for v in losses)

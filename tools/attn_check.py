@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""GPU diagnostic for the tcgen05 attention kernels against torch (prints error statistics and timings)."""
+import math, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.nn.functional as F
+from rgb_no_more_b200 import attention as A
+
+dev = "cuda:0"
+torch.manual_seed(0)
+fails = 0
+
+
+def check(B, H, E, do_time=False):
+    global fails
+    D, N = 64, 196
+    scale = 1.0 / math.sqrt(E)
+    qkv = (torch.randn(B * N, 3 * H * D, device=dev) * 2.0).to(torch.bfloat16)
+    o = torch.zeros(B * N, H * D, dtype=torch.bfloat16, device=dev)
+    lse = torch.zeros(B, H, N, device=dev)
+    A.forward(qkv, o, lse, B, H, D, scale, backend="b200")
+    torch.cuda.synchronize()
+    v = qkv.float().view(B, N, 3, H, D).permute(2, 0, 3, 1, 4)
+    s = torch.einsum("bhqd,bhkd->bhqk", v[0], v[1]) * scale
+    ref = torch.einsum("bhqk,bhkd->bhqd", torch.softmax(s, -1), v[2]).transpose(1, 2).reshape(B * N, H * D)
+    lref = torch.logsumexp(s, -1)
+    d = (o.float() - ref).abs()
+    dl = (lse - lref).abs()
+    bad = float(d.max()) > 2e-2 * float(ref.abs().max()) or float(dl.max()) > 1e-2 or not torch.isfinite(o.float()).all()
+    print(f"{'FAIL' if bad else 'ok  '} fwd B{B} H{H}: max|do|={float(d.max()):.4g} (ref max {float(ref.abs().max()):.3g}) "
+          f"mean|do|={float(d.mean()):.3g} max|dlse|={float(dl.max()):.3g}", flush=True)
+    if bad:
+        fails += 1
+        idx = torch.nonzero(d > 2e-2 * ref.abs().max())
+        print("   n_bad", idx.shape[0], "of", d.numel(), "first", idx[:8].tolist())
+        rows = torch.unique(idx[:, 0] % N)[:20].tolist(); cols = torch.unique(idx[:, 1])[:20].tolist()
+        print("   bad token rows", rows, "bad cols", cols)
+        print("   sample got", o[0, :8].float().tolist(), "\n   sample ref", ref[0, :8].tolist())
+    if do_time:
+        for name, be in (("b200", "b200"), ("torch-sdpa", "torch")):
+            for _ in range(3):
+                A.forward(qkv, o, lse, B, H, D, scale, backend=be)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                A.forward(qkv, o, lse, B, H, D, scale, backend=be)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            print(f"time fwd {name} B{B} H{H}: {ms*1e3:.1f} us  {4*B*H*N*N*D/ms/1e9:.1f} TFLOP/s (algorithmic)", flush=True)
+
+
+check(1, 1, 64)
+check(2, 3, 192)
+check(5, 6, 384)
+check(256, 6, 384, do_time=True)
+print("FAILS", fails)
+sys.exit(1 if fails else 0)
