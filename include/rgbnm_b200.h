@@ -203,6 +203,11 @@ int rgbnm_adamw_step(float* p, const float* g, float* m, float* v, long long n, 
  * (log-sum-exp of the scaled scores, for backward).  N = 196, D = 64. */
 int rgbnm_attention_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int D, float scale, void* stream);
 
+/* (K8) attention core, backward: dqkv bf16 [B][N][3*H*D] = [dq | dk | dv] from dout bf16 [B][N][H*D]; P is recomputed from
+ * qkv and lse; dvec fp32 [B][H][N] is scratch for rowsum(dout * o).  Three launches (prep, dQ kernel, dK/dV kernel). */
+int rgbnm_attention_bwd(const void* dout, const void* qkv, const void* o, const float* lse, void* dqkv, float* dvec, int B,
+                        int N, int H, int D, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,13 +44,16 @@ def forward(qkv, o, lse, B, H, D, scale, backend="auto"):
     o.view(B, -1, H, D).copy_(out.transpose(1, 2))
 
 
-def backward(do, qkv, o, lse, dqkv, B, H, D, scale, backend="auto"):
+def backward(do, qkv, o, lse, dqkv, B, H, D, scale, backend="auto", dvec=None):
     if backend == "auto":
         backend = "b200" if _have_b200() else "torch"
-    if backend == "b200" and hasattr(_lib.load(), "rgbnm_attention_bwd"):
+    if backend == "b200":
         L = _lib.load()
-        _lib.check(L.rgbnm_attention_bwd(do.data_ptr(), qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B,
-                                         qkv.shape[0] // B, H, D, C.c_float(scale), _lib.stream_ptr()), "rgbnm_attention_bwd")
+        if dvec is None:
+            dvec = torch.empty((B, H, qkv.shape[0] // B), dtype=torch.float32, device=qkv.device)
+        _lib.check(L.rgbnm_attention_bwd(do.data_ptr(), qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                                         dvec.data_ptr(), B, qkv.shape[0] // B, H, D, C.c_float(scale), _lib.stream_ptr()),
+                   "rgbnm_attention_bwd")
         return
     with torch.enable_grad():
         leaf = qkv.detach().requires_grad_(True)

@@ -60,8 +60,9 @@ struct Smem {
 struct GeluParts { float cdf, pdf; };
 __device__ __forceinline__ GeluParts gelu_parts(float x) {
     const float u = fabsf(x) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
-    const float ex = exp2f(x * x * -0.72134752044448170f);          // exp(-x^2 / 2)
+    float t, ex;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(x * x * -0.72134752044448170f));   // exp(-x^2 / 2)
     float poly = fmaf(t, 1.061405429f, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);

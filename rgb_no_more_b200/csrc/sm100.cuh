@@ -15,7 +15,7 @@ namespace sm100 {
 // Debug guard: a wait that spins longer than this many polls traps instead of hanging the GPU
 // (a hung kernel costs a whole gpurun slot).  ~2^28 polls of >= 20 ns each is > 5 s.
 #ifndef RGBNM_MBAR_SPIN_LIMIT
-#define RGBNM_MBAR_SPIN_LIMIT (1u << 28)
+#define RGBNM_MBAR_SPIN_LIMIT (1u << 24)
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }

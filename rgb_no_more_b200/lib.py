@@ -43,6 +43,7 @@ SIGNATURES = {
     "rgbnm_k0_launch_count": (_i, []),
     "rgbnm_gemm_bf16": (_i, [_vp, _vp]),
     "rgbnm_attention_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_float, _vp]),
+    "rgbnm_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.c_float, _vp]),
     "rgbnm_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.c_float, _vp]),
     "rgbnm_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "rgbnm_colsum_bf16": (_i, [_vp, C.c_longlong, _i, _i, _vp, _vp]),

@@ -192,7 +192,8 @@ class ViTEngine:
                          rstdH=torch.empty(M, **f32),
                          # backward scratch (shared by all layers)
                          dA=torch.empty((M, E), **bf), dB=torch.empty((M, E), **bf), dC=torch.empty((M, E), **bf),
-                         dU=torch.empty((M, 4 * E), **bf), dO=torch.empty((M, HD), **bf), dQKV=torch.empty((M, 3 * HD), **bf))
+                         dU=torch.empty((M, 4 * E), **bf), dO=torch.empty((M, HD), **bf), dQKV=torch.empty((M, 3 * HD), **bf),
+                         dvec=torch.empty((B, self.H, TOKENS), **f32))
         self.batch = B
 
     # -- attention ------------------------------------------------------------------------------------
@@ -203,7 +204,8 @@ class ViTEngine:
 
     def _attn_bwd(self, do: torch.Tensor, qkv: torch.Tensor, o: torch.Tensor, lse: torch.Tensor, dqkv: torch.Tensor, B: int) -> None:
         from . import attention as A
-        A.backward(do, qkv, o, lse, dqkv, B, self.H, self.D, 1.0 / math.sqrt(self.E), backend=self.attention_backend)
+        A.backward(do, qkv, o, lse, dqkv, B, self.H, self.D, 1.0 / math.sqrt(self.E), backend=self.attention_backend,
+                   dvec=self.bufs["dvec"])
         self.launches += 3
 
     # -- forward ------------------------------------------------------------------------------------

@@ -95,3 +95,30 @@ def test_embed_input_bit_exact_permutation():
     # chroma part is a pure permutation -> bit exact; luma part goes through A16 X A16^T
     assert np.array_equal(e[..., 256:], ref[..., 256:])
     assert np.abs(e[..., :256] - ref[..., :256]).max() < 1e-5
+
+
+def test_vit_oracle_matches_reference():
+    """oracle/vit_oracle.py against the real pvit.ViT outputs in embed_vit.npz (fp32 CPU both sides)."""
+    from oracle import vit_oracle as VO
+    from tests.helpers import seeded_state_dict, golden_vit_inputs
+    from rgb_no_more_b200 import vit as V
+    g = load("embed_vit.npz")
+    shell = V.ViT(patch_size=16, emb_size=192, depth=12, n_classes=1000, drop_p=0.0, num_heads=3, head_size=64,
+                  pixel_space="DCT", ver=1, use_subblock=True)           # only used for the key/shape list
+    sd = seeded_state_dict(shell)
+    yf, cf = golden_vit_inputs(g["input_seed"])
+    emb_in = O.embed_input(yf, cf)
+    assert np.abs(VO.tokens(sd, emb_in)[0].numpy() - g["tokens"]).max() < 2e-5
+    assert np.abs(VO.forward(sd, yf, cf, upto_block=1)[0].numpy() - g["after_block0"]).max() < 5e-5
+    logits = VO.forward(sd, yf, cf)
+    assert np.abs(logits.numpy() - g["logits_vitti"]).max() < 2e-4
+    labels = torch.zeros((2, 1000))
+    labels[0, 3], labels[0, 7], labels[1, 999] = 0.7, 0.3, 1.0
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss = torch.nn.CrossEntropyLoss()(VO.forward(params, yf, cf), labels)
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 1e-4
+    for k in ("patchembed.projection.0.weight", "encoder.0.0.fn.eb_mha.qkv.weight", "encoder.11.1.fn.eb_ffb.3.bias",
+              "classhead.ch_linear2.weight", "encoder.5.0.fn.eb_lrnorm1.weight"):
+        got = params[k].grad.reshape(-1)[:4096].numpy()
+        assert np.abs(got - g["grad:" + k]).max() < 1e-4 * max(1.0, np.abs(g["grad:" + k]).max()), k

@@ -36,7 +36,39 @@ def check(B, H, E, do_time=False):
         rows = torch.unique(idx[:, 0] % N)[:20].tolist(); cols = torch.unique(idx[:, 1])[:20].tolist()
         print("   bad token rows", rows, "bad cols", cols)
         print("   sample got", o[0, :8].float().tolist(), "\n   sample ref", ref[0, :8].tolist())
+    # ---- backward ----
+    do = torch.randn(B * N, H * D, device=dev).to(torch.bfloat16)
+    dqkv = torch.zeros_like(qkv)
+    A.backward(do, qkv, o, lse, dqkv, B, H, D, scale, backend="b200")
+    torch.cuda.synchronize()
+    leaf = qkv.float().requires_grad_(True)
+    vv = leaf.view(B, N, 3, H, D).permute(2, 0, 3, 1, 4)
+    ss = torch.einsum("bhqd,bhkd->bhqk", vv[0], vv[1]) * scale
+    oo = torch.einsum("bhqk,bhkd->bhqd", torch.softmax(ss, -1), vv[2]).transpose(1, 2).reshape(B * N, H * D)
+    (gref,) = torch.autograd.grad(oo, leaf, do.float())
+    HDs = H * D
+    for nm, sl in (("dq", slice(0, HDs)), ("dk", slice(HDs, 2 * HDs)), ("dv", slice(2 * HDs, 3 * HDs))):
+        dd = (dqkv[:, sl].float() - gref[:, sl]).abs()
+        rmax = float(gref[:, sl].abs().max())
+        bad = float(dd.max()) > 3e-2 * rmax or not torch.isfinite(dqkv.float()).all()
+        print(f"{'FAIL' if bad else 'ok  '} bwd {nm} B{B} H{H}: max|d|={float(dd.max()):.4g} (ref max {rmax:.3g}) mean|d|={float(dd.mean()):.3g}", flush=True)
+        if bad:
+            fails += 1
+            idx = torch.nonzero(dd > 3e-2 * rmax)
+            print("   n_bad", idx.shape[0], "of", dd.numel(), "first", idx[:8].tolist())
+            print("   bad token rows", torch.unique(idx[:, 0] % N)[:24].tolist(), "bad cols", torch.unique(idx[:, 1])[:24].tolist())
+            print("   got", dqkv[:, sl][0, :6].float().tolist(), "\n   ref", gref[:, sl][0, :6].tolist())
     if do_time:
+        for name, be in (("b200", "b200"), ("torch-sdpa", "torch")):
+            for _ in range(3):
+                A.backward(do, qkv, o, lse, dqkv, B, H, D, scale, backend=be)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                A.backward(do, qkv, o, lse, dqkv, B, H, D, scale, backend=be)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            print(f"time bwd {name} B{B} H{H}: {ms*1e3:.1f} us", flush=True)
         for name, be in (("b200", "b200"), ("torch-sdpa", "torch")):
             for _ in range(3):
                 A.forward(qkv, o, lse, B, H, D, scale, backend=be)
