@@ -163,8 +163,9 @@ typedef struct {
     int M, N, K;
     int epilogue;               /* enum rgbnm_epilogue */
     int pos_period;
-    int splits;
+    int splits;                 /* WGRAD_ATOMIC: split count over the reduction; <= 0 = chosen by the library */
     float alpha;
+    int trans_out;              /* WGRAD_ATOMIC: out_f32[n * ldo + m] += ... (lets the caller put the longer side on M) */
 } rgbnm_gemm_args;
 
 int rgbnm_gemm_bf16(const rgbnm_gemm_args* args, void* stream);

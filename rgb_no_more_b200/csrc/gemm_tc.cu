@@ -425,7 +425,8 @@ static int launch(const rgbnm_gemm_args& a, cudaStream_t st) {
 
 }  // namespace gemm
 
-extern "C" int rgbnm_gemm_bf16(const rgbnm_gemm_args* args, void* stream) {
+// Single-CTA (cta_group::1) kernel: superseded by gemm2_tc.cu, kept selectable (RGBNM_GEMM_V1=1) for A/B measurements.
+int rgbnm_gemm_bf16_v1(const rgbnm_gemm_args* args, void* stream) {
     using namespace gemm;
     if (!args || !args->A || !args->B || args->M <= 0 || args->N <= 0 || args->K <= 0) return RGBNM_ERR_ARG;
     const rgbnm_gemm_args& a = *args;

@@ -19,7 +19,7 @@ class GemmArgs(C.Structure):
                 ("bias", C.c_void_p), ("posemb", C.c_void_p), ("out_f32", C.c_void_p),
                 ("lda", C.c_longlong), ("ldb", C.c_longlong), ("ldc", C.c_longlong), ("ldaux", C.c_longlong),
                 ("ldo", C.c_longlong), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("epilogue", C.c_int),
-                ("pos_period", C.c_int), ("splits", C.c_int), ("alpha", C.c_float)]
+                ("pos_period", C.c_int), ("splits", C.c_int), ("alpha", C.c_float), ("trans_out", C.c_int)]
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -33,10 +33,12 @@ def _check_bf16(t, name):
 
 def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int = EPI_STORE, bias: Optional[torch.Tensor] = None,
          aux: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
-         posemb: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None, splits: int = 1,
-         alpha: float = 1.0):
+         posemb: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None, splits: int = 0,
+         alpha: float = 1.0, trans_out: bool = False):
     """Forward / dgrad form: a [M,K], b [N,K] (both row-major, K contiguous) -> out [M,N].
-    For EPI_WGRAD_ATOMIC: a [T,M] and b [T,N] (T = reduction/token index) -> out_f32 [M,N] += alpha * a^T b."""
+    For EPI_WGRAD_ATOMIC: a [T,M] and b [T,N] (T = reduction/token index) -> out_f32 [M,N] += alpha * a^T b
+    (trans_out: out_f32 [N,M] += alpha * b^T a, so the caller can put the longer side on the 256-row tile axis);
+    splits = 0 lets the library pick the split count over T."""
     L = _lib.load()
     _check_bf16(a, "a")
     _check_bf16(b, "b")
@@ -55,10 +57,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int = EPI_STORE, bias: Opti
     args.epilogue = epilogue
     args.splits = splits
     args.alpha = alpha
+    args.trans_out = 1 if trans_out else 0
     ret = None
     if epilogue in (EPI_WGRAD_ATOMIC, EPI_F32):
         if out_f32 is None:
-            out_f32 = torch.zeros((M, N), dtype=torch.float32, device=a.device)
+            out_f32 = torch.zeros((N, M) if trans_out else (M, N), dtype=torch.float32, device=a.device)
         if out_f32.dtype != torch.float32 or out_f32.stride(-1) != 1:
             raise ValueError("rgbnm gemm: out_f32 must be fp32 with unit inner stride")
         args.out_f32, args.ldo = out_f32.data_ptr(), out_f32.stride(0)

@@ -22,6 +22,7 @@ output, plainvit.py:478), fp32 master weights.  There is no CPU fallback."""
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 from typing import Dict, List, Optional
 
@@ -33,6 +34,7 @@ from . import gemm as G
 from . import lib as _lib
 from . import ops as K
 
+_V1 = bool(os.environ.get("RGBNM_GEMM_V1"))      # single-CTA GEMM kernel (A/B measurements only)
 TOKENS = 196          # 14 x 14 patches of 16 x 16 pixels (224 px input)
 IN_FEAT = 384         # 256 luma + 64 Cb + 64 Cr coefficients per patch
 
@@ -250,6 +252,13 @@ class ViTEngine:
         return F.linear(z, self.head2[0].data, self.head2[1].data)
 
     # -- backward -----------------------------------------------------------------------------------
+    def _wgrad_gemm(self, dy: torch.Tensor, x: torch.Tensor, gw: torch.Tensor, splits: int) -> None:
+        # gw [out, in] += dy^T x.  The CTA-pair kernel tiles 256 (M) x 128 (N): put the longer side on M.
+        if x.shape[1] > dy.shape[1] and not _V1:
+            self._gemm(x, dy, G.EPI_WGRAD_ATOMIC, out_f32=gw, splits=splits, trans_out=True)
+        else:
+            self._gemm(dy, x, G.EPI_WGRAD_ATOMIC, out_f32=gw, splits=splits)
+
     def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, lin: _Lin, splits: int) -> None:
         """dW += dy^T x, db += colsum(dy) into the flat gradient buffer (reference parameter order)."""
         if lin.qkv_heads:
@@ -257,14 +266,14 @@ class ViTEngine:
             gw, gb, tmp = self.qkv_gw, self.qkv_gb, self.qkv_tmp
             gw.zero_()
             gb.zero_()
-            self._gemm(dy, x, G.EPI_WGRAD_ATOMIC, out_f32=gw, splits=splits)
+            self._wgrad_gemm(dy, x, gw, splits)
             K.colsum(dy, gb)
             K.qkv_unperm_rows_add(gw, self.grad_of(lin.weight), self.H, self.D)
             K.qkv_perm_vec(gb, tmp, self.H, self.D, inverse=True)
             self.grad_of(lin.bias).add_(tmp)
             self.launches += 3
         else:
-            self._gemm(dy, x, G.EPI_WGRAD_ATOMIC, out_f32=self.grad_of(lin.weight), splits=splits)
+            self._wgrad_gemm(dy, x, self.grad_of(lin.weight), splits)
             K.colsum(dy, self.grad_of(lin.bias))
             self.launches += 1
 
@@ -275,7 +284,7 @@ class ViTEngine:
         M, E = B * TOKENS, self.E
         if zero_grad:
             self.flat_grad.zero_()
-        splits = max(1, min(16, (M // 64) // 8))
+        splits = max(1, min(16, (M // 64) // 8)) if _V1 else 0       # 0: chosen by the library (whole waves of CTA pairs)
         # ---- head (torch ops on B x E) ----
         z, pooled = bufs["z"], bufs["pooled"]
         w2, w1 = self.head2[0].data, self.head1[0].data

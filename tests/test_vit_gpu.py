@@ -60,6 +60,10 @@ def test_gemm_wgrad_atomic(T, M, N, splits):
     assert _rel(out, ref) < 1e-4                                             # fp32 accumulate, order differs
     G.gemm(dy, x, G.EPI_WGRAD_ATOMIC, out_f32=out, splits=splits, alpha=0.5)
     assert _rel(out, 1.5 * ref) < 1e-4
+    # transposed output (the caller puts the longer side on the 256-row tile axis), library-chosen split count
+    out_t = torch.zeros(N, M, device=DEV)
+    G.gemm(dy, x, G.EPI_WGRAD_ATOMIC, out_f32=out_t, splits=0, trans_out=True)
+    assert _rel(out_t, ref.t()) < 1e-4
 
 
 def test_gemm_bad_arguments():

@@ -60,6 +60,10 @@ def run_wgrad(T, M, N, splits):
     report(f"WGRAD T{T} M{M} N{N} splits{splits}", out, ref, 5e-3)
     G.gemm(dy, x, G.EPI_WGRAD_ATOMIC, out_f32=out, splits=splits, alpha=0.5)
     report(f"WGRAD accumulate alpha", out, 1.5 * ref, 5e-3)
+    if not os.environ.get("RGBNM_GEMM_V1"):
+        outT = torch.zeros(N, M, device=dev)
+        G.gemm(dy, x, G.EPI_WGRAD_ATOMIC, out_f32=outT, splits=0, trans_out=True)
+        report(f"WGRAD trans_out auto-splits T{T} M{M} N{N}", outT, ref.t(), 5e-3)
 
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -74,10 +78,12 @@ if which in ("all", "wgrad"):
 if which in ("all", "big"):
     run_case(50176, 1152, 384)
     run_wgrad(50176, 1536, 384, 16)
+    run_case(50176, 1536, 384)
     # timing at the ViT-S shapes (B=256)
     shapes = [("qkv", 50176, 1152, 384, G.EPI_STORE), ("proj", 50176, 384, 384, G.EPI_RESIDUAL),
               ("fc1", 50176, 1536, 384, G.EPI_GELU), ("fc2", 50176, 384, 1536, G.EPI_RESIDUAL),
-              ("dfc1", 50176, 1536, 384, G.EPI_DGELU)]
+              ("dfc1", 50176, 1536, 384, G.EPI_DGELU), ("dfc2", 50176, 384, 1536, G.EPI_STORE),
+              ("dqkv", 50176, 384, 1152, G.EPI_STORE), ("dproj", 50176, 384, 384, G.EPI_STORE)]
     for name, M, N, K, epi in shapes:
         a, w = mk(M, K), mk(N, K, K ** -0.5)
         bias = torch.randn(N, device=dev)
@@ -99,17 +105,29 @@ if which in ("all", "big"):
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         print(f"     cublas plain {name}: {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
-    dy, x = mk(50176, 1536), mk(50176, 384)
-    out = torch.zeros(1536, 384, device=dev)
-    for sp in (8, 16, 28):
-        G.gemm(dy, x, G.EPI_WGRAD_ATOMIC, out_f32=out, splits=sp)
+    for name, Mo, No in (("fc1", 1536, 384), ("qkv", 1152, 384), ("proj", 384, 384)):
+        dy, x = mk(50176, Mo), mk(50176, No)
+        out = torch.zeros(Mo, No, device=dev)
+        for sp in ((0, 2, 4, 8) if not os.environ.get("RGBNM_GEMM_V1") else (8, 16)):
+            G.gemm(dy, x, G.EPI_WGRAD_ATOMIC, out_f32=out, splits=sp)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                G.gemm(dy, x, G.EPI_WGRAD_ATOMIC, out_f32=out, splits=sp)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            print(f"time wgrad {name} splits {sp}: {ms*1e3:.1f} us  {2*50176*Mo*No/ms/1e9:.1f} TFLOP/s", flush=True)
+    if not os.environ.get("RGBNM_GEMM_V1"):
+        x, dy = mk(50176, 1536), mk(50176, 384)          # fc2: the longer side is the input -> transposed form
+        out = torch.zeros(384, 1536, device=dev)
+        G.gemm(x, dy, G.EPI_WGRAD_ATOMIC, out_f32=out, splits=0, trans_out=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
-            G.gemm(dy, x, G.EPI_WGRAD_ATOMIC, out_f32=out, splits=sp)
+            G.gemm(x, dy, G.EPI_WGRAD_ATOMIC, out_f32=out, splits=0, trans_out=True)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        print(f"time wgrad fc1 splits {sp}: {ms*1e3:.1f} us  {2*50176*1536*384/ms/1e9:.1f} TFLOP/s", flush=True)
+        print(f"time wgrad fc2 (trans_out) auto: {ms*1e3:.1f} us  {2*50176*1536*384/ms/1e9:.1f} TFLOP/s", flush=True)
 torch.cuda.synchronize()
 print("FAILS", fails)
 sys.exit(1 if fails else 0)
