@@ -250,22 +250,24 @@ def run_ours(args):
                                    "algorithmic_bytes_per_launch": alg_eval, "kernel_ms": ms_eval,
                                    "images_per_s": B / (ms_eval * 1e-3)},
     }
-    if world == 1:
-        line["cpu_baseline"] = cpu_baseline(args, sample_images=16, threads=1)
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------
 # CPU legs (oracle port of the reference path) -- the only place bench.py touches oracle/
+#
+# The reference's own pipeline for this workload is: DataLoader worker processes running the DCT transforms one image
+# at a time with one torch thread each (datasets.py:542-556, pipeline_utils.py:125), then the model's training step
+# (train.py:146-176) in the main process with every core.  The CPU arm restates exactly that on a bounded sample:
+# oracle/dct_oracle.transform_embed in `cores` forked workers -> mixup -> oracle/vit_oracle.train_step (ViT of the
+# benchmarked arch, fp32) on all cores.  /root/reference itself cannot be installed.
 # ----------------------------------------------------------------------------------------------
 def _cpu_transform_worker(job):
     from oracle import dct_oracle as O
-    torch.set_num_threads(1)
     y, c, q, plan, filters = job
     return O.transform_embed(y, c, q, plan, filters)
-
-
-_POOL = {}
 
 
 def _cpu_jobs(n_images: int):
@@ -283,37 +285,72 @@ def _cpu_jobs(n_images: int):
 
 def _cpu_chunk(jobs):
     torch.set_num_threads(1)
-    acc = 0.0
-    for j in jobs:
-        acc += float(_cpu_transform_worker(j)[0, 0])     # keep the result alive; return a scalar, like a loss
-    return acc
+    return torch.stack([_cpu_transform_worker(j) for j in jobs]) if jobs else torch.zeros((0, 196, 384))
 
 
-def cpu_path_images_per_s(args, n_images: int, threads: int):
-    """Reference CPU data path (oracle restatement) on `n_images` images with `threads` persistent worker
-    processes (the reference's DataLoader-worker model, datasets.py:542-556, one torch thread each)."""
-    jobs = _cpu_jobs(n_images)
-    if threads <= 1:
-        _cpu_chunk(jobs[:2])
-        t0 = time.perf_counter()
-        _cpu_chunk(jobs)
-        return n_images / (time.perf_counter() - t0), None
+def _cpu_state_dict(arch: str):
+    from rgb_no_more_b200 import train_step as TS, vit as V
+    cfg = TS.ARCHS[arch]
+    torch.manual_seed(11997733)
+    m = V.ViT(patch_size=16, emb_size=cfg["emb_size"], depth=cfg["depth"], n_classes=1000, drop_p=0.0, pixel_space="DCT",
+              ver=1, use_subblock=True, device="cpu", num_heads=cfg["num_heads"], head_size=64)     # parameters only, never run
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}, cfg["wd"]
+
+
+def cpu_train_steps(args, n_images: int, cores: int, steps: int, warmup: int):
+    """`warmup + steps` CPU training steps over the same `n_images`-image sample; returns seconds per timed step
+    and the split (data path, model)."""
     import multiprocessing as mp
-    if threads not in _POOL:
-        _POOL[threads] = mp.get_context("fork").Pool(threads)
-    pool = _POOL[threads]
-    chunks = [jobs[i::threads] for i in range(threads)]
-    pool.map(_cpu_chunk, [ch[:1] for ch in chunks])         # warm the workers
-    t0 = time.perf_counter()
-    pool.map(_cpu_chunk, chunks)
-    return n_images / (time.perf_counter() - t0), None
+    from oracle import vit_oracle as VO
+    jobs = _cpu_jobs(n_images)
+    pool = mp.get_context("fork").Pool(cores) if cores > 1 else None      # forked before the parent spins up its torch threads
+    try:
+        chunks = [jobs[i::cores] for i in range(cores)]
+        sd, wd = _cpu_state_dict(args.arch)
+        torch.set_num_threads(cores)
+        state, labels = {}, torch.arange(n_images) % 1000
+        gen = torch.Generator().manual_seed(5)
+        t_data, t_model = [], []
+        for s in range(warmup + steps):
+            t0 = time.perf_counter()
+            parts = pool.map(_cpu_chunk, chunks) if pool is not None else [_cpu_chunk(jobs)]
+            x = torch.cat([p_ for p_ in parts if p_.shape[0]])
+            t1 = time.perf_counter()
+            lam = torch._sample_dirichlet(torch.tensor([0.2, 0.2]), generator=gen).sort(descending=True)[0]
+            onehot = torch.nn.functional.one_hot(labels, 1000).float()
+            x = lam[0] * x + lam[1] * x.roll(1, 0)                                        # RandomMixup_DCT (cls_transforms.py:135-182)
+            soft = lam[0] * onehot + lam[1] * onehot.roll(1, 0)
+            VO.train_step(sd, x.reshape(n_images, 14, 14, 384), soft, state, lr=3e-3 * (s + 1) / 10000, wd=wd)
+            t2 = time.perf_counter()
+            if s >= warmup:
+                t_data.append(t1 - t0)
+                t_model.append(t2 - t1)
+        return float(np.mean(t_data) + np.mean(t_model)), float(np.mean(t_data)), float(np.mean(t_model))
+    finally:
+        if pool is not None:
+            pool.close()
+            pool.join()
 
 
-def cpu_baseline(args, sample_images: int, threads: int):
-    ips, _ = cpu_path_images_per_s(args, sample_images, threads)
-    return {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{sample_images} images of the same workload through oracle/dct_oracle.py "
-                      f"(dequant->crop->resize->flip->RandAugment->ToRange->embed input), {threads} thread(s)"}
+def _cpu_desc(args, n, cores, t_data, t_model):
+    return (f"{n} images per step of the same workload ({args.arch} DCT train step, RandAugment num_ops=2 magnitude=9): "
+            f"oracle/dct_oracle.py data path in {cores} worker processes ({t_data * 1e3:.0f} ms) + oracle/vit_oracle.py "
+            f"fp32 forward/backward/AdamW on {cores} torch threads ({t_model * 1e3:.0f} ms)")
+
+
+def cpu_baseline(args):
+    """Our arm's `cpu_baseline`: the reference arm below, run once in a fresh process (this one already holds a CUDA
+    context and a warm torch thread pool -- forking it is not safe) on a smaller sample."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1", "--arch", args.arch,
+           "--cpu-sample", str(args.cpu_sample)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+    for line in reversed(out.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)["cpu_baseline"]
+    return {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "cpu leg failed: " + out.stderr[-300:]}
 
 
 def run_reference(args):
@@ -322,22 +359,29 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = max(cores * 16, 64)
-    times = []
-    for s in range(args.warmup + args.steps):
-        ips, _ = cpu_path_images_per_s(args, n, cores)
-        if s >= args.warmup:
-            times.append(n / ips)
-    sec = float(np.mean(times))
+    n = args.cpu_sample
+    sec, t_data, t_model = cpu_train_steps(args, n, cores, args.steps, args.warmup)
     val = n / sec
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"reference CPU data path (oracle port), bounded sample of {n} images/step of the same "
-                                   f"workload (batch {args.batch}, RandAugment num_ops=2 magnitude=9)"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{n} images per step"},
+            "config": {"workload": f"reference CPU path (oracle port) of the {args.arch} DCT train step, bounded sample of {n} "
+                                   f"images/step (our arm: batch {args.batch}/GPU), RandAugment num_ops=2 magnitude=9",
+                       "cpu_model": _cpu_model()},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": _cpu_desc(args, n, cores, t_data, t_model)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def _cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def main():
@@ -351,20 +395,16 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--stage", default="auto", choices=["auto", "k0", "train"])
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly (for ncu launch lists)")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="images per CPU step of the reference arm")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.stage == "auto":
         args.stage = "train" if os.path.exists(os.path.join(ROOT, "rgb_no_more_b200", "train_step.py")) else "k0"
-    try:
-        if args.impl == "reference":
-            run_reference(args)
-        else:
-            run_ours(args)
-    finally:
-        for pool in _POOL.values():
-            pool.close()
-            pool.join()
-        _POOL.clear()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
 
 
 if __name__ == "__main__":

@@ -1,4 +1,4 @@
-// Attention core of the DCT ViT on tcgen05 tensor cores (sm_100a), forward:
+// Attention core of the DCT ViT on tcgen05 tensor cores (sm_100a):
 //     O = softmax(Q K^T / sqrt(emb_size)) V        per (image, head)     models/plainvit.py:450-461
 // (the reference divides by sqrt(emb_size), not sqrt(head_dim): plainvit.py:455-457).
 //
@@ -6,18 +6,20 @@
 //        regrouped once per step, rgbnm_weight_prep);  output o [B][N][H*64] bf16 ('b n (h d)', :461) and
 //        lse [B][H][N] fp32 (log-sum-exp of the scaled scores, kept for backward).
 //
-// One work item = one 128-query tile of one (image, head): the whole key row (196 keys, padded to 208) fits one
-// UMMA N, so the softmax is single-pass.  Per item:
-//   TMA        Q tile [128 x 64], K [208 x 64], V [208 x 64] (3-D tensor map over qkv; rows past token 195 are
-//              zero-filled by the TMA unit)
-//   MMA 1      S[128 x 208] = Q K^T            UMMA 128x208x16 x 4, fp32 in TMEM columns [0, 208)
-//   softmax    one thread per query row: tcgen05.ld S, max / exp2 / sum in registers, P as packed bf16 back
-//              into TMEM columns [0, 104) (aliasing the S columns already consumed)
-//   MMA 2      O[128 x 64] = P V               A operand from TMEM (tcgen05.mma ..., [tmem_a], ...), V as
-//              MN-major smem operand, fp32 in TMEM columns [128, 192)
-//   epilogue   O / rowsum -> bf16 -> swizzled staging (the dead Q tile) -> TMA store (rows past 195 clipped)
-// Persistent CTAs, 256 TMEM columns each, 2 CTAs per SM so one CTA's softmax overlaps the other's MMAs.
-// Warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = softmax / epilogue (TMEM lane quadrant = warp % 4).
+// Forward: one work item = one (image, head).  The 196 keys (padded to 208 = one UMMA N) are loaded once and
+// shared by the two 128-query tiles, each owned by one softmax warpgroup:
+//   TMA        Q0, Q1 [128 x 64], K, V [208 x 64] into a 2-stage ring: the next item's operands land while
+//              this one computes (3-D tensor map over qkv; rows past token 195 are zero-filled)
+//   MMA 1      S_w[128 x 208] = Q_w K^T         UMMA 128x208x16 x 4, fp32 in TMEM columns w*256 + [0, 208)
+//   softmax    one thread per query row, two TMEM passes (max, then exp2 + row sum), P as packed bf16 back
+//              into TMEM columns [0, 104) of the same slot (behind the read pointer)
+//   MMA 2      O_w[128 x 64] = P_w V            A operand from TMEM, V as MN-major smem operand, fp32 in
+//              TMEM columns w*256 + [128, 192)
+//   epilogue   O / rowsum -> bf16 -> swizzled staging (the dead Q_w tile) -> TMA store (rows past 195 clipped)
+// The two warpgroups run half an item apart, so one group's exponentials (the MUFU unit is the bound: 128 x 208
+// ex2 per tile at 16/clk/SM) overlap the other group's MMAs, epilogue and barrier latencies.
+// Warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = softmax / epilogue (warpgroup (warp-2)/4,
+// TMEM lane quadrant warp % 4).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -37,56 +39,69 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 2^x on the FMA pipe (x <= 0 after the max subtraction): round-to-nearest split x = n + f, |f| <= 1/2, a cubic for
+// 2^f (|rel err| < 1.1e-4, below the bf16 rounding of P) and n added into the exponent field.  Used for one element
+// in four so the 16-lane MUFU unit and the FMA pipes finish together.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -125.0f);
+    const float r = x + 12582912.0f;                  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+    const float f = x - (r - 12582912.0f);
+    float p = fmaf(f, 0.0550086908f, 0.2422106266f);
+    p = fmaf(p, f, 0.6932829022f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
 
 constexpr int BM = 128;          // queries per tile
 constexpr int NK = 208;          // keys padded to a multiple of 16 (UMMA N granularity at M = 128)
 constexpr int HD = 64;           // head dim
-constexpr int THREADS = 6 * 32;
-constexpr int TMEM_COLS = 256;
-constexpr int COL_S = 0, COL_P = 0, COL_O = 128;
-
 constexpr int Q_BYTES = BM * HD * 2;      // 16384
 constexpr int KV_BYTES = NK * HD * 2;     // 26624
-constexpr int OFF_Q = 0, OFF_K = OFF_Q + Q_BYTES, OFF_V = OFF_K + 27648 /* 1024-aligned */, OFF_BAR = OFF_V + 27648;
-constexpr int SMEM_TOTAL = OFF_BAR + 64 + 16 + 1024;
+constexpr int KV_SLOT = 27648;            // 1024-aligned
+
+// ================================================= forward ==========================================================
+constexpr int F_THREADS = 10 * 32;
+constexpr int F_STAGE = 2 * Q_BYTES + 2 * KV_SLOT;          // Q0 | Q1 | K | V  = 88064
+constexpr int F_OFF_BAR = 2 * F_STAGE;
+constexpr int F_SMEM_TOTAL = F_OFF_BAR + 128 + 16 + 1024;
+constexpr int F_TMEM_COLS = 512;
+constexpr int COL_S = 0, COL_P = 0, COL_O = 128;            // inside a warpgroup's 256-column slot
 
 struct Params {
     int B, N, H;
-    int items;            // B * H * tiles
-    int tiles;            // ceil(N / 128)
+    int items;            // B * H
     float scale_log2e;    // scale * log2(e)
     float scale;
     float* lse;
 };
 
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(F_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                 const __grid_constant__ CUtensorMap tmO, const Params p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-    uint64_t* full_qk = bars + 0;     // Q + K landed
-    uint64_t* full_v = bars + 1;      // V landed
-    uint64_t* s_full = bars + 2;      // S accumulator complete
-    uint64_t* p_ready = bars + 3;     // P written to TMEM by all 128 softmax threads
-    uint64_t* o_full = bars + 4;      // O accumulator complete
-    uint64_t* item_done = bars + 5;   // smem + TMEM free for the next item
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 64);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_OFF_BAR);
+    uint64_t* full_qk = bars + 0;        // [2] stage: Q0, Q1, K landed
+    uint64_t* full_v = bars + 2;         // [2] stage: V landed
+    uint64_t* stage_free = bars + 4;     // [2] stage: both warpgroups have stored their O tile (count 2)
+    uint64_t* s_full = bars + 6;         // [2] warpgroup: S accumulator complete
+    uint64_t* p_ready = bars + 8;        // [2] warpgroup: P written to TMEM (count 4 warps)
+    uint64_t* o_full = bars + 10;        // [2] warpgroup: O accumulator complete
+    uint64_t* o_drained = bars + 12;     // [2] warpgroup: O read out of TMEM (count 4 warps) -> slot reusable
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + F_OFF_BAR + 128);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tmQ);
         prefetch_tensormap(&tmKV);
         prefetch_tensormap(&tmO);
-        mbar_init(full_qk, 1);
-        mbar_init(full_v, 1);
-        mbar_init(s_full, 1);
-        mbar_init(p_ready, 4);
-        mbar_init(o_full, 1);
-        mbar_init(item_done, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(full_qk + s, 1); mbar_init(full_v + s, 1); mbar_init(stage_free + s, 2);
+            mbar_init(s_full + s, 1); mbar_init(p_ready + s, 4); mbar_init(o_full + s, 1); mbar_init(o_drained + s, 4);
+        }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    if (warp == 1) tmem_alloc<F_TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -96,170 +111,202 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (lane == 0) {
             int it = 0;
             for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-                const int t = item % p.tiles, bh = item / p.tiles;
-                const int h = bh % p.H, b = bh / p.H;
-                mbar_wait(item_done, (it & 1) ^ 1);
-                mbar_arrive_expect_tx(full_qk, Q_BYTES + KV_BYTES);
-                tma_load_3d(smem + OFF_Q, &tmQ, full_qk, h * HD, t * BM, b);
-                tma_load_3d(smem + OFF_K, &tmKV, full_qk, (p.H + h) * HD, 0, b);
-                mbar_arrive_expect_tx(full_v, KV_BYTES);
-                tma_load_3d(smem + OFF_V, &tmKV, full_v, (2 * p.H + h) * HD, 0, b);
+                const int h = item % p.H, b = item / p.H;
+                const int st = it & 1;
+                unsigned char* sg = smem + st * F_STAGE;
+                mbar_wait(stage_free + st, ((it >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(full_qk + st, 2 * Q_BYTES + KV_BYTES);
+                tma_load_3d(sg, &tmQ, full_qk + st, h * HD, 0, b);
+                tma_load_3d(sg + 2 * Q_BYTES, &tmKV, full_qk + st, (p.H + h) * HD, 0, b);
+                tma_load_3d(sg + Q_BYTES, &tmQ, full_qk + st, h * HD, BM, b);
+                mbar_arrive_expect_tx(full_v + st, KV_BYTES);
+                tma_load_3d(sg + 2 * Q_BYTES + KV_SLOT, &tmKV, full_v + st, (2 * p.H + h) * HD, 0, b);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc_s = make_idesc_bf16(BM, NK, false, false);
             constexpr uint32_t idesc_o = make_idesc_bf16(BM, HD, false, true);      // B = V is MN-major (keys are the reduction)
-            const uint32_t sq = smem_u32(smem + OFF_Q), sk = smem_u32(smem + OFF_K), sv = smem_u32(smem + OFF_V);
             int it = 0;
             for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-                const uint32_t ph = it & 1;
-                mbar_wait(full_qk, ph);
-                tc_fence_after();
+                const int st = it & 1;
+                const uint32_t ph = it & 1, sph = (it >> 1) & 1;
+                const uint32_t sq = smem_u32(smem + st * F_STAGE), sk = sq + 2 * Q_BYTES, sv = sk + KV_SLOT;
+                mbar_wait(full_qk + st, sph);
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
-                    tc_mma_f16(tmem_base + COL_S, make_smem_desc_sw128(sq + k * 32, 0, 1024),
-                               make_smem_desc_sw128(sk + k * 32, 0, 1024), idesc_s, k != 0);
-                tc_commit(s_full);
-                mbar_wait(full_v, ph);
-                mbar_wait(p_ready, ph);
-                tc_fence_after();
+                for (int w = 0; w < 2; ++w) {
+                    mbar_wait(o_drained + w, ph ^ 1);                // the previous item's O_w has left this TMEM slot
+                    tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < NK / 16; ++k)
-                    tc_mma_f16_ts(tmem_base + COL_O, tmem_base + COL_P + k * 8,
-                                  make_smem_desc_sw128(sv + k * 2048, 0, 1024), idesc_o, k != 0);
-                tc_commit(o_full);
+                    for (int k = 0; k < HD / 16; ++k)
+                        tc_mma_f16(tmem_base + w * 256 + COL_S, make_smem_desc_sw128(sq + w * Q_BYTES + k * 32, 0, 1024),
+                                   make_smem_desc_sw128(sk + k * 32, 0, 1024), idesc_s, k != 0);
+                    tc_commit(s_full + w);
+                }
+                mbar_wait(full_v + st, sph);
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    mbar_wait(p_ready + w, ph);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < NK / 16; ++k)
+                        tc_mma_f16_ts(tmem_base + w * 256 + COL_O, tmem_base + w * 256 + COL_P + k * 8,
+                                      make_smem_desc_sw128(sv + k * 2048, 0, 1024), idesc_o, k != 0);
+                    tc_commit(o_full + w);
+                }
             }
         }
     } else {
+        const int w = (warp - 2) >> 2;              // warpgroup = query tile
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        const uint32_t lane_addr = tmem_base + (uint32_t(quad * 32) << 16);
-        const bool leader = (warp == 2 && lane == 0);
+        const int qrow = w * BM + row;
+        const bool warp_live = (w * BM + quad * 32) < p.N;       // tile 1, rows 224..255: nothing to compute
+        const uint32_t lane_addr = tmem_base + (uint32_t(quad * 32) << 16) + w * 256;
+        const bool leader = (quad == 0 && lane == 0);
+        const int bar_id = 1 + w;
         int it = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-            const int t = item % p.tiles, bh = item / p.tiles;
-            const int h = bh % p.H, b = bh / p.H;
+            const int h = item % p.H, b = item / p.H;
+            const int st = it & 1;
             const uint32_t ph = it & 1;
-            mbar_wait(s_full, ph);
+            unsigned char* stg = smem + st * F_STAGE + w * Q_BYTES;     // Q_w: dead once S_w is complete
+            mbar_wait(s_full + w, ph);
             tc_fence_after();
-            // ---- pass 1: row maximum over the 196 real keys -----------------------------------------
-            float mx = -INFINITY;
+            float sum = 1.0f, mx = 0.0f;
+            if (warp_live) {
+                // ---- pass 1: row maximum over the 196 real keys -----------------------------------------
+                mx = -INFINITY;
 #pragma unroll 1
-            for (int c = 0; c < 6; ++c) {
+                for (int c = 0; c < 6; c += 2) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(lane_addr + COL_S + c * 32, r0);
+                    tmem_ld32(lane_addr + COL_S + c * 32 + 32, r1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j])));
+                }
+                {
+                    uint32_t r[16];
+                    tmem_ld16(lane_addr + COL_S + 192, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));       // keys 192..195
+                }
+                const float moff = mx * p.scale_log2e;
+                // ---- pass 2: p = exp2(s * scale*log2e - max*scale*log2e), row sum, P (bf16) back into TMEM ----
+                sum = 0.0f;
                 uint32_t r[32];
-                tmem_ld32(lane_addr + COL_S + c * 32, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-            }
-            {
-                uint32_t r[16];
-                tmem_ld16(lane_addr + COL_S + 192, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 4; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));       // keys 192..195
-            }
-            const float moff = mx * p.scale_log2e;
-            // ---- pass 2: p = exp2(s * scale*log2e - max*scale*log2e), row sum, P (bf16) back into TMEM ----
-            float sum = 0.0f;
+                tmem_ld32(lane_addr + COL_S, r);
 #pragma unroll 1
-            for (int c = 0; c < 6; ++c) {
-                uint32_t r[32];
-                tmem_ld32(lane_addr + COL_S + c * 32, r);
-                tmem_ld_wait();
-                uint32_t pk[16];
+                for (int c = 0; c < 6; ++c) {
+                    tmem_ld_wait();
+                    float x[32];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), p.scale_log2e, -moff));
-                    const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), p.scale_log2e, -moff));
-                    // the sum uses the bf16-rounded probabilities, i.e. exactly what the P.V MMA sees
-                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(e0, e1);
-                    sum += __bfloat162float(b2.x) + __bfloat162float(b2.y);
-                    pk[j] = *reinterpret_cast<const uint32_t*>(&b2);
+                    for (int j = 0; j < 32; ++j) x[j] = fmaf(__uint_as_float(r[j]), p.scale_log2e, -moff);
+                    // next chunk's TMEM load overlaps this chunk's math (r is dead after the fma above)
+                    if (c < 5) tmem_ld32(lane_addr + COL_S + (c + 1) * 32, r);
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float e0 = ex2_approx(x[2 * j]);
+                        const float e1 = (j & 1) ? ex2_poly(x[2 * j + 1]) : ex2_approx(x[2 * j + 1]);
+                        sum += e0 + e1;
+                        pk[j] = pack_bf16(e0, e1);
+                    }
+                    tmem_st16(lane_addr + COL_P + c * 16, pk);
                 }
-                tmem_st16(lane_addr + COL_P + c * 16, pk);
-            }
-            {
-                uint32_t r[16];
-                tmem_ld16(lane_addr + COL_S + 192, r);
-                tmem_ld_wait();
-                // keys 192..195 are real, 196..207 are padding: probability 0 (their V rows are zero-filled as well)
-                uint32_t pk[16];
+                {
+                    uint32_t t[16];
+                    tmem_ld16(lane_addr + COL_S + 192, t);
+                    tmem_ld_wait();
+                    // keys 192..195 are real, 196..207 are padding: probability 0 (their V rows are zero-filled as well)
+                    uint32_t pk[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) pk[j] = 0u;
+                    for (int j = 0; j < 16; ++j) pk[j] = 0u;
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const float e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), p.scale_log2e, -moff));
-                    const float e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), p.scale_log2e, -moff));
-                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(e0, e1);
-                    sum += __bfloat162float(b2.x) + __bfloat162float(b2.y);
-                    pk[j] = *reinterpret_cast<const uint32_t*>(&b2);
+                    for (int j = 0; j < 2; ++j) {
+                        const float e0 = ex2_approx(fmaf(__uint_as_float(t[2 * j]), p.scale_log2e, -moff));
+                        const float e1 = ex2_approx(fmaf(__uint_as_float(t[2 * j + 1]), p.scale_log2e, -moff));
+                        sum += e0 + e1;
+                        pk[j] = pack_bf16(e0, e1);
+                    }
+                    // P columns 96..103 hold keys 192..207; the x16 store also zeroes columns 104..111, which are free
+                    tmem_st16(lane_addr + COL_P + 96, pk);
                 }
-                // P columns 96..103 hold keys 192..207; the x16 store also zeroes columns 104..111, which are free
-                tmem_st16(lane_addr + COL_P + 96, pk);
+                tmem_st_wait();
             }
-            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(p_ready);
-            const int qrow = t * BM + row;
+            if (lane == 0) mbar_arrive(p_ready + w);
             if (qrow < p.N) p.lse[(size_t(b) * p.H + h) * p.N + qrow] = mx * p.scale + __logf(sum);
-            // ---- epilogue: O / sum -> bf16 -> staging (the Q tile, dead since MMA 1) -> TMA store ----
-            mbar_wait(o_full, ph);
+            // ---- epilogue: O / sum -> bf16 -> staging (the Q_w tile, dead since MMA 1) -> TMA store ----
+            mbar_wait(o_full + w, ph);
             tc_fence_after();
-            const float inv = 1.0f / sum;
-            unsigned char* rowp = smem + OFF_Q + row * 128;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t r[32];
-                tmem_ld32(lane_addr + COL_O + c * 32, r);
+            if (warp_live) {
+                const float inv = 1.0f / sum;
+                unsigned char* rowp = stg + row * 128;
+                uint32_t r0[32], r1[32];
+                tmem_ld32(lane_addr + COL_O, r0);
+                tmem_ld32(lane_addr + COL_O + 32, r1);
                 tmem_ld_wait();
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    const int q = c * 4 + q4;
-                    const float* x = reinterpret_cast<const float*>(r) + 8 * q4;
-                    *reinterpret_cast<uint4*>(rowp + ((q ^ (row & 7)) << 4)) =
-                        make_uint4(pack_bf16(x[0] * inv, x[1] * inv), pack_bf16(x[2] * inv, x[3] * inv),
-                                   pack_bf16(x[4] * inv, x[5] * inv), pack_bf16(x[6] * inv, x[7] * inv));
+                for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const int q = c * 4 + q4;
+                        const float* x = reinterpret_cast<const float*>(c == 0 ? r0 : r1) + 8 * q4;
+                        *reinterpret_cast<uint4*>(rowp + ((q ^ (row & 7)) << 4)) =
+                            make_uint4(pack_bf16(x[0] * inv, x[1] * inv), pack_bf16(x[2] * inv, x[3] * inv),
+                                       pack_bf16(x[4] * inv, x[5] * inv), pack_bf16(x[6] * inv, x[7] * inv));
+                    }
                 }
             }
             tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_drained + w);
             fence_proxy_async();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
             if (leader) {
-                tma_store_3d(&tmO, smem + OFF_Q, h * HD, t * BM, b);
+                tma_store_3d(&tmO, stg, h * HD, w * BM, b);
                 tma_store_commit();
                 tma_store_wait_read<0>();
-                mbar_arrive(item_done);
+                mbar_arrive(stage_free + st);
             }
         }
         if (leader) tma_store_wait<0>();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (warp == 1) tmem_dealloc<F_TMEM_COLS>(tmem_base);
 }
 
 
 // =================================================================================================
 // Backward.  With P = softmax(S), S = Q K^T * scale, O = P V, Dr = rowsum(dO * O):
 //     dV = P^T dO        dP = dO V^T        dS = P * (dP - Dr) * scale        dQ = dS K        dK = dS^T Q
-// P is recomputed from S and the saved log-sum-exp.  Two kernels, each a copy of the forward schedule
-// (score MMAs -> one thread per accumulator row -> bf16 operand parked in TMEM -> second MMA):
-//   attn_bwd_q_kernel   item = 128 queries x all keys:   S, dP as [q x key]; dS (TMEM A operand) . K -> dQ
-//   attn_bwd_kv_kernel  item = 128 keys x all queries:   S^T = K Q^T, dP^T = V dO^T as [key x q];
-//                       P^T . dO -> dV,  dS^T . Q -> dK   (both A operands straight from TMEM)
+// P is recomputed from S and the saved log-sum-exp.  Two kernels on one skeleton (score MMAs -> element-wise pass
+// with one thread per accumulator row -> bf16 operands parked in TMEM -> output MMAs):
+//   attn_bwd_kernel<false>  item = 128 queries x all keys:   S, dP as [q x key]; dS (TMEM A operand) . K -> dQ
+//   attn_bwd_kernel<true>   item = 128 keys x all queries:   S^T = K Q^T, dP^T = V dO^T as [key x q];
+//                           P^T . dO -> dV,  dS^T . Q -> dK   (both A operands straight from TMEM)
 // The transposed formulation costs a second evaluation of S and dP, and in exchange no operand ever has to be
 // transposed through shared memory and no partial dQ has to be reduced across CTAs.
+// Schedule: operands of the next item are TMA-loaded into the second smem stage while this item computes; the
+// element-wise pass is split over 8 warps (TMEM lane quadrant x column half).  Column half 0 owns score columns
+// 0..95 and 192..207 and parks its bf16 results behind its own read pointer; half 1 owns columns 96..191 and parks
+// its results in the 96 spare TMEM columns, so the two warps of a quadrant never touch each other's columns.
 // =================================================================================================
+constexpr int B_THREADS = 10 * 32;
 constexpr int COL_DP = 208;                 // second score accumulator
-constexpr int COL_DS = 208;                 // bf16 dS / dS^T, aliasing the consumed dP columns
+constexpr int COL_DS = 208;                 // bf16 dS / dS^T of column half 0, aliasing consumed dP columns
 constexpr int COL_OUT2 = 336;               // second output accumulator (dK), inside the dP region
+constexpr int SPARE_P = 416, SPARE_DS = 464;// column half 1: bf16 P and dS (48 columns each)
 constexpr int BWD_TMEM_COLS = 512;
-constexpr int B_OFF_A0 = 0, B_OFF_A1 = 16384, B_OFF_B0 = 32768, B_OFF_B1 = B_OFF_B0 + 27648, B_OFF_VEC = B_OFF_B1 + 27648;
-constexpr int B_OFF_BAR = B_OFF_VEC + 2 * NK * 4;
-constexpr int B_SMEM_TOTAL = B_OFF_BAR + 64 + 16 + 1024;
+constexpr int B_STAGE = 2 * Q_BYTES + 2 * KV_SLOT;           // A0 | A1 | B0 | B1 = 88064
+constexpr int B_OFF_VEC = 2 * B_STAGE;                       // 2 x float2[NK]: per-query {lse * log2e, Dr * scale}
+constexpr int B_OFF_BAR = B_OFF_VEC + 2 * NK * 8;
+constexpr int B_SMEM_TOTAL = B_OFF_BAR + 128 + 16 + 1024;
 
 struct BwdParams {
     int B, N, H, items, tiles;
@@ -279,11 +326,13 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* 
     const int q = int(row % N), b = int(row / N);
     const uint4* a = reinterpret_cast<const uint4*>(dO + row * (long long)(H * HD) + h * HD);
     const uint4* c = reinterpret_cast<const uint4*>(O + row * (long long)(H * HD) + h * HD);
+    uint4 x[8], y[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { x[k] = __ldg(a + k); y[k] = __ldg(c + k); }
     float s = 0.0f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const uint4 x = __ldg(a + k), y = __ldg(c + k);
-        const unsigned xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+        const unsigned xw[4] = {x[k].x, x[k].y, x[k].z, x[k].w}, yw[4] = {y[k].x, y[k].y, y[k].z, y[k].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             s += __uint_as_float(xw[e] << 16) * __uint_as_float(yw[e] << 16);
@@ -293,31 +342,37 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* 
     dvec[((long long)b * H + h) * N + q] = s;
 }
 
-// Shared skeleton of the two backward kernels.  KV = false: rows are queries (A0 = Q tile, A1 = dO tile, B0 = K, B1 = V),
-// one output dQ = dS . K.  KV = true: rows are keys (A0 = K tile, A1 = V tile, B0 = Q, B1 = dO), two outputs
-// dV = P^T . dO (into the V tile's staging) and dK = dS^T . Q.
+// TMEM column of the bf16 A operand for reduction step k (16 score columns = 8 packed columns per step)
+__device__ __forceinline__ uint32_t bwd_a_col(int base_half0, int base_half1, int k) {
+    return k < 6 ? base_half0 + 8 * k : (k < 12 ? base_half1 + 8 * (k - 6) : base_half0 + 48);
+}
+
+// KV = false: rows are queries (A0 = Q tile, A1 = dO tile, B0 = K, B1 = V), one output dQ = dS . K.
+// KV = true: rows are keys (A0 = K tile, A1 = V tile, B0 = Q, B1 = dO), two outputs dV = P^T . dO (into the V tile's
+// staging) and dK = dS^T . Q.
 template <bool KV>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(B_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmTile, const __grid_constant__ CUtensorMap tmAll,
                 const __grid_constant__ CUtensorMap tmTileDO, const __grid_constant__ CUtensorMap tmAllDO,
                 const __grid_constant__ CUtensorMap tmOut, const BwdParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF_BAR);
-    uint64_t* full = bars + 0;        // all four operand tiles landed
-    uint64_t* s_full = bars + 1;      // both score accumulators complete
-    uint64_t* p_ready = bars + 2;     // bf16 operands parked in TMEM
-    uint64_t* o_full = bars + 3;      // output accumulator(s) complete
-    uint64_t* item_done = bars + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B_OFF_BAR + 64);
-    float* vec_lse = reinterpret_cast<float*>(smem + B_OFF_VEC);          // KV: per-query lse * log2e (+inf past the last query)
-    float* vec_d = vec_lse + NK;                                            // KV: per-query Dr
+    uint64_t* full = bars + 0;          // [2] stage: all four operand tiles landed
+    uint64_t* stage_free = bars + 2;    // [2] stage: outputs stored, smem reusable
+    uint64_t* s_full = bars + 4;        // both score accumulators complete
+    uint64_t* p_ready = bars + 5;       // bf16 operands parked in TMEM (count 8 warps)
+    uint64_t* o_full = bars + 6;        // output accumulator(s) complete
+    uint64_t* acc_free = bars + 7;      // output accumulators read out (count 8 warps) -> TMEM reusable
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B_OFF_BAR + 128);
+    float2* vec = reinterpret_cast<float2*>(smem + B_OFF_VEC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tmTile); prefetch_tensormap(&tmAll); prefetch_tensormap(&tmTileDO);
         prefetch_tensormap(&tmAllDO); prefetch_tensormap(&tmOut);
-        mbar_init(full, 1); mbar_init(s_full, 1); mbar_init(p_ready, 4); mbar_init(o_full, 1); mbar_init(item_done, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(full + s, 1); mbar_init(stage_free + s, 1); }
+        mbar_init(s_full, 1); mbar_init(p_ready, 8); mbar_init(o_full, 1); mbar_init(acc_free, 8);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<BWD_TMEM_COLS>(tmem_slot);
@@ -332,18 +387,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmTile, const __grid_constan
             for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
                 const int t = item % p.tiles, bh = item / p.tiles;
                 const int h = bh % p.H, b = bh / p.H;
-                mbar_wait(item_done, (it & 1) ^ 1);
-                mbar_arrive_expect_tx(full, 2 * Q_BYTES + 2 * KV_BYTES);
+                const int st = it & 1;
+                unsigned char* sg = smem + st * B_STAGE;
+                mbar_wait(stage_free + st, ((it >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(full + st, 2 * Q_BYTES + 2 * KV_BYTES);
                 if (!KV) {
-                    tma_load_3d(smem + B_OFF_A0, &tmTile, full, h * HD, t * BM, b);                   // Q tile
-                    tma_load_3d(smem + B_OFF_A1, &tmTileDO, full, h * HD, t * BM, b);                 // dO tile
-                    tma_load_3d(smem + B_OFF_B0, &tmAll, full, (p.H + h) * HD, 0, b);                 // K
-                    tma_load_3d(smem + B_OFF_B1, &tmAll, full, (2 * p.H + h) * HD, 0, b);             // V
+                    tma_load_3d(sg, &tmTile, full + st, h * HD, t * BM, b);                                   // Q tile
+                    tma_load_3d(sg + 2 * Q_BYTES, &tmAll, full + st, (p.H + h) * HD, 0, b);                   // K
+                    tma_load_3d(sg + Q_BYTES, &tmTileDO, full + st, h * HD, t * BM, b);                       // dO tile
+                    tma_load_3d(sg + 2 * Q_BYTES + KV_SLOT, &tmAll, full + st, (2 * p.H + h) * HD, 0, b);     // V
                 } else {
-                    tma_load_3d(smem + B_OFF_A0, &tmTile, full, (p.H + h) * HD, t * BM, b);           // K tile
-                    tma_load_3d(smem + B_OFF_A1, &tmTile, full, (2 * p.H + h) * HD, t * BM, b);       // V tile
-                    tma_load_3d(smem + B_OFF_B0, &tmAll, full, h * HD, 0, b);                         // Q
-                    tma_load_3d(smem + B_OFF_B1, &tmAllDO, full, h * HD, 0, b);                       // dO
+                    tma_load_3d(sg, &tmTile, full + st, (p.H + h) * HD, t * BM, b);                           // K tile
+                    tma_load_3d(sg + 2 * Q_BYTES, &tmAll, full + st, h * HD, 0, b);                           // Q
+                    tma_load_3d(sg + Q_BYTES, &tmTile, full + st, (2 * p.H + h) * HD, t * BM, b);             // V tile
+                    tma_load_3d(sg + 2 * Q_BYTES + KV_SLOT, &tmAllDO, full + st, h * HD, 0, b);               // dO
                 }
             }
         }
@@ -351,12 +408,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmTile, const __grid_constan
         if (lane == 0) {
             constexpr uint32_t idesc_s = make_idesc_bf16(BM, NK, false, false);
             constexpr uint32_t idesc_o = make_idesc_bf16(BM, HD, false, true);
-            const uint32_t a0 = smem_u32(smem + B_OFF_A0), a1 = smem_u32(smem + B_OFF_A1);
-            const uint32_t b0 = smem_u32(smem + B_OFF_B0), b1 = smem_u32(smem + B_OFF_B1);
             int it = 0;
             for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+                const int st = it & 1;
                 const uint32_t ph = it & 1;
-                mbar_wait(full, ph);
+                const uint32_t a0 = smem_u32(smem + st * B_STAGE), a1 = a0 + Q_BYTES, b0 = a0 + 2 * Q_BYTES, b1 = b0 + KV_SLOT;
+                mbar_wait(full + st, (it >> 1) & 1);
+                mbar_wait(acc_free, ph ^ 1);          // the previous item's outputs (aliasing S / dP) have been read out
                 tc_fence_after();
                 // scores:  !KV: S = Q K^T, dP = dO V^T      KV: S^T = K Q^T, dP^T = V dO^T
 #pragma unroll
@@ -374,17 +432,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmTile, const __grid_constan
                     // dQ = dS . K   (K as MN-major operand: keys are the reduction)
 #pragma unroll
                     for (int k = 0; k < NK / 16; ++k)
-                        tc_mma_f16_ts(tmem_base + COL_O, tmem_base + COL_DS + k * 8,
+                        tc_mma_f16_ts(tmem_base + COL_O, tmem_base + bwd_a_col(COL_DS, SPARE_DS, k),
                                       make_smem_desc_sw128(b0 + k * 2048, 0, 1024), idesc_o, k != 0);
                 } else {
                     // dV = P^T . dO,  dK = dS^T . Q
 #pragma unroll
                     for (int k = 0; k < NK / 16; ++k)
-                        tc_mma_f16_ts(tmem_base + COL_O, tmem_base + COL_P + k * 8,
+                        tc_mma_f16_ts(tmem_base + COL_O, tmem_base + bwd_a_col(COL_P, SPARE_P, k),
                                       make_smem_desc_sw128(b1 + k * 2048, 0, 1024), idesc_o, k != 0);
 #pragma unroll
                     for (int k = 0; k < NK / 16; ++k)
-                        tc_mma_f16_ts(tmem_base + COL_OUT2, tmem_base + COL_DS + k * 8,
+                        tc_mma_f16_ts(tmem_base + COL_OUT2, tmem_base + bwd_a_col(COL_DS, SPARE_DS, k),
                                       make_smem_desc_sw128(b0 + k * 2048, 0, 1024), idesc_o, k != 0);
                 }
                 tc_commit(o_full);
@@ -392,6 +450,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmTile, const __grid_constan
         }
     } else {
         const int quad = warp & 3;
+        const int halfc = (warp - 2) >> 2;          // column half of the element-wise pass / of the 64 output columns
         const int row = quad * 32 + lane;
         const int tid = threadIdx.x - 64;
         const uint32_t lane_addr = tmem_base + (uint32_t(quad * 32) << 16);
@@ -400,85 +459,90 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmTile, const __grid_constan
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
             const int t = item % p.tiles, bh = item / p.tiles;
             const int h = bh % p.H, b = bh / p.H;
+            const int st = it & 1;
             const uint32_t ph = it & 1;
+            const bool warp_live = (t * BM + quad * 32) < p.N;      // rows past the last token: outputs are clipped
             const float* lse_bh = p.lse + (size_t(b) * p.H + h) * p.N;
             const float* d_bh = p.dvec + (size_t(b) * p.H + h) * p.N;
-            float my_lse2 = 0.0f, my_d = 0.0f;
+            float my_lse2 = 0.0f, my_dds = 0.0f;
+            const float2* vq = vec + (it & 1) * NK;
             if (!KV) {
                 const int q = t * BM + row;
-                if (q < p.N) { my_lse2 = lse_bh[q] * 1.4426950408889634f; my_d = d_bh[q]; }
+                if (q < p.N) { my_lse2 = lse_bh[q] * 1.4426950408889634f; my_dds = d_bh[q] * p.scale; }
             } else {
-                for (int q = tid; q < NK; q += 128) {
-                    vec_lse[q] = q < p.N ? lse_bh[q] * 1.4426950408889634f : INFINITY;     // padded queries: P = 0
-                    vec_d[q] = q < p.N ? d_bh[q] : 0.0f;
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                float2* vw = vec + (it & 1) * NK;
+                if (tid < NK)        // padded queries: P = 0 (lse = +inf), dS = 0
+                    vw[tid] = tid < p.N ? make_float2(lse_bh[tid] * 1.4426950408889634f, d_bh[tid] * p.scale) : make_float2(INFINITY, 0.0f);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             mbar_wait(s_full, ph);
             tc_fence_after();
-            // one pass over the 208 columns: P and dS as packed bf16, written behind the read pointer
+            if (warp_live) {
+                // chunks of 32 score columns: half 0 -> chunks 0,1,2 and the 16-column tail; half 1 -> chunks 3,4,5
 #pragma unroll 1
-            for (int c = 0; c < 7; ++c) {
-                uint32_t rs[32], rd[32];
-                if (c < 6) {
-                    tmem_ld32(lane_addr + COL_S + c * 32, rs);
-                    tmem_ld32(lane_addr + COL_DP + c * 32, rd);
-                } else {
-                    uint32_t t16a[16], t16b[16];
-                    tmem_ld16(lane_addr + COL_S + 192, t16a);
-                    tmem_ld16(lane_addr + COL_DP + 192, t16b);
-                    tmem_ld_wait();
+                for (int ci = 0; ci < 3 + (halfc == 0 ? 1 : 0); ++ci) {
+                    const bool tail = (ci == 3);
+                    const int c = tail ? 6 : halfc * 3 + ci;
+                    uint32_t rs[32], rd[32];
+                    if (!tail) {
+                        tmem_ld32(lane_addr + COL_S + c * 32, rs);
+                        tmem_ld32(lane_addr + COL_DP + c * 32, rd);
+                        tmem_ld_wait();
+                    } else {
+                        uint32_t ta[16], tb[16];
+                        tmem_ld16(lane_addr + COL_S + 192, ta);
+                        tmem_ld16(lane_addr + COL_DP + 192, tb);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) { rs[j] = t16a[j]; rd[j] = t16b[j]; rs[16 + j] = 0u; rd[16 + j] = 0u; }
-                }
-                tmem_ld_wait();
-                uint32_t pk[16], dk[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float pv[2], dv[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int col = c * 32 + 2 * j + e;
-                        float l2, dd;
-                        if (!KV) { l2 = my_lse2; dd = my_d; }
-                        else { l2 = vec_lse[col < NK ? col : NK - 1]; dd = vec_d[col < NK ? col : NK - 1]; }
-                        const float pr = ex2_approx(fmaf(__uint_as_float(rs[2 * j + e]), p.scale_log2e, -l2));
-                        pv[e] = pr;
-                        dv[e] = pr * (__uint_as_float(rd[2 * j + e]) - dd) * p.scale;
+                        for (int j = 0; j < 16; ++j) { rs[j] = ta[j]; rd[j] = tb[j]; rs[16 + j] = 0u; rd[16 + j] = 0u; }
                     }
-                    pk[j] = pack_bf16(pv[0], pv[1]);
-                    dk[j] = pack_bf16(dv[0], dv[1]);
+                    uint32_t pk[16], dk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float l2a = my_lse2, dda = my_dds, l2b = my_lse2, ddb = my_dds;
+                        if (KV) {
+                            const int col = c * 32 + 2 * j;                                     // even -> 16-byte aligned pair
+                            const float4 v4 = *reinterpret_cast<const float4*>(vq + (col < NK ? col : NK - 2));
+                            l2a = v4.x; dda = v4.y; l2b = v4.z; ddb = v4.w;
+                        }
+                        const float xa = fmaf(__uint_as_float(rs[2 * j]), p.scale_log2e, -l2a);
+                        const float xb = fmaf(__uint_as_float(rs[2 * j + 1]), p.scale_log2e, -l2b);
+                        const float pa = ex2_approx(xa);
+                        const float pb = (j & 1) ? ex2_poly(xb) : ex2_approx(xb);
+                        const float da = pa * fmaf(__uint_as_float(rd[2 * j]), p.scale, -dda);
+                        const float db = pb * fmaf(__uint_as_float(rd[2 * j + 1]), p.scale, -ddb);
+                        pk[j] = pack_bf16(pa, pb);
+                        dk[j] = pack_bf16(da, db);
+                    }
+                    // half 0 parks chunk ci behind its own read pointer (tail: columns 48..63 of its region, read long ago);
+                    // half 1 parks in the spare columns.  The tail's x16 store spills zeros/garbage into 8 columns nobody reads.
+                    const uint32_t pcol = halfc == 0 ? COL_P + 16 * ci : SPARE_P + 16 * ci;
+                    const uint32_t dcol = halfc == 0 ? COL_DS + 16 * ci : SPARE_DS + 16 * ci;
+                    if (KV) tmem_st16(lane_addr + pcol, pk);
+                    tmem_st16(lane_addr + dcol, dk);
                 }
-                if (c < 6) {
-                    if (KV) tmem_st16(lane_addr + COL_P + c * 16, pk);
-                    tmem_st16(lane_addr + COL_DS + c * 16, dk);
-                } else {
-                    // last 16 columns -> 8 packed columns; the x16 store spills zeros/garbage into 8 free columns
-                    if (KV) tmem_st16(lane_addr + COL_P + 96, pk);
-                    tmem_st16(lane_addr + COL_DS + 96, dk);
-                }
+                tmem_st_wait();
             }
-            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_ready);
-            // ---- epilogue: accumulators -> bf16 -> swizzled staging (dead A tiles) -> TMA store ----
+            // ---- epilogue: accumulators -> bf16 -> swizzled staging (dead A tiles) -> TMA store; this warp converts
+            //      columns [32 * halfc, +32) of each output ----
             mbar_wait(o_full, ph);
             tc_fence_after();
+            unsigned char* sg = smem + st * B_STAGE;
+            if (warp_live) {
 #pragma unroll
-            for (int o = 0; o < (KV ? 2 : 1); ++o) {
-                // !KV: dQ -> staging A0 (Q tile).   KV: o = 0: dV (COL_O) -> staging A1 (V tile); o = 1: dK (COL_OUT2) -> A0 (K tile)
-                const uint32_t col0 = (o == 0) ? COL_O : COL_OUT2;
-                unsigned char* stg = smem + ((KV && o == 0) ? B_OFF_A1 : B_OFF_A0);
-                unsigned char* rowp = stg + row * 128;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
+                for (int o = 0; o < (KV ? 2 : 1); ++o) {
+                    // !KV: dQ -> staging A0 (Q tile).   KV: o = 0: dV (COL_O) -> staging A1 (V tile); o = 1: dK (COL_OUT2) -> A0 (K tile)
+                    const uint32_t col0 = (o == 0) ? COL_O : COL_OUT2;
+                    unsigned char* rowp = sg + ((KV && o == 0) ? Q_BYTES : 0) + row * 128;
                     uint32_t r[32];
-                    tmem_ld32(lane_addr + col0 + c * 32, r);
+                    tmem_ld32(lane_addr + col0 + halfc * 32, r);
                     tmem_ld_wait();
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
-                        const int q = c * 4 + q4;
+                        const int q = halfc * 4 + q4;
                         const float* x = reinterpret_cast<const float*>(r) + 8 * q4;
                         *reinterpret_cast<uint4*>(rowp + ((q ^ (row & 7)) << 4)) =
                             make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
@@ -486,18 +550,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmTile, const __grid_constan
                 }
             }
             tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_free);
             fence_proxy_async();
-            asm volatile("bar.sync 2, 128;" ::: "memory");
+            asm volatile("bar.sync 2, 256;" ::: "memory");
             if (leader) {
                 if (!KV) {
-                    tma_store_3d(&tmOut, smem + B_OFF_A0, h * HD, t * BM, b);                          // dQ
+                    tma_store_3d(&tmOut, sg, h * HD, t * BM, b);                                       // dQ
                 } else {
-                    tma_store_3d(&tmOut, smem + B_OFF_A1, (2 * p.H + h) * HD, t * BM, b);              // dV
-                    tma_store_3d(&tmOut, smem + B_OFF_A0, (p.H + h) * HD, t * BM, b);                  // dK
+                    tma_store_3d(&tmOut, sg + Q_BYTES, (2 * p.H + h) * HD, t * BM, b);                 // dV
+                    tma_store_3d(&tmOut, sg, (p.H + h) * HD, t * BM, b);                               // dK
                 }
                 tma_store_commit();
                 tma_store_wait_read<0>();
-                mbar_arrive(item_done);
+                mbar_arrive(stage_free + st);
             }
         }
         if (leader) tma_store_wait<0>();
@@ -516,7 +582,7 @@ extern "C" int rgbnm_attention_fwd(const void* qkv, void* o, float* lse, int B, 
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
-        RGBNM_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        RGBNM_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_TOTAL));
         int dev = 0;
         RGBNM_CUDA_CHECK(cudaGetDevice(&dev));
         RGBNM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -530,13 +596,12 @@ extern "C" int rgbnm_attention_fwd(const void* qkv, void* o, float* lse, int B, 
     if ((rc = rgbnm_make_tmap_bf16_3d(&tmO, o, (long long)H * HD, N, B, (long long)H * HD, (long long)H * HD * N, HD, BM))) return rc;
     Params p;
     p.B = B; p.N = N; p.H = H;
-    p.tiles = (N + BM - 1) / BM;
-    p.items = B * H * p.tiles;
+    p.items = B * H;
     p.scale = scale;
     p.scale_log2e = scale * 1.4426950408889634f;
     p.lse = lse;
-    const int grid = p.items < 2 * num_sms ? p.items : 2 * num_sms;
-    attn_fwd_kernel<<<grid, THREADS, SMEM_TOTAL, static_cast<cudaStream_t>(stream)>>>(tmQ, tmKV, tmO, p);
+    const int grid = p.items < num_sms ? p.items : num_sms;
+    attn_fwd_kernel<<<grid, F_THREADS, F_SMEM_TOTAL, static_cast<cudaStream_t>(stream)>>>(tmQ, tmKV, tmO, p);
     RGBNM_CUDA_CHECK(cudaGetLastError());
     return RGBNM_OK;
 }
@@ -580,9 +645,9 @@ extern "C" int rgbnm_attention_bwd(const void* dout, const void* qkv, const void
     p.lse = lse;
     p.dvec = dvec;
     const int grid = p.items < num_sms ? p.items : num_sms;
-    attn_bwd_kernel<false><<<grid, THREADS, B_SMEM_TOTAL, st>>>(tmTile, tmAll, tmTileDO, tmAllDO, tmOut, p);
+    attn_bwd_kernel<false><<<grid, B_THREADS, B_SMEM_TOTAL, st>>>(tmTile, tmAll, tmTileDO, tmAllDO, tmOut, p);
     RGBNM_CUDA_CHECK(cudaGetLastError());
-    attn_bwd_kernel<true><<<grid, THREADS, B_SMEM_TOTAL, st>>>(tmTile, tmAll, tmTileDO, tmAllDO, tmOut, p);
+    attn_bwd_kernel<true><<<grid, B_THREADS, B_SMEM_TOTAL, st>>>(tmTile, tmAll, tmTileDO, tmAllDO, tmOut, p);
     RGBNM_CUDA_CHECK(cudaGetLastError());
     return RGBNM_OK;
 }

@@ -97,6 +97,34 @@ def test_layernorm_fwd_bwd(E):
     assert _rel(dg, gr.grad) < 1e-4 and _rel(db, br.grad) < 1e-4
 
 
+@pytest.mark.parametrize("B,H", [(1, 1), (2, 3), (5, 6), (37, 6)])
+def test_attention_fwd_bwd(B, H):
+    """tcgen05 attention kernels vs a plain fp32 torch evaluation of plainvit.py:450-461 (scale 1/sqrt(emb_size))."""
+    from rgb_no_more_b200 import attention as A
+    torch.manual_seed(B * 10 + H)
+    D, N = 64, 196
+    scale = 1.0 / math.sqrt(H * D)
+    qkv = _bf(B * N, 3 * H * D, scale=2.0)
+    o = torch.zeros(B * N, H * D, dtype=torch.bfloat16, device=DEV)
+    lse = torch.zeros(B, H, N, device=DEV)
+    A.forward(qkv, o, lse, B, H, D, scale, backend="b200")
+    leaf = qkv.float().requires_grad_(True)
+    v = leaf.view(B, N, 3, H, D).permute(2, 0, 3, 1, 4)
+    s = torch.einsum("bhqd,bhkd->bhqk", v[0], v[1]) * scale
+    ref = torch.einsum("bhqk,bhkd->bhqd", torch.softmax(s, -1), v[2]).transpose(1, 2).reshape(B * N, H * D)
+    # bf16 P and bf16 output: 2e-2 of the output range; lse is fp32 up to the ex2.approx / cubic-exp2 error
+    assert _rel(o, ref) < 2e-2
+    assert float((lse - torch.logsumexp(s, -1)).abs().max()) < 1e-2
+    do = _bf(B * N, H * D)
+    dqkv = torch.zeros_like(qkv)
+    A.backward(do, qkv, o, lse, dqkv, B, H, D, scale, backend="b200")
+    (gref,) = torch.autograd.grad(ref, leaf, do.float())
+    HD = H * D
+    for sl in (slice(0, HD), slice(HD, 2 * HD), slice(2 * HD, 3 * HD)):          # dq | dk | dv
+        assert _rel(dqkv[:, sl], gref[:, sl]) < 3e-2
+    assert torch.isfinite(dqkv.float()).all()
+
+
 def test_colsum_weightprep_adamw():
     torch.manual_seed(3)
     a = _bf(5000, 1152)
