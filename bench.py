@@ -163,23 +163,45 @@ def run_ours(args):
             return stage.step(x, labels_pool[k])
         return x
 
+    # ---- end-to-end arm: host buffers in, host scalar out, every step ---------------------------------------
+    # Two device staging sets; the pinned-host -> device copy of step i+1 runs on a copy stream while step i computes
+    # (the copy engine and the SMs overlap), each timed region still contains exactly one copy per step: the first
+    # copy of a region is exposed, the last step of a region does not prefetch.
     h2d_stream = torch.cuda.Stream(device=dev)
     stage_bufs = [tuple(torch.empty_like(t, device=dev) for t in host_pool[0]) for _ in range(2)]
     stage_plans = [torch.empty_like(packed_pool[0], device=dev) for _ in range(2)]
     result_host = torch.empty((1,), dtype=torch.float32).pin_memory()
+    ev_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    copied = set()
+    region_last = {args.warmup - 1, args.warmup + args.steps - 1}
+
+    def issue_copy(i):
+        k, sidx = i % N_POOL, i % 2
+        with torch.cuda.stream(h2d_stream):
+            h2d_stream.wait_event(ev_free[sidx])              # the step that last read this staging set has finished
+            for dst, src in zip(stage_bufs[sidx], host_pool[k]):
+                dst.copy_(src, non_blocking=True)
+            stage_plans[sidx].copy_(packed_pool[k], non_blocking=True)
+            ev_ready[sidx].record(h2d_stream)
+        copied.add(i)
 
     def step_e2e(i):
-        k = i % N_POOL
-        s = i % 2
-        for dst, src in zip(stage_bufs[s], host_pool[k]):
-            dst.copy_(src, non_blocking=True)
-        stage_plans[s].copy_(packed_pool[k], non_blocking=True)
-        x = tf.run(*stage_bufs[s], None, plans_dev=stage_plans[s], out=out_buf)
+        k, sidx = i % N_POOL, i % 2
+        if i not in copied:
+            issue_copy(i)
+        if i not in region_last:
+            issue_copy(i + 1)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev_ready[sidx])
+        x = tf.run(*stage_bufs[sidx], None, plans_dev=stage_plans[sidx], out=out_buf)
         if stage is not None:
             res = stage.step(x, labels_pool[k])
         else:
             res = x[:, 0, :8].float().sum().reshape(1)     # a scalar that depends on the step's output
+        ev_free[sidx].record(cur)
         result_host.copy_(res.reshape(-1)[:1].float(), non_blocking=True)
+        copied.discard(i)
 
     def timed_loop(fn, steps, warmup, **kw):
         for i in range(warmup):

@@ -127,33 +127,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (lane == 0) {
             constexpr uint32_t idesc_s = make_idesc_bf16(BM, NK, false, false);
             constexpr uint32_t idesc_o = make_idesc_bf16(BM, HD, false, true);      // B = V is MN-major (keys are the reduction)
-            int it = 0;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+            // Issue order  S0(0) S1(0) | PV0(i) S0(i+1) PV1(i) S1(i+1) | ...: a warpgroup gets its next score tile as soon
+            // as its own O has left TMEM, without waiting for the other group's softmax, so the two groups drift half an
+            // item apart and one group's exponentials cover the other group's MMA / barrier latencies.
+            const int n_it = (p.items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+            auto issue_s = [&](int it, int w) {
                 const int st = it & 1;
-                const uint32_t ph = it & 1, sph = (it >> 1) & 1;
-                const uint32_t sq = smem_u32(smem + st * F_STAGE), sk = sq + 2 * Q_BYTES, sv = sk + KV_SLOT;
-                mbar_wait(full_qk + st, sph);
+                const uint32_t sq = smem_u32(smem + st * F_STAGE), sk = sq + 2 * Q_BYTES;
+                if (w == 0) mbar_wait(full_qk + st, (it >> 1) & 1);
+                mbar_wait(o_drained + w, (it & 1) ^ 1);              // the previous item's O_w has left this TMEM slot
+                tc_fence_after();
 #pragma unroll
-                for (int w = 0; w < 2; ++w) {
-                    mbar_wait(o_drained + w, ph ^ 1);                // the previous item's O_w has left this TMEM slot
-                    tc_fence_after();
+                for (int k = 0; k < HD / 16; ++k)
+                    tc_mma_f16(tmem_base + w * 256 + COL_S, make_smem_desc_sw128(sq + w * Q_BYTES + k * 32, 0, 1024),
+                               make_smem_desc_sw128(sk + k * 32, 0, 1024), idesc_s, k != 0);
+                tc_commit(s_full + w);
+            };
+            auto issue_pv = [&](int it, int w) {
+                const int st = it & 1;
+                const uint32_t sv = smem_u32(smem + st * F_STAGE) + 2 * Q_BYTES + KV_SLOT;
+                if (w == 0) mbar_wait(full_v + st, (it >> 1) & 1);
+                mbar_wait(p_ready + w, it & 1);
+                tc_fence_after();
 #pragma unroll
-                    for (int k = 0; k < HD / 16; ++k)
-                        tc_mma_f16(tmem_base + w * 256 + COL_S, make_smem_desc_sw128(sq + w * Q_BYTES + k * 32, 0, 1024),
-                                   make_smem_desc_sw128(sk + k * 32, 0, 1024), idesc_s, k != 0);
-                    tc_commit(s_full + w);
-                }
-                mbar_wait(full_v + st, sph);
-#pragma unroll
-                for (int w = 0; w < 2; ++w) {
-                    mbar_wait(p_ready + w, ph);
-                    tc_fence_after();
-#pragma unroll
-                    for (int k = 0; k < NK / 16; ++k)
-                        tc_mma_f16_ts(tmem_base + w * 256 + COL_O, tmem_base + w * 256 + COL_P + k * 8,
-                                      make_smem_desc_sw128(sv + k * 2048, 0, 1024), idesc_o, k != 0);
-                    tc_commit(o_full + w);
-                }
+                for (int k = 0; k < NK / 16; ++k)
+                    tc_mma_f16_ts(tmem_base + w * 256 + COL_O, tmem_base + w * 256 + COL_P + k * 8,
+                                  make_smem_desc_sw128(sv + k * 2048, 0, 1024), idesc_o, k != 0);
+                tc_commit(o_full + w);
+            };
+            if (n_it > 0) { issue_s(0, 0); issue_s(0, 1); }
+            for (int it = 0; it < n_it; ++it) {
+                issue_pv(it, 0);
+                if (it + 1 < n_it) issue_s(it + 1, 0);
+                issue_pv(it, 1);
+                if (it + 1 < n_it) issue_s(it + 1, 1);
             }
         }
     } else {
@@ -294,18 +301,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // transposed through shared memory and no partial dQ has to be reduced across CTAs.
 // Schedule: operands of the next item are TMA-loaded into the second smem stage while this item computes; the
 // element-wise pass is split over 8 warps (TMEM lane quadrant x column half).  Column half 0 owns score columns
-// 0..95 and 192..207 and parks its bf16 results behind its own read pointer; half 1 owns columns 96..191 and parks
-// its results in the 96 spare TMEM columns, so the two warps of a quadrant never touch each other's columns.
+// 0..95 and 192..207, half 1 owns columns 96..191; each parks its bf16 results behind its own read pointer, so the
+// two warps of a quadrant never touch each other's columns.  The score MMAs are issued as two column groups and the
+// output MMAs per half, so half 0 starts (and its part of the reduction is consumed) while half 1 is still busy;
+// the first output accumulator lives in the 96 spare TMEM columns and can be written while scores are still read.
 // =================================================================================================
 constexpr int B_THREADS = 10 * 32;
 constexpr int COL_DP = 208;                 // second score accumulator
 constexpr int COL_DS = 208;                 // bf16 dS / dS^T of column half 0, aliasing consumed dP columns
-constexpr int COL_OUT2 = 336;               // second output accumulator (dK), inside the dP region
-constexpr int SPARE_P = 416, SPARE_DS = 464;// column half 1: bf16 P and dS (48 columns each)
+constexpr int COL_P1 = 96, COL_DS1 = 304;   // column half 1 parks behind its own read pointers (S cols 96.., dP cols 304..)
+constexpr int COL_OUT = 416;                // first output accumulator (dQ / dV): the 96 spare columns, aliases nothing
+constexpr int COL_OUT2 = 352;               // second output accumulator (dK): dP columns that are consumed by then
 constexpr int BWD_TMEM_COLS = 512;
 constexpr int B_STAGE = 2 * Q_BYTES + 2 * KV_SLOT;           // A0 | A1 | B0 | B1 = 88064
-constexpr int B_OFF_VEC = 2 * B_STAGE;                       // 2 x float2[NK]: per-query {lse * log2e, Dr * scale}
-constexpr int B_OFF_BAR = B_OFF_VEC + 2 * NK * 8;
+constexpr int NKV = 224;                                     // per-query vector padded so the 32-wide tail chunk stays in bounds
+constexpr int B_OFF_VEC = 2 * B_STAGE;                       // 2 x float2[NKV]: per-query {lse * log2e, Dr * scale}
+constexpr int B_OFF_BAR = B_OFF_VEC + 2 * NKV * 8;
 constexpr int B_SMEM_TOTAL = B_OFF_BAR + 128 + 16 + 1024;
 
 struct BwdParams {
@@ -360,10 +371,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmTile, const __grid_constan
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF_BAR);
     uint64_t* full = bars + 0;          // [2] stage: all four operand tiles landed
     uint64_t* stage_free = bars + 2;    // [2] stage: outputs stored, smem reusable
-    uint64_t* s_full = bars + 4;        // both score accumulators complete
-    uint64_t* p_ready = bars + 5;       // bf16 operands parked in TMEM (count 8 warps)
-    uint64_t* o_full = bars + 6;        // output accumulator(s) complete
-    uint64_t* acc_free = bars + 7;      // output accumulators read out (count 8 warps) -> TMEM reusable
+    uint64_t* s_full = bars + 4;        // [2] score accumulators complete: columns [0, 96) | [96, 208)
+    uint64_t* p_ready = bars + 6;       // [3] bf16 operands parked in TMEM (count 4 warps each): half 0 chunks | half 1 chunks | tail
+    uint64_t* o_full = bars + 9;        // output accumulator(s) complete
+    uint64_t* acc_free = bars + 10;     // output accumulators read out (count 8 warps) -> TMEM reusable
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B_OFF_BAR + 128);
     float2* vec = reinterpret_cast<float2*>(smem + B_OFF_VEC);
 
@@ -372,7 +383,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmTile, const __grid_constan
         prefetch_tensormap(&tmTile); prefetch_tensormap(&tmAll); prefetch_tensormap(&tmTileDO);
         prefetch_tensormap(&tmAllDO); prefetch_tensormap(&tmOut);
         for (int s = 0; s < 2; ++s) { mbar_init(full + s, 1); mbar_init(stage_free + s, 1); }
-        mbar_init(s_full, 1); mbar_init(p_ready, 8); mbar_init(o_full, 1); mbar_init(acc_free, 8);
+        mbar_init(s_full, 1); mbar_init(s_full + 1, 1); mbar_init(o_full, 1); mbar_init(acc_free, 8);
+        for (int s = 0; s < 3; ++s) mbar_init(p_ready + s, 4);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<BWD_TMEM_COLS>(tmem_slot);
@@ -414,35 +426,46 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmTile, const __grid_constan
                 const uint32_t ph = it & 1;
                 const uint32_t a0 = smem_u32(smem + st * B_STAGE), a1 = a0 + Q_BYTES, b0 = a0 + 2 * Q_BYTES, b1 = b0 + KV_SLOT;
                 mbar_wait(full + st, (it >> 1) & 1);
-                mbar_wait(acc_free, ph ^ 1);          // the previous item's outputs (aliasing S / dP) have been read out
+                // KV: the second output accumulator aliases dP columns -> the previous item's outputs must have been read out.
+                // !KV: nothing aliases; the score MMAs simply queue behind the previous item's output MMAs.
+                if (KV) mbar_wait(acc_free, ph ^ 1);
                 tc_fence_after();
-                // scores:  !KV: S = Q K^T, dP = dO V^T      KV: S^T = K Q^T, dP^T = V dO^T
+                // scores:  !KV: S = Q K^T, dP = dO V^T      KV: S^T = K Q^T, dP^T = V dO^T.  Two column groups ([0, 96) then
+                // [96, 208)) so the element-wise warps of half 0 start one MMA group earlier.
+                constexpr uint32_t idesc_sa = make_idesc_bf16(BM, 96, false, false), idesc_sb = make_idesc_bf16(BM, NK - 96, false, false);
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
-                    tc_mma_f16(tmem_base + COL_S, make_smem_desc_sw128(a0 + k * 32, 0, 1024),
-                               make_smem_desc_sw128(b0 + k * 32, 0, 1024), idesc_s, k != 0);
+                for (int g = 0; g < 2; ++g) {
+                    const uint32_t idesc_g = g == 0 ? idesc_sa : idesc_sb;
+                    const uint32_t boff = g * 96 * 128, coff = g * 96;         // B rows (K-major, 128 B each) / accumulator columns
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
-                    tc_mma_f16(tmem_base + COL_DP, make_smem_desc_sw128(a1 + k * 32, 0, 1024),
-                               make_smem_desc_sw128(b1 + k * 32, 0, 1024), idesc_s, k != 0);
-                tc_commit(s_full);
-                mbar_wait(p_ready, ph);
+                    for (int k = 0; k < HD / 16; ++k)
+                        tc_mma_f16(tmem_base + COL_S + coff, make_smem_desc_sw128(a0 + k * 32, 0, 1024),
+                                   make_smem_desc_sw128(b0 + boff + k * 32, 0, 1024), idesc_g, k != 0);
+#pragma unroll
+                    for (int k = 0; k < HD / 16; ++k)
+                        tc_mma_f16(tmem_base + COL_DP + coff, make_smem_desc_sw128(a1 + k * 32, 0, 1024),
+                                   make_smem_desc_sw128(b1 + boff + k * 32, 0, 1024), idesc_g, k != 0);
+                    tc_commit(s_full + g);
+                }
+                // first output (dQ / dV) into the spare columns: reduction steps 0..5 as soon as half 0 has parked them
+                if (!KV) mbar_wait(acc_free, ph ^ 1);          // the previous item's dQ has been read out of the spare columns
+                mbar_wait(p_ready + 0, ph);
                 tc_fence_after();
-                if (!KV) {
-                    // dQ = dS . K   (K as MN-major operand: keys are the reduction)
-#pragma unroll
+                const uint32_t bo = KV ? b1 : b0;                // reduction-side operand of the first output: dO (KV) / K
+                const int a0col = KV ? COL_P : COL_DS, a1col = KV ? COL_P1 : COL_DS1;
+                for (int k = 0; k < 6; ++k)
+                    tc_mma_f16_ts(tmem_base + COL_OUT, tmem_base + bwd_a_col(a0col, a1col, k),
+                                  make_smem_desc_sw128(bo + k * 2048, 0, 1024), idesc_o, k != 0);
+                mbar_wait(p_ready + 1, ph);
+                mbar_wait(p_ready + 2, ph);
+                tc_fence_after();
+                for (int k = 6; k < NK / 16; ++k)
+                    tc_mma_f16_ts(tmem_base + COL_OUT, tmem_base + bwd_a_col(a0col, a1col, k),
+                                  make_smem_desc_sw128(bo + k * 2048, 0, 1024), idesc_o, true);
+                if (KV) {
+                    // dK = dS^T . Q: its accumulator aliases dP columns, so only once every score column has been consumed
                     for (int k = 0; k < NK / 16; ++k)
-                        tc_mma_f16_ts(tmem_base + COL_O, tmem_base + bwd_a_col(COL_DS, SPARE_DS, k),
-                                      make_smem_desc_sw128(b0 + k * 2048, 0, 1024), idesc_o, k != 0);
-                } else {
-                    // dV = P^T . dO,  dK = dS^T . Q
-#pragma unroll
-                    for (int k = 0; k < NK / 16; ++k)
-                        tc_mma_f16_ts(tmem_base + COL_O, tmem_base + bwd_a_col(COL_P, SPARE_P, k),
-                                      make_smem_desc_sw128(b1 + k * 2048, 0, 1024), idesc_o, k != 0);
-#pragma unroll
-                    for (int k = 0; k < NK / 16; ++k)
-                        tc_mma_f16_ts(tmem_base + COL_OUT2, tmem_base + bwd_a_col(COL_DS, SPARE_DS, k),
+                        tc_mma_f16_ts(tmem_base + COL_OUT2, tmem_base + bwd_a_col(COL_DS, COL_DS1, k),
                                       make_smem_desc_sw128(b0 + k * 2048, 0, 1024), idesc_o, k != 0);
                 }
                 tc_commit(o_full);
@@ -465,67 +488,75 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmTile, const __grid_constan
             const float* lse_bh = p.lse + (size_t(b) * p.H + h) * p.N;
             const float* d_bh = p.dvec + (size_t(b) * p.H + h) * p.N;
             float my_lse2 = 0.0f, my_dds = 0.0f;
-            const float2* vq = vec + (it & 1) * NK;
+            const float2* vq = vec + (it & 1) * NKV;
             if (!KV) {
                 const int q = t * BM + row;
                 if (q < p.N) { my_lse2 = lse_bh[q] * 1.4426950408889634f; my_dds = d_bh[q] * p.scale; }
             } else {
-                float2* vw = vec + (it & 1) * NK;
-                if (tid < NK)        // padded queries: P = 0 (lse = +inf), dS = 0
+                float2* vw = vec + (it & 1) * NKV;
+                if (tid < NKV)       // padded queries: P = 0 (lse = +inf), dS = 0
                     vw[tid] = tid < p.N ? make_float2(lse_bh[tid] * 1.4426950408889634f, d_bh[tid] * p.scale) : make_float2(INFINITY, 0.0f);
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
-            mbar_wait(s_full, ph);
-            tc_fence_after();
-            if (warp_live) {
-                // chunks of 32 score columns: half 0 -> chunks 0,1,2 and the 16-column tail; half 1 -> chunks 3,4,5
+            // chunks of 32 score columns: half 0 -> chunks 0,1,2 and the 16-column tail; half 1 -> chunks 3,4,5
+            const uint32_t vq_s = smem_u32(vq);
 #pragma unroll 1
-                for (int ci = 0; ci < 3 + (halfc == 0 ? 1 : 0); ++ci) {
-                    const bool tail = (ci == 3);
-                    const int c = tail ? 6 : halfc * 3 + ci;
-                    uint32_t rs[32], rd[32];
-                    if (!tail) {
-                        tmem_ld32(lane_addr + COL_S + c * 32, rs);
-                        tmem_ld32(lane_addr + COL_DP + c * 32, rd);
-                        tmem_ld_wait();
-                    } else {
-                        uint32_t ta[16], tb[16];
-                        tmem_ld16(lane_addr + COL_S + 192, ta);
-                        tmem_ld16(lane_addr + COL_DP + 192, tb);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) { rs[j] = ta[j]; rd[j] = tb[j]; rs[16 + j] = 0u; rd[16 + j] = 0u; }
-                    }
-                    uint32_t pk[16], dk[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float l2a = my_lse2, dda = my_dds, l2b = my_lse2, ddb = my_dds;
-                        if (KV) {
-                            const int col = c * 32 + 2 * j;                                     // even -> 16-byte aligned pair
-                            const float4 v4 = *reinterpret_cast<const float4*>(vq + (col < NK ? col : NK - 2));
-                            l2a = v4.x; dda = v4.y; l2b = v4.z; ddb = v4.w;
-                        }
-                        const float xa = fmaf(__uint_as_float(rs[2 * j]), p.scale_log2e, -l2a);
-                        const float xb = fmaf(__uint_as_float(rs[2 * j + 1]), p.scale_log2e, -l2b);
-                        const float pa = ex2_approx(xa);
-                        const float pb = (j & 1) ? ex2_poly(xb) : ex2_approx(xb);
-                        const float da = pa * fmaf(__uint_as_float(rd[2 * j]), p.scale, -dda);
-                        const float db = pb * fmaf(__uint_as_float(rd[2 * j + 1]), p.scale, -ddb);
-                        pk[j] = pack_bf16(pa, pb);
-                        dk[j] = pack_bf16(da, db);
-                    }
-                    // half 0 parks chunk ci behind its own read pointer (tail: columns 48..63 of its region, read long ago);
-                    // half 1 parks in the spare columns.  The tail's x16 store spills zeros/garbage into 8 columns nobody reads.
-                    const uint32_t pcol = halfc == 0 ? COL_P + 16 * ci : SPARE_P + 16 * ci;
-                    const uint32_t dcol = halfc == 0 ? COL_DS + 16 * ci : SPARE_DS + 16 * ci;
-                    if (KV) tmem_st16(lane_addr + pcol, pk);
-                    tmem_st16(lane_addr + dcol, dk);
+            for (int ci = 0; ci < 3 + (halfc == 0 ? 1 : 0); ++ci) {
+                const bool tail = (ci == 3);
+                const int c = tail ? 6 : halfc * 3 + ci;
+                if (ci == 0) { mbar_wait(s_full + halfc, ph); tc_fence_after(); }
+                if (tail) {
+                    // chunks 0..2 of this half are parked: the MMA warp may start on their reduction steps
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(p_ready + 0);
+                    mbar_wait(s_full + 1, ph);                    // the tail columns belong to the second score group
+                    tc_fence_after();
                 }
-                tmem_st_wait();
+                if (!warp_live) continue;
+                uint32_t rs[32], rd[32];
+                if (!tail) {
+                    tmem_ld32(lane_addr + COL_S + c * 32, rs);
+                    tmem_ld32(lane_addr + COL_DP + c * 32, rd);
+                    tmem_ld_wait();
+                } else {
+                    uint32_t ta[16], tb[16];
+                    tmem_ld16(lane_addr + COL_S + 192, ta);
+                    tmem_ld16(lane_addr + COL_DP + 192, tb);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { rs[j] = ta[j]; rd[j] = tb[j]; rs[16 + j] = 0u; rd[16 + j] = 0u; }
+                }
+                uint32_t pk[16], dk[16];
+                const uint32_t vaddr = vq_s + c * 256;                      // 32 columns x float2
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float l2a = my_lse2, dda = my_dds, l2b = my_lse2, ddb = my_dds;
+                    if (KV) {
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(l2a), "=f"(dda), "=f"(l2b), "=f"(ddb) : "r"(vaddr + j * 16));
+                    }
+                    const float xa = fmaf(__uint_as_float(rs[2 * j]), p.scale_log2e, -l2a);
+                    const float xb = fmaf(__uint_as_float(rs[2 * j + 1]), p.scale_log2e, -l2b);
+                    const float pa = ex2_approx(xa);
+                    const float pb = (j & 1) ? ex2_poly(xb) : ex2_approx(xb);
+                    const float da = pa * fmaf(__uint_as_float(rd[2 * j]), p.scale, -dda);
+                    const float db = pb * fmaf(__uint_as_float(rd[2 * j + 1]), p.scale, -ddb);
+                    pk[j] = pack_bf16(pa, pb);
+                    dk[j] = pack_bf16(da, db);
+                }
+                // parked behind this half's own read pointer (tail: columns 48..63 of half 0's region, read long ago; its
+                // x16 store spills zeros/garbage into 8 columns nobody reads)
+                const uint32_t pcol = (halfc == 0 ? COL_P : COL_P1) + 16 * ci;
+                const uint32_t dcol = (halfc == 0 ? COL_DS : COL_DS1) + 16 * ci;
+                if (KV) tmem_st16(lane_addr + pcol, pk);
+                tmem_st16(lane_addr + dcol, dk);
             }
+            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(p_ready);
+            if (lane == 0) mbar_arrive(p_ready + (halfc == 0 ? 2 : 1));
             // ---- epilogue: accumulators -> bf16 -> swizzled staging (dead A tiles) -> TMA store; this warp converts
             //      columns [32 * halfc, +32) of each output ----
             mbar_wait(o_full, ph);
@@ -535,7 +566,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmTile, const __grid_constan
 #pragma unroll
                 for (int o = 0; o < (KV ? 2 : 1); ++o) {
                     // !KV: dQ -> staging A0 (Q tile).   KV: o = 0: dV (COL_O) -> staging A1 (V tile); o = 1: dK (COL_OUT2) -> A0 (K tile)
-                    const uint32_t col0 = (o == 0) ? COL_O : COL_OUT2;
+                    const uint32_t col0 = (o == 0) ? COL_OUT : COL_OUT2;
                     unsigned char* rowp = sg + ((KV && o == 0) ? Q_BYTES : 0) + row * 128;
                     uint32_t r[32];
                     tmem_ld32(lane_addr + col0 + halfc * 32, r);
