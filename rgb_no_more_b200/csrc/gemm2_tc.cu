@@ -146,7 +146,9 @@ struct Cfg {
     static constexpr int NBARS = 2 * STAGES + 4 + 2 * (NBUF > 0 ? NBUF : 1);
     static constexpr int OFF_TMEM = OFF_BAR + NBARS * 8;
     static constexpr int TOTAL = OFF_TMEM + 16 + 1024;
-    static_assert(BN % 64 == 0 && 2 * BN <= 512 && (BN / 2) % 8 == 0, "tile shape");
+    static constexpr int NACC = 2 * BN <= 512 ? 2 : 1;          // TMEM accumulator buffers (BN = 384: one, the epilogue is not overlapped)
+    static_assert(BN % 64 == 0 && BN <= 512 && (BN / 2) % 8 == 0, "tile shape");
+    static_assert(BN <= 256 || (BN == 384 && B_MN), "BN = 384 is implemented for the MN-major (wgrad) operands only");
     static_assert(!B_MN || (BN / 2) % 64 == 0, "MN-major B: each CTA needs whole 64-wide swizzle atoms");
     static_assert(TOTAL <= 232448, "shared memory");
 };
@@ -222,9 +224,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     }
                     if (!B_MN) {
                         tma_load_2d_pair(sb, &tmB, full + stage, kb * BK, n0);
-                    } else {
+                    } else if (BN <= 256) {
 #pragma unroll
                         for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(sb + j * (BK * 128), &tmB, full + stage, n0 + j * 64, kb * BK);
+                    } else {
+                        // BN = 384 runs as two UMMAs per step (N = 256, then N = 128); a cta_group::2 UMMA takes the first half
+                        // of its N from CTA 0 and the second half from CTA 1, so CTA r holds columns {r*128 .. +128} and
+                        // {256 + r*64 .. +64} of the tile: accumulator column == tile column.
+                        const int nb = n_blk * BN;
+                        tma_load_2d_pair(sb, &tmB, full + stage, nb + int(rank) * 128, kb * BK);
+                        tma_load_2d_pair(sb + BK * 128, &tmB, full + stage, nb + int(rank) * 128 + 64, kb * BK);
+                        tma_load_2d_pair(sb + 2 * BK * 128, &tmB, full + stage, nb + 256 + int(rank) * 64, kb * BK);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -233,14 +243,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     } else if (warp == 1) {
         // ===================================== MMA issuer (leader CTA only) =====================
         if (rank == 0 && lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN <= 256 ? BN : 256, A_MN, B_MN);
+            constexpr uint32_t idesc_hi = make_idesc_bf16(BM, 128, A_MN, B_MN);          // BN = 384: second UMMA of a step
             int stage = 0, phase = 0, it = 0;
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
                 const int sp = tile % p.splits;
                 int k0, k1;
                 k_range(sp, k0, k1);
-                const int acc = it & 1;
-                mbar_wait(tempty + acc, ((it >> 1) & 1) ^ 1);
+                const int acc = L::NACC == 2 ? (it & 1) : 0;
+                mbar_wait(tempty + acc, ((L::NACC == 2 ? (it >> 1) : it) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = k0; kb < k1; ++kb) {
@@ -255,6 +266,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
                                                  : make_smem_desc_sw128(sb + k * 32, 0, 1024);
                         tc_mma_f16_pair(d_tmem, da, db, idesc, (kb != k0) || (k != 0));
+                        if (BN > 256)       // columns [256, 384): the third 64-column atom of each CTA's B tile
+                            tc_mma_f16_pair(d_tmem + 256, da, make_smem_desc_sw128(sb + 2 * BK * 128 + k * 2048, BK * 128, 1024), idesc_hi,
+                                            (kb != k0) || (k != 0));
                     }
                     tc_commit_pair(empty + stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -312,9 +326,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
             const int rest = tile / p.splits;
             const int n_blk = rest % p.n_tiles, m_blk = rest / p.n_tiles;
-            const int acc = it & 1;
+            const int acc = L::NACC == 2 ? (it & 1) : 0;
             const int n0 = n_blk * BN, m0 = m_blk * BM + int(rank) * BM_CTA;
-            mbar_wait(tfull + acc, (it >> 1) & 1);
+            mbar_wait(tfull + acc, (L::NACC == 2 ? (it >> 1) : it) & 1);
             tc_fence_after();
 #pragma unroll 1
             for (int s = 0; s < NSUB; ++s, ++g) {
@@ -422,14 +436,14 @@ static int g_num_sms = 0;
 
 static int pick_splits(int tiles, int k_blocks, int clusters) {
     // fill whole waves of `clusters` work items; fewer splits = fewer atomics, so take the smallest
-    // split count within 3 % of the best wave efficiency
+    // split count within 5 % of the best wave efficiency
     int best = 1;
     double best_eff = 0.0;
-    for (int s = 1; s <= 16 && s <= k_blocks; ++s) {
+    for (int s = 1; s <= 40 && s <= k_blocks / 8; ++s) {
         const int items = tiles * s;
         const int waves = (items + clusters - 1) / clusters;
         const double eff = double(items) / (double(waves) * clusters);
-        if (eff > best_eff + 0.03) { best_eff = eff; best = s; }
+        if (eff > best_eff + 0.05) { best_eff = eff; best = s; }
     }
     return best;
 }
@@ -513,6 +527,8 @@ extern "C" int rgbnm_gemm_bf16(const rgbnm_gemm_args* args, void* stream) {
             return launch<192, 5, EPI_POSEMB, false, false>(a, st);
         case RGBNM_EPI_WGRAD_ATOMIC:
             if (!a.out_f32) return RGBNM_ERR_ARG;
+            // N = 384 (every wgrad of ViT-S once the longer side sits on M): one 256 x 384 tile per CTA pair, 157 FLOP per L2 byte
+            if (a.N % 384 == 0 && !getenv("RGBNM_WGRAD_BN128")) return launch<384, 5, EPI_ATOMIC, true, true>(a, st);
             return launch<128, 6, EPI_ATOMIC, true, true>(a, st);
         case RGBNM_EPI_F32:
             if (!a.out_f32) return RGBNM_ERR_ARG;
