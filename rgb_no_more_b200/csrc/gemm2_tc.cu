@@ -148,7 +148,7 @@ struct Cfg {
     static constexpr int TOTAL = OFF_TMEM + 16 + 1024;
     static constexpr int NACC = 2 * BN <= 512 ? 2 : 1;          // TMEM accumulator buffers (BN = 384: one, the epilogue is not overlapped)
     static_assert(BN % 64 == 0 && BN <= 512 && (BN / 2) % 8 == 0, "tile shape");
-    static_assert(BN <= 256 || (BN == 384 && B_MN), "BN = 384 is implemented for the MN-major (wgrad) operands only");
+    static_assert(BN <= 256 || BN == 384, "BN = 384: two UMMAs per step (N = 256 + 128)");
     static_assert(!B_MN || (BN / 2) % 64 == 0, "MN-major B: each CTA needs whole 64-wide swizzle atoms");
     static_assert(TOTAL <= 232448, "shared memory");
 };
@@ -222,8 +222,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
                         for (int j = 0; j < BM_CTA / 64; ++j) tma_load_2d_pair(sa + j * (BK * 128), &tmA, full + stage, m0 + j * 64, kb * BK);
                     }
-                    if (!B_MN) {
+                    if (!B_MN && BN <= 256) {
                         tma_load_2d_pair(sb, &tmB, full + stage, kb * BK, n0);
+                    } else if (!B_MN) {
+                        // BN = 384, K-major: rows {r*128 .. +128} and {256 + r*64 .. +64} of the B tile (see the MN-major case below)
+                        const int nb = n_blk * BN;
+                        tma_load_2d_pair(sb, &tmB, full + stage, kb * BK, nb + int(rank) * 128);
+                        tma_load_2d_pair(sb + 64 * 128, &tmB, full + stage, kb * BK, nb + int(rank) * 128 + 64);
+                        tma_load_2d_pair(sb + 128 * 128, &tmB, full + stage, kb * BK, nb + 256 + int(rank) * 64);
                     } else if (BN <= 256) {
 #pragma unroll
                         for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(sb + j * (BK * 128), &tmB, full + stage, n0 + j * 64, kb * BK);
@@ -266,9 +272,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
                                                  : make_smem_desc_sw128(sb + k * 32, 0, 1024);
                         tc_mma_f16_pair(d_tmem, da, db, idesc, (kb != k0) || (k != 0));
-                        if (BN > 256)       // columns [256, 384): the third 64-column atom of each CTA's B tile
-                            tc_mma_f16_pair(d_tmem + 256, da, make_smem_desc_sw128(sb + 2 * BK * 128 + k * 2048, BK * 128, 1024), idesc_hi,
-                                            (kb != k0) || (k != 0));
+                        if (BN > 256) {     // columns [256, 384): the third 64-wide block of each CTA's B tile
+                            const uint64_t db2 = B_MN ? make_smem_desc_sw128(sb + 2 * BK * 128 + k * 2048, BK * 128, 1024)
+                                                      : make_smem_desc_sw128(sb + 128 * 128 + k * 32, 0, 1024);
+                            tc_mma_f16_pair(d_tmem + 256, da, db2, idesc_hi, (kb != k0) || (k != 0));
+                        }
                     }
                     tc_commit_pair(empty + stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -467,7 +475,7 @@ static int launch(const rgbnm_gemm_args& a, cudaStream_t st) {
     if (!A_MN) rc = rgbnm_make_tmap_bf16(&tmA, a.A, a.M, a.K, a.lda, BK, BM_CTA);
     else rc = rgbnm_make_tmap_bf16(&tmA, a.A, a.K, a.M, a.lda, 64, BK);
     if (rc) return rc;
-    if (!B_MN) rc = rgbnm_make_tmap_bf16(&tmB, a.B, a.N, a.K, a.ldb, BK, BN / 2);
+    if (!B_MN) rc = rgbnm_make_tmap_bf16(&tmB, a.B, a.N, a.K, a.ldb, BK, BN <= 256 ? BN / 2 : 64);
     else rc = rgbnm_make_tmap_bf16(&tmB, a.B, a.K, a.N, a.ldb, 64, BK);
     if (rc) return rc;
     tmC = tmA; tmC2 = tmA; tmAux = tmA;
@@ -509,13 +517,17 @@ extern "C" int rgbnm_gemm_bf16(const rgbnm_gemm_args* args, void* stream) {
     if ((a.lda % 8) || (a.ldb % 8)) return RGBNM_ERR_ARG;                      // TMA: 16-byte aligned row pitch
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool wide = (a.N % 256 == 0);
+    // N = 384 with a long reduction: one 256 x 384 tile per CTA pair (157 FLOP per L2 byte).  Its single TMEM accumulator
+    // leaves the epilogue exposed, which only pays off when the main loop is long (K >= 768).
+    static const bool no384 = (getenv("RGBNM_GEMM_NO384") != nullptr);
+    const bool tall = (a.N % 384 == 0) && a.K >= 768 && !no384;
     switch (a.epilogue) {
         case RGBNM_EPI_STORE:
             if (!a.C || (a.ldc % 8)) return RGBNM_ERR_ARG;
-            return launch<192, 5, EPI_STORE, false, false>(a, st);
+            return tall ? launch<384, 4, EPI_STORE, false, false>(a, st) : launch<192, 5, EPI_STORE, false, false>(a, st);
         case RGBNM_EPI_RESIDUAL:
             if (!a.C || !a.aux || (a.ldc % 8) || (a.ldaux % 8)) return RGBNM_ERR_ARG;
-            return launch<192, 5, EPI_RESIDUAL, false, false>(a, st);
+            return tall ? launch<384, 4, EPI_RESIDUAL, false, false>(a, st) : launch<192, 5, EPI_RESIDUAL, false, false>(a, st);
         case RGBNM_EPI_GELU:
             if (!a.C || !a.C2 || (a.ldc % 8)) return RGBNM_ERR_ARG;
             return wide ? launch<256, 4, EPI_GELU, false, false>(a, st) : launch<192, 4, EPI_GELU, false, false>(a, st);

@@ -71,6 +71,8 @@ if which in ("all", "small"):
     run_case(128, 192, 64)
     run_case(256, 384, 128)
     run_case(1000, 1000, 384)      # ragged M and N
+    run_case(392, 384, 1536)       # N = 384, long K: the 256 x 384 tile
+    run_case(1000, 768, 1152)
 if which in ("all", "wgrad"):
     run_wgrad(64, 128, 192, 1)
     run_wgrad(256, 384, 384, 2)
