@@ -178,9 +178,14 @@ int rgbnm_gemm_bf16(const rgbnm_gemm_args* args, void* stream);
  * gamma/beta fp32, statistics fp32 [rows] kept for backward.  emb in {192, 384, 768}. */
 int rgbnm_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                         int rows, int emb, float eps, void* stream);
-/* dx = LN'(dy) (+ dres if non-NULL: the residual branch gradient, plainvit.py:475-479); dgamma/dbeta += */
+/* dx = LN'(dy) (+ dres if non-NULL: the residual branch gradient, plainvit.py:475-479); dgamma/dbeta +=; if dxsum is
+ * non-NULL, dxsum[emb] += column sums of the stored dx (= the bias gradient of the Linear that wrote the residual stream,
+ * saving a separate pass over dx) */
 int rgbnm_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
-                        const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int emb, void* stream);
+                        const void* dres, void* dx, float* dgamma, float* dbeta, float* dxsum, int rows, int emb, void* stream);
+/* RandomMixup_DCT on the bf16 embed input (utils/cls_transforms.py:135-182): out[b] = lam[0] * x[b] + lam[1] * x[(b-1) mod batch];
+ * lam = 2 device floats; per_image = elements per image (multiple of 8); out != x. */
+int rgbnm_mixup_bf16(const void* x, void* out, const float* lam, int batch, long long per_image, void* stream);
 /* out[cols] += column sums of a bf16 matrix (bias gradients of nn.Linear) */
 int rgbnm_colsum_bf16(const void* a, long long ld, int rows, int cols, float* out, void* stream);
 /* fp32 master weight [n][k] -> bf16 working copy (rows regrouped q|k|v head-major when qkv_heads > 0,

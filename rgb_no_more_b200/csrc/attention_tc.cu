@@ -418,7 +418,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmTile, const __grid_constan
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc_s = make_idesc_bf16(BM, NK, false, false);
             constexpr uint32_t idesc_o = make_idesc_bf16(BM, HD, false, true);
             int it = 0;
             for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {

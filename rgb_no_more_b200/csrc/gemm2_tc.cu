@@ -349,18 +349,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     slotp = smem + L::OFF_STG + slot * L::SLOT_BYTES;
                     mbar_wait(stg_ready + slot, (g / NBUF) & 1);
                 }
+                // bias for this chunk: warp-uniform addresses, issued before the TMEM wait so the loads overlap it
+                const int col0 = n0 + c * 32;
+                constexpr bool ADD_BIAS = (EPI != EPI_ATOMIC && EPI != EPI_DGELU);
+                float4 b4[8];
+                const bool bias_vec = ADD_BIAS && p.bias != nullptr && col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+                if (bias_vec) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                }
                 tmem_ld_wait();
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                const int col0 = n0 + c * 32;
-                if (EPI != EPI_ATOMIC && EPI != EPI_DGELU) {
-                    if (p.bias != nullptr && col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+                if (ADD_BIAS) {
+                    if (bias_vec) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));      // warp-uniform address
-                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                        }
+                        for (int j = 0; j < 8; ++j) { v[4 * j] += b4[j].x; v[4 * j + 1] += b4[j].y; v[4 * j + 2] += b4[j].z; v[4 * j + 3] += b4[j].w; }
                     } else if (p.bias != nullptr) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);

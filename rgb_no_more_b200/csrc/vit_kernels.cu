@@ -73,16 +73,18 @@ template <int PPL>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(const unsigned* __restrict__ dy, const unsigned* __restrict__ x, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, const float* __restrict__ gamma, const unsigned* __restrict__ dres,
-              unsigned* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows) {
+              unsigned* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum,
+              int rows) {
     constexpr int E = PPL * 64;
     __shared__ float red[LN_WARPS][E + 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2 g[PPL], dg[PPL], db[PPL];
+    float2 g[PPL], dg[PPL], db[PPL], dc[PPL];
 #pragma unroll
     for (int k = 0; k < PPL; ++k) {
         g[k] = *reinterpret_cast<const float2*>(gamma + 2 * (k * 32 + lane));
         dg[k] = make_float2(0.0f, 0.0f);
         db[k] = make_float2(0.0f, 0.0f);
+        dc[k] = make_float2(0.0f, 0.0f);
     }
     for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
         const size_t off = size_t(row) * (E / 2);
@@ -109,14 +111,18 @@ ln_bwd_kernel(const unsigned* __restrict__ dy, const unsigned* __restrict__ x, c
                 const float2 r = bf2_to_f2(__ldg(dres + off + k * 32 + lane));
                 a += r.x; c += r.y;
             }
-            dx[off + k * 32 + lane] = f2_to_bf2(a, c);
+            const unsigned packed = f2_to_bf2(a, c);
+            dx[off + k * 32 + lane] = packed;
+            // column sums of the stored (bf16-rounded) dx: the bias gradient of the Linear that produced this residual stream
+            const float2 r = bf2_to_f2(packed);
+            dc[k].x += r.x; dc[k].y += r.y;
         }
     }
     // CTA-level reduction of the per-lane column partials, then one atomic per column per CTA
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = 0; pass < (dxsum != nullptr ? 3 : 2); ++pass) {
 #pragma unroll
         for (int k = 0; k < PPL; ++k) {
-            const float2 v = pass == 0 ? dg[k] : db[k];
+            const float2 v = pass == 0 ? dg[k] : (pass == 1 ? db[k] : dc[k]);
             red[warp][2 * (k * 32 + lane)] = v.x;
             red[warp][2 * (k * 32 + lane) + 1] = v.y;
         }
@@ -125,7 +131,7 @@ ln_bwd_kernel(const unsigned* __restrict__ dy, const unsigned* __restrict__ x, c
             float s = 0.0f;
 #pragma unroll
             for (int w = 0; w < LN_WARPS; ++w) s += red[w][c];
-            atomicAdd((pass == 0 ? dgamma : dbeta) + c, s);
+            atomicAdd((pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum)) + c, s);
         }
         __syncthreads();
     }
@@ -287,6 +293,28 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     }
 }
 
+// RandomMixup_DCT on the embed input (cls_transforms.py:135-182): out[b] = lam0 * x[b] + lam1 * x[b-1 mod B], the batch
+// rolled by one image.  lam lives in device memory (a captured CUDA graph replays with a fresh draw).  per_image = bf16
+// elements per image, a multiple of 8.
+__global__ void __launch_bounds__(256)
+mixup_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, const float* __restrict__ lam, int batch, size_t vec_per_image) {
+    const float l0 = lam[0], l1 = lam[1];
+    const size_t total = size_t(batch) * vec_per_image;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const size_t b = i / vec_per_image, r = i - b * vec_per_image;
+        const size_t j = (b == 0 ? size_t(batch) - 1 : b - 1) * vec_per_image + r;
+        const uint4 a = __ldg(x + i), c = __ldg(x + j);
+        const unsigned aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+        unsigned o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 fa = bf2_to_f2(aw[e]), fc = bf2_to_f2(cw[e]);
+            o[e] = f2_to_bf2(fa.x * l0 + fc.x * l1, fa.y * l0 + fc.y * l1);
+        }
+        out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 static int g_sms = 0;
 static int sms() {
     if (g_sms == 0) {
@@ -319,7 +347,7 @@ int rgbnm_layernorm_fwd(const void* x, const float* gamma, const float* beta, vo
 }
 
 int rgbnm_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
-                        const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int emb, void* stream) {
+                        const void* dres, void* dx, float* dgamma, float* dbeta, float* dxsum, int rows, int emb, void* stream) {
     using namespace vitk;
     if (!dy || !x || !mean || !rstd || !gamma || !dx || !dgamma || !dbeta || rows < 0) return RGBNM_ERR_ARG;
     if (rows == 0) return RGBNM_OK;
@@ -329,10 +357,21 @@ int rgbnm_layernorm_bwd(const void* dy, const void* x, const float* mean, const 
     const unsigned* b = static_cast<const unsigned*>(x);
     const unsigned* r = static_cast<const unsigned*>(dres);
     unsigned* o = static_cast<unsigned*>(dx);
-    if (emb == 192) ln_bwd_kernel<3><<<grid, LN_WARPS * 32, 0, st>>>(a, b, mean, rstd, gamma, r, o, dgamma, dbeta, rows);
-    else if (emb == 384) ln_bwd_kernel<6><<<grid, LN_WARPS * 32, 0, st>>>(a, b, mean, rstd, gamma, r, o, dgamma, dbeta, rows);
-    else if (emb == 768) ln_bwd_kernel<12><<<grid, LN_WARPS * 32, 0, st>>>(a, b, mean, rstd, gamma, r, o, dgamma, dbeta, rows);
+    if (emb == 192) ln_bwd_kernel<3><<<grid, LN_WARPS * 32, 0, st>>>(a, b, mean, rstd, gamma, r, o, dgamma, dbeta, dxsum, rows);
+    else if (emb == 384) ln_bwd_kernel<6><<<grid, LN_WARPS * 32, 0, st>>>(a, b, mean, rstd, gamma, r, o, dgamma, dbeta, dxsum, rows);
+    else if (emb == 768) ln_bwd_kernel<12><<<grid, LN_WARPS * 32, 0, st>>>(a, b, mean, rstd, gamma, r, o, dgamma, dbeta, dxsum, rows);
     else return RGBNM_ERR_UNSUPPORTED;
+    RGBNM_CUDA_CHECK(cudaGetLastError());
+    return RGBNM_OK;
+}
+
+int rgbnm_mixup_bf16(const void* x, void* out, const float* lam, int batch, long long per_image, void* stream) {
+    if (!x || !out || !lam || batch <= 0 || per_image <= 0 || (per_image & 7) || x == out) return RGBNM_ERR_ARG;
+    const size_t total = size_t(batch) * size_t(per_image / 8);
+    size_t blocks = (total + 255) / 256;
+    const int grid = int(blocks > size_t(vitk::sms()) * 16 ? size_t(vitk::sms()) * 16 : blocks);
+    vitk::mixup_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(out), lam,
+                                                                           batch, size_t(per_image / 8));
     RGBNM_CUDA_CHECK(cudaGetLastError());
     return RGBNM_OK;
 }

@@ -22,11 +22,22 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, y: t
 
 
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor,
-                  dres: Optional[torch.Tensor], dx: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor) -> None:
+                  dres: Optional[torch.Tensor], dx: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor,
+                  dxsum: Optional[torch.Tensor] = None) -> None:
+    """dxsum (fp32 [emb], optional) += column sums of dx: the bias gradient of the Linear feeding this residual stream."""
     rows, emb = x.shape
     _lib.check(_L().rgbnm_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
                                         None if dres is None else dres.data_ptr(), dx.data_ptr(), dgamma.data_ptr(),
-                                        dbeta.data_ptr(), rows, emb, _lib.stream_ptr()), "rgbnm_layernorm_bwd")
+                                        dbeta.data_ptr(), None if dxsum is None else dxsum.data_ptr(), rows, emb,
+                                        _lib.stream_ptr()), "rgbnm_layernorm_bwd")
+
+
+def mixup(x: torch.Tensor, out: torch.Tensor, lam: torch.Tensor) -> None:
+    """out[b] = lam[0] * x[b] + lam[1] * x[b-1] on a contiguous bf16 batch (RandomMixup_DCT, cls_transforms.py:135-182)."""
+    if x.dtype != torch.bfloat16 or not x.is_contiguous() or not out.is_contiguous() or out.shape != x.shape:
+        raise ValueError("rgbnm mixup: contiguous bf16 tensors of equal shape expected")
+    _lib.check(_L().rgbnm_mixup_bf16(x.data_ptr(), out.data_ptr(), lam.data_ptr(), x.shape[0], x[0].numel(), _lib.stream_ptr()),
+               "rgbnm_mixup_bf16")
 
 
 def colsum(a: torch.Tensor, out: torch.Tensor) -> None:

@@ -50,6 +50,7 @@ class TrainStage:
         self.g_fb: Optional[torch.cuda.CUDAGraph] = None
         self.g_opt: Optional[torch.cuda.CUDAGraph] = None
         self.x_static = torch.zeros((batch, V.TOKENS, V.IN_FEAT), dtype=torch.bfloat16, device=self.dev)
+        self.x_mixed = torch.zeros_like(self.x_static)
         self.y_static = torch.zeros((batch,), dtype=torch.int64, device=self.dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
         self.launches_per_step = 0
@@ -66,7 +67,8 @@ class TrainStage:
     def _fwd_bwd(self):
         x, y, lam = self.x_static, self.y_static, self.lam
         # RandomMixup_DCT: batch rolled by one, lambda from a sorted Dirichlet(alpha, alpha) draw
-        xm = (x.float() * lam[0] + x.roll(1, 0).float() * lam[1]).to(torch.bfloat16)
+        xm = self.x_mixed
+        K.mixup(x, xm, lam)
         onehot = torch.nn.functional.one_hot(y, 1000).float()
         soft = onehot * lam[0] + onehot.roll(1, 0) * lam[1]
         logits = self.eng.forward(xm)

@@ -259,8 +259,9 @@ class ViTEngine:
         else:
             self._gemm(dy, x, G.EPI_WGRAD_ATOMIC, out_f32=gw, splits=splits)
 
-    def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, lin: _Lin, splits: int) -> None:
-        """dW += dy^T x, db += colsum(dy) into the flat gradient buffer (reference parameter order)."""
+    def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, lin: _Lin, splits: int, bias_done: bool = False) -> None:
+        """dW += dy^T x, db += colsum(dy) into the flat gradient buffer (reference parameter order).  bias_done: the
+        LayerNorm backward that produced dy already accumulated its column sums into the bias gradient."""
         if lin.qkv_heads:
             # the kernel-side qkv layout is q|k|v head-major: accumulate in that order, then add back row-permuted
             gw, gb, tmp = self.qkv_gw, self.qkv_gb, self.qkv_tmp
@@ -274,8 +275,9 @@ class ViTEngine:
             self.launches += 3
         else:
             self._wgrad_gemm(dy, x, self.grad_of(lin.weight), splits)
-            K.colsum(dy, self.grad_of(lin.bias))
-            self.launches += 1
+            if not bias_done:
+                K.colsum(dy, self.grad_of(lin.bias))
+                self.launches += 1
 
     def backward(self, dlogits: torch.Tensor, zero_grad: bool = True) -> None:
         """Fill the flat gradient buffer (and nothing else) from d(loss)/d(logits), (B, n_classes) fp32."""
@@ -296,31 +298,35 @@ class ViTEngine:
         dpooled = dz.mm(w1) * (1.0 / TOKENS)
         dA, dB, dC = bufs["dA"], bufs["dB"], bufs["dC"]
         dA.view(B, TOKENS, E).copy_(dpooled.to(torch.bfloat16).unsqueeze(1).expand(B, TOKENS, E))
+        # every LayerNorm backward below also accumulates the column sums of the dx it writes: that is the bias gradient of
+        # the Linear whose output (+ residual) this dx is the gradient of (fc2 of the layer, proj of the layer, the embed)
         K.layernorm_bwd(dA, bufs["x_last"], bufs["meanH"], bufs["rstdH"], self.lnh[0].data, None, dB,
-                        self.grad_of(self.lnh[0]), self.grad_of(self.lnh[1]))
+                        self.grad_of(self.lnh[0]), self.grad_of(self.lnh[1]),
+                        dxsum=self.grad_of(self.layers[-1]["fc2"].bias))
         self.launches += 1
         dx, spare1, spare2 = dB, dA, dC
         for l in reversed(range(self.depth)):
             ly, b = self.layers[l], bufs["layers"][l]
             # ---- MLP branch: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid)))) ----
-            self._wgrad(dx, b["f"], ly["fc2"], splits)
+            self._wgrad(dx, b["f"], ly["fc2"], splits, bias_done=True)
             du = self._gemm(dx, ly["fc2"].wt, G.EPI_DGELU, aux=b["u"], out=bufs["dU"])
             self._wgrad(du, b["h2"], ly["fc1"], splits)
             dh2 = self._gemm(du, ly["fc1"].wt, G.EPI_STORE, out=spare1)
             K.layernorm_bwd(dh2, b["x_mid"], b["mean2"], b["rstd2"], ly["ln2"][0].data, dx, spare2,
-                            self.grad_of(ly["ln2"][0]), self.grad_of(ly["ln2"][1]))
+                            self.grad_of(ly["ln2"][0]), self.grad_of(ly["ln2"][1]), dxsum=self.grad_of(ly["proj"].bias))
             self.launches += 1
             dx_mid = spare2
             # ---- attention branch: x_mid = x_in + proj(attn(qkv(LN1(x_in)))) ----
-            self._wgrad(dx_mid, b["o"], ly["proj"], splits)
+            self._wgrad(dx_mid, b["o"], ly["proj"], splits, bias_done=True)
             do = self._gemm(dx_mid, ly["proj"].wt, G.EPI_STORE, out=bufs["dO"])
             self._attn_bwd(do, b["qkv"], b["o"], b["lse"], bufs["dQKV"], B)
             self._wgrad(bufs["dQKV"], b["h1"], ly["qkv"], splits)
             dh1 = self._gemm(bufs["dQKV"], ly["qkv"].wt, G.EPI_STORE, out=spare1)
+            below = self.layers[l - 1]["fc2"].bias if l > 0 else self.lin_embed.bias
             K.layernorm_bwd(dh1, b["x_in"], b["mean1"], b["rstd1"], ly["ln1"][0].data, dx_mid, dx,
-                            self.grad_of(ly["ln1"][0]), self.grad_of(ly["ln1"][1]))
+                            self.grad_of(ly["ln1"][0]), self.grad_of(ly["ln1"][1]), dxsum=self.grad_of(below))
             self.launches += 1
-        self._wgrad(dx, bufs["x_embed_in"], self.lin_embed, splits)
+        self._wgrad(dx, bufs["x_embed_in"], self.lin_embed, splits, bias_done=True)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -92,9 +92,21 @@ def test_layernorm_fwd_bwd(E):
     (ref * dy.float()).sum().backward()
     dx = torch.empty_like(x)
     dg, db = torch.zeros(E, device=DEV), torch.zeros(E, device=DEV)
-    K.layernorm_bwd(dy, x, mean, rstd, g, dres, dx, dg, db)
+    dsum = torch.zeros(E, device=DEV)
+    K.layernorm_bwd(dy, x, mean, rstd, g, dres, dx, dg, db, dxsum=dsum)
     assert _rel(dx, xr.grad + dres.float()) < 1e-2
     assert _rel(dg, gr.grad) < 1e-4 and _rel(db, br.grad) < 1e-4
+    assert _rel(dsum, dx.float().sum(0)) < 1e-5            # fused bias gradient = column sums of the stored dx
+
+
+def test_mixup_kernel():
+    torch.manual_seed(9)
+    x = _bf(7, 196, 384)
+    lam = torch.tensor([0.8, 0.2], device=DEV)
+    out = torch.empty_like(x)
+    K.mixup(x, out, lam)
+    ref = (x.float() * lam[0] + x.roll(1, 0).float() * lam[1]).to(torch.bfloat16)        # cls_transforms.py:176-179
+    assert torch.equal(out, ref)
 
 
 @pytest.mark.parametrize("B,H", [(1, 1), (2, 3), (5, 6), (37, 6)])
