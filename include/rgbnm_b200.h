@@ -166,6 +166,8 @@ typedef struct {
     int splits;                 /* WGRAD_ATOMIC: split count over the reduction; <= 0 = chosen by the library */
     float alpha;
     int trans_out;              /* WGRAD_ATOMIC: out_f32[n * ldo + m] += ... (lets the caller put the longer side on M) */
+    int perm_heads;             /* WGRAD_ATOMIC: > 0: the M index is in the kernel's qkv order (q|k|v head-major, rgbnm_weight_prep); */
+    int perm_head_dim;          /*   results are added at the reference row h*3D + d*3 + which ("(h d qkv)", plainvit.py:447) */
 } rgbnm_gemm_args;
 
 int rgbnm_gemm_bf16(const rgbnm_gemm_args* args, void* stream);
@@ -186,8 +188,9 @@ int rgbnm_layernorm_bwd(const void* dy, const void* x, const float* mean, const 
 /* RandomMixup_DCT on the bf16 embed input (utils/cls_transforms.py:135-182): out[b] = lam[0] * x[b] + lam[1] * x[(b-1) mod batch];
  * lam = 2 device floats; per_image = elements per image (multiple of 8); out != x. */
 int rgbnm_mixup_bf16(const void* x, void* out, const float* lam, int batch, long long per_image, void* stream);
-/* out[cols] += column sums of a bf16 matrix (bias gradients of nn.Linear) */
-int rgbnm_colsum_bf16(const void* a, long long ld, int rows, int cols, float* out, void* stream);
+/* out[cols] += column sums of a bf16 matrix (bias gradients of nn.Linear).  qkv_heads > 0: the columns are in the kernel's
+ * qkv order and column c is added at its reference position (see perm_heads above). */
+int rgbnm_colsum_bf16(const void* a, long long ld, int rows, int cols, float* out, int qkv_heads, int head_dim, void* stream);
 /* fp32 master weight [n][k] -> bf16 working copy (rows regrouped q|k|v head-major when qkv_heads > 0,
  * undoing the "(h d qkv)" interleave of plainvit.py:447) and, if wt_bf16 != NULL, its transpose [k][n] */
 int rgbnm_weight_prep(const float* w, int n, int k, int qkv_heads, int head_dim, void* w_bf16, void* wt_bf16, void* stream);

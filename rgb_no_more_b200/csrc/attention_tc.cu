@@ -327,30 +327,33 @@ struct BwdParams {
 };
 
 // Dr[b][h][q] = sum_d dO[b][q][h*64+d] * O[b][q][h*64+d]
+// 8 lanes share one (token, head) segment of 128 bytes, 16 bytes each: consecutive threads read consecutive 16-byte
+// chunks of dO / O (fully coalesced), then three shuffles reduce the partial dot products.
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O, float* __restrict__ dvec,
                      int B, int N, int H) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (b*N + q) * H + h
-    if (idx >= (long long)B * N * H) return;
-    const int h = int(idx % H);
-    const long long row = idx / H;
-    const int q = int(row % N), b = int(row / N);
-    const uint4* a = reinterpret_cast<const uint4*>(dO + row * (long long)(H * HD) + h * HD);
-    const uint4* c = reinterpret_cast<const uint4*>(O + row * (long long)(H * HD) + h * HD);
-    uint4 x[8], y[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { x[k] = __ldg(a + k); y[k] = __ldg(c + k); }
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // 16-byte chunk index
+    const long long seg = idx >> 3;                                                // (b*N + q) * H + h
+    const bool live = seg < (long long)B * N * H;
     float s = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const unsigned xw[4] = {x[k].x, x[k].y, x[k].z, x[k].w}, yw[4] = {y[k].x, y[k].y, y[k].z, y[k].w};
+    if (live) {
+        const uint4 x = __ldg(reinterpret_cast<const uint4*>(dO) + idx), y = __ldg(reinterpret_cast<const uint4*>(O) + idx);
+        const unsigned xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             s += __uint_as_float(xw[e] << 16) * __uint_as_float(yw[e] << 16);
             s += __uint_as_float(xw[e] & 0xffff0000u) * __uint_as_float(yw[e] & 0xffff0000u);
         }
     }
-    dvec[((long long)b * H + h) * N + q] = s;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (live && (idx & 7) == 0) {
+        const int h = int(seg % H);
+        const long long row = seg / H;
+        const int q = int(row % N), b = int(row / N);
+        dvec[((long long)b * H + h) * N + q] = s;
+    }
 }
 
 // TMEM column of the bf16 A operand for reduction step k (16 score columns = 8 packed columns per step)
@@ -654,7 +657,7 @@ extern "C" int rgbnm_attention_bwd(const void* dout, const void* qkv, const void
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long ldq = 3LL * H * HD, ldo = (long long)H * HD;
     {
-        const long long total = (long long)B * N * H;
+        const long long total = (long long)B * N * H * 8;          // 16-byte chunks: 8 per (token, head)
         attn_bwd_prep_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dout),
                                                                             static_cast<const __nv_bfloat16*>(o), dvec, B, N, H);
         RGBNM_CUDA_CHECK(cudaGetLastError());

@@ -52,6 +52,7 @@ struct Params {
     float alpha;
     int trans_out;            // atomic epilogue: out[n * ldo + m] instead of out[m * ldo + n]
     int vec_ok;               // atomic epilogue: 16-byte aligned rows -> red.global.add.v4.f32
+    int perm_heads, perm_hd;  // atomic epilogue: M index is in kernel qkv order (q|k|v head-major) -> reference row h*3D + d*3 + which
 };
 
 // ---- PTX pieces that only the CTA-pair kernel needs ------------------------------------------------
@@ -380,8 +381,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     }
                 }
                 if (EPI == EPI_ATOMIC || EPI == EPI_F32) {
-                    const int gr = m0 + row;
-                    if (gr < p.M) {
+                    int gr = m0 + row;
+                    const bool in_range = gr < p.M;
+                    if (EPI == EPI_ATOMIC && p.perm_heads > 0 && in_range) {
+                        // undo the qkv row regrouping of rgbnm_weight_prep: kernel row = which*(H*D) + h*D + d
+                        const int hd_all = p.perm_heads * p.perm_hd;
+                        const int which = gr / hd_all, rem = gr - which * hd_all;
+                        const int h = rem / p.perm_hd, d = rem - h * p.perm_hd;
+                        gr = h * (3 * p.perm_hd) + d * 3 + which;
+                    }
+                    if (in_range) {
                         if (EPI == EPI_F32) {
                             float* o = p.out_f32 + size_t(gr) * p.ldo + col0;
 #pragma unroll
@@ -501,6 +510,8 @@ static int launch(const rgbnm_gemm_args& a, cudaStream_t st) {
     p.bias = a.bias; p.posemb = a.posemb; p.pos_period = a.pos_period > 0 ? a.pos_period : 1;
     p.out_f32 = a.out_f32; p.ldo = a.ldo; p.alpha = a.alpha;
     p.trans_out = a.trans_out;
+    p.perm_heads = a.perm_heads; p.perm_hd = a.perm_head_dim;
+    if (a.perm_heads > 0 && (a.perm_head_dim <= 0 || a.M != 3 * a.perm_heads * a.perm_head_dim)) return RGBNM_ERR_ARG;
     p.vec_ok = (!a.trans_out && (reinterpret_cast<uintptr_t>(a.out_f32) % 16 == 0) && (a.ldo % 4 == 0) && (a.N % 4 == 0)) ? 1 : 0;
     const int tiles = p.m_tiles * p.n_tiles * p.splits;
     const int clusters = tiles < clusters_max ? tiles : clusters_max;

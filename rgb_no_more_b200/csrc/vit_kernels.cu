@@ -22,6 +22,12 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// kernel qkv order (which*(H*D) + h*D + d) -> reference order (h*3D + d*3 + which); plainvit.py:447
+__device__ __forceinline__ int qkv_unperm(int r, int heads, int hd) {
+    const int which = r / (heads * hd), rem = r - which * heads * hd;
+    const int h = rem / hd, d = rem - h * hd;
+    return h * (3 * hd) + d * 3 + which;
+}
 __device__ __forceinline__ float2 bf2_to_f2(unsigned w) {
     return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
@@ -143,7 +149,7 @@ ln_bwd_kernel(const unsigned* __restrict__ dy, const unsigned* __restrict__ x, c
 // CTA = 8 warps on 8 interleaved row streams; grid (ceil(cols/256), row chunks).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-colsum_kernel(const __nv_bfloat16* __restrict__ a, long long ld, int rows, int cols, float* __restrict__ out) {
+colsum_kernel(const __nv_bfloat16* __restrict__ a, long long ld, int rows, int cols, float* __restrict__ out, int heads, int hd) {
     __shared__ float red[8][256 + 8];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c0 = blockIdx.x * 256 + 8 * lane;
@@ -178,7 +184,7 @@ colsum_kernel(const __nv_bfloat16* __restrict__ a, long long ld, int rows, int c
 #pragma unroll
     for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
     const int c = blockIdx.x * 256 + threadIdx.x;
-    if (c < cols) atomicAdd(out + c, s);
+    if (c < cols) atomicAdd(out + (heads > 0 ? qkv_unperm(c, heads, hd) : c), s);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -376,14 +382,15 @@ int rgbnm_mixup_bf16(const void* x, void* out, const float* lam, int batch, long
     return RGBNM_OK;
 }
 
-int rgbnm_colsum_bf16(const void* a, long long ld, int rows, int cols, float* out, void* stream) {
+int rgbnm_colsum_bf16(const void* a, long long ld, int rows, int cols, float* out, int qkv_heads, int head_dim, void* stream) {
     if (!a || !out || rows < 0 || cols <= 0 || (ld & 7) || (cols & 7)) return RGBNM_ERR_ARG;
+    if (qkv_heads > 0 && cols != 3 * qkv_heads * head_dim) return RGBNM_ERR_ARG;
     if (rows == 0) return RGBNM_OK;
     const int gx = (cols + 255) / 256;
     int gy = (vitk::sms() * 4 + gx - 1) / gx;
     if (gy > (rows + 7) / 8) gy = (rows + 7) / 8;
     vitk::colsum_kernel<<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(a), ld, rows, cols, out);
+        static_cast<const __nv_bfloat16*>(a), ld, rows, cols, out, qkv_heads, head_dim);
     RGBNM_CUDA_CHECK(cudaGetLastError());
     return RGBNM_OK;
 }

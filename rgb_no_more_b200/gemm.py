@@ -19,7 +19,8 @@ class GemmArgs(C.Structure):
                 ("bias", C.c_void_p), ("posemb", C.c_void_p), ("out_f32", C.c_void_p),
                 ("lda", C.c_longlong), ("ldb", C.c_longlong), ("ldc", C.c_longlong), ("ldaux", C.c_longlong),
                 ("ldo", C.c_longlong), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("epilogue", C.c_int),
-                ("pos_period", C.c_int), ("splits", C.c_int), ("alpha", C.c_float), ("trans_out", C.c_int)]
+                ("pos_period", C.c_int), ("splits", C.c_int), ("alpha", C.c_float), ("trans_out", C.c_int),
+                ("perm_heads", C.c_int), ("perm_head_dim", C.c_int)]
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -34,7 +35,7 @@ def _check_bf16(t, name):
 def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int = EPI_STORE, bias: Optional[torch.Tensor] = None,
          aux: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
          posemb: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None, splits: int = 0,
-         alpha: float = 1.0, trans_out: bool = False):
+         alpha: float = 1.0, trans_out: bool = False, perm_heads: int = 0, perm_head_dim: int = 0):
     """Forward / dgrad form: a [M,K], b [N,K] (both row-major, K contiguous) -> out [M,N].
     For EPI_WGRAD_ATOMIC: a [T,M] and b [T,N] (T = reduction/token index) -> out_f32 [M,N] += alpha * a^T b
     (trans_out: out_f32 [N,M] += alpha * b^T a, so the caller can put the longer side on the 256-row tile axis);
@@ -58,6 +59,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int = EPI_STORE, bias: Opti
     args.splits = splits
     args.alpha = alpha
     args.trans_out = 1 if trans_out else 0
+    args.perm_heads, args.perm_head_dim = perm_heads, perm_head_dim     # WGRAD_ATOMIC: M index kernel-qkv order -> reference rows
     ret = None
     if epilogue in (EPI_WGRAD_ATOMIC, EPI_F32):
         if out_f32 is None:

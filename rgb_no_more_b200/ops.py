@@ -40,10 +40,11 @@ def mixup(x: torch.Tensor, out: torch.Tensor, lam: torch.Tensor) -> None:
                "rgbnm_mixup_bf16")
 
 
-def colsum(a: torch.Tensor, out: torch.Tensor) -> None:
+def colsum(a: torch.Tensor, out: torch.Tensor, qkv_heads: int = 0, head_dim: int = 0) -> None:
+    """out += column sums of a.  qkv_heads > 0: columns of `a` are in the kernel's q|k|v order, `out` in reference order."""
     rows, cols = a.shape
-    _lib.check(_L().rgbnm_colsum_bf16(a.data_ptr(), a.stride(0), rows, cols, out.data_ptr(), _lib.stream_ptr()),
-               "rgbnm_colsum_bf16")
+    _lib.check(_L().rgbnm_colsum_bf16(a.data_ptr(), a.stride(0), rows, cols, out.data_ptr(), qkv_heads, head_dim,
+                                      _lib.stream_ptr()), "rgbnm_colsum_bf16")
 
 
 def weight_prep(w: torch.Tensor, wb: torch.Tensor, wt: Optional[torch.Tensor], qkv_heads: int = 0, head_dim: int = 0) -> None:

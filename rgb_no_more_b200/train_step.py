@@ -122,8 +122,8 @@ class TrainStage:
 
     def _allreduce(self):
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.eng.flat_grad)          # one flat SUM allreduce; 1/world folded into the optimiser kernel
+            from . import ddp
+            ddp.allreduce_flat(self.eng.flat_grad, self.world)   # one flat SUM allreduce; 1/world folded into the optimiser kernel (hyper[7])
 
     def _capture(self):
         # warm up on a side stream (lazy allocations, cuTensorMap encodes, cuBLAS handles of the tiny head ops)

@@ -262,8 +262,14 @@ class ViTEngine:
     def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, lin: _Lin, splits: int, bias_done: bool = False) -> None:
         """dW += dy^T x, db += colsum(dy) into the flat gradient buffer (reference parameter order).  bias_done: the
         LayerNorm backward that produced dy already accumulated its column sums into the bias gradient."""
-        if lin.qkv_heads:
-            # the kernel-side qkv layout is q|k|v head-major: accumulate in that order, then add back row-permuted
+        if lin.qkv_heads and not _V1:
+            # the kernel-side qkv layout is q|k|v head-major: the epilogue / column-sum kernels add each row at its
+            # reference position ("(h d qkv)", plainvit.py:447), so the flat buffer keeps the reference layout
+            self._gemm(dy, x, G.EPI_WGRAD_ATOMIC, out_f32=self.grad_of(lin.weight), splits=splits,
+                       perm_heads=self.H, perm_head_dim=self.D)
+            K.colsum(dy, self.grad_of(lin.bias), self.H, self.D)
+            self.launches += 1
+        elif lin.qkv_heads:
             gw, gb, tmp = self.qkv_gw, self.qkv_gb, self.qkv_tmp
             gw.zero_()
             gb.zero_()

@@ -143,6 +143,17 @@ def test_colsum_weightprep_adamw():
     out = torch.zeros(1152, device=DEV)
     K.colsum(a, out)
     assert _rel(out, a.float().sum(0)) < 1e-5
+    # column sums / weight gradients delivered in the reference "(h d qkv)" order from kernel-order (q|k|v) inputs
+    Hh, Dd = 6, 64
+    ref_order = a.float().sum(0).view(3, Hh, Dd).permute(1, 2, 0).reshape(-1)
+    outp = torch.zeros(1152, device=DEV)
+    K.colsum(a, outp, Hh, Dd)
+    assert _rel(outp, ref_order) < 1e-5
+    xg = _bf(5000, 384)
+    gwp = torch.zeros(1152, 384, device=DEV)
+    G.gemm(a, xg, G.EPI_WGRAD_ATOMIC, out_f32=gwp, perm_heads=Hh, perm_head_dim=Dd)
+    gref = (a.float().t() @ xg.float()).view(3, Hh, Dd, 384).permute(1, 2, 0, 3).reshape(1152, 384)
+    assert _rel(gwp, gref) < 1e-4
     # weight prep: plain and qkv-regrouped
     H, D, E = 6, 64, 384
     w = torch.randn(3 * H * D, E, device=DEV)
