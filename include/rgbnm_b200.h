@@ -194,6 +194,14 @@ int rgbnm_colsum_bf16(const void* a, long long ld, int rows, int cols, float* ou
 /* fp32 master weight [n][k] -> bf16 working copy (rows regrouped q|k|v head-major when qkv_heads > 0,
  * undoing the "(h d qkv)" interleave of plainvit.py:447) and, if wt_bf16 != NULL, its transpose [k][n] */
 int rgbnm_weight_prep(const float* w, int n, int k, int qkv_heads, int head_dim, void* w_bf16, void* wt_bf16, void* stream);
+/* The same for every Linear of the model in one launch.  descs_dev: device array; first_tile = running sum of
+ * ceil(n/32) * ceil(k/32) over the preceding descriptors (total_tiles = the sum over all); bias / bias_k (may be NULL):
+ * qkv bias regrouped into kernel order alongside. */
+typedef struct {
+    const float* w; void* w_bf16; void* wt_bf16; const float* bias; float* bias_k;
+    int32_t n, k, qkv_heads, head_dim, first_tile, pad;
+} rgbnm_wprep_desc;
+int rgbnm_weight_prep_batch(const rgbnm_wprep_desc* descs_dev, int n_desc, int total_tiles, void* stream);
 int rgbnm_qkv_perm_vec(const float* src, float* dst, int n, int heads, int head_dim, int inverse, void* stream);
 int rgbnm_qkv_unperm_rows_add(const float* src, float* dst, int n, int k, int heads, int head_dim, void* stream);
 /* *out += sum(g^2) */

@@ -230,6 +230,50 @@ weight_prep_kernel(const float* __restrict__ w, int N, int K, int heads, int hd,
     }
 }
 
+// All Linear layers of the model in ONE launch (49 launches of a few microseconds each otherwise dominate the refresh):
+// block -> descriptor by a scan over the per-descriptor first-tile table, then the body of weight_prep_kernel.  The block
+// owning tile 0 of a qkv descriptor also regroups that layer's bias into kernel order.
+__global__ void __launch_bounds__(256)
+weight_prep_batch_kernel(const rgbnm_wprep_desc* __restrict__ descs, int n_desc) {
+    __shared__ float tile[32][33];
+    __shared__ int s_d;
+    if (threadIdx.x == 0) {
+        int d = 0;
+        while (d + 1 < n_desc && int(blockIdx.x) >= descs[d + 1].first_tile) ++d;
+        s_d = d;
+    }
+    __syncthreads();
+    const rgbnm_wprep_desc D = descs[s_d];
+    const int t = int(blockIdx.x) - D.first_tile;
+    const int tiles_k = (D.k + 31) / 32;
+    const int k0 = (t % tiles_k) * 32, n0 = (t / tiles_k) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float* __restrict__ w = D.w;
+    __nv_bfloat16* __restrict__ wb = static_cast<__nv_bfloat16*>(D.w_bf16);
+    __nv_bfloat16* __restrict__ wt = static_cast<__nv_bfloat16*>(D.wt_bf16);
+    const int N = D.n, K = D.k, heads = D.qkv_heads, hd = D.head_dim;
+    for (int i = ty; i < 32; i += 8) {
+        const int n = n0 + i, k = k0 + tx;
+        float v = 0.0f;
+        if (n < N && k < K) {
+            v = w[size_t(n) * K + k];
+            const int np = heads > 0 ? qkv_perm(n, heads, hd) : n;
+            wb[size_t(np) * K + k] = __float2bfloat16_rn(v);
+        }
+        tile[i][tx] = v;
+    }
+    __syncthreads();
+    if (wt != nullptr) {
+        for (int i = ty; i < 32; i += 8) {
+            const int k = k0 + i, n = n0 + tx;
+            if (n < N && k < K) wt[size_t(k) * N + (heads > 0 ? qkv_perm(n, heads, hd) : n)] = __float2bfloat16_rn(tile[tx][i]);
+        }
+    }
+    if (t == 0 && heads > 0 && D.bias != nullptr) {
+        for (int i = threadIdx.x; i < N; i += 256) D.bias_k[qkv_perm(i, heads, hd)] = D.bias[i];
+    }
+}
+
 // bias (fp32, reference order) -> fp32 working copy in kernel order; gradient (kernel order) -> reference order
 __global__ void perm_vec_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int heads, int hd, int inverse) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -400,6 +444,13 @@ int rgbnm_weight_prep(const float* w, int n, int k, int qkv_heads, int head_dim,
     if (qkv_heads > 0 && n != 3 * qkv_heads * head_dim) return RGBNM_ERR_ARG;
     vitk::weight_prep_kernel<<<dim3((k + 31) / 32, (n + 31) / 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         w, n, k, qkv_heads, head_dim, static_cast<__nv_bfloat16*>(w_bf16), static_cast<__nv_bfloat16*>(wt_bf16));
+    RGBNM_CUDA_CHECK(cudaGetLastError());
+    return RGBNM_OK;
+}
+
+int rgbnm_weight_prep_batch(const rgbnm_wprep_desc* descs_dev, int n_desc, int total_tiles, void* stream) {
+    if (!descs_dev || n_desc <= 0 || total_tiles <= 0) return RGBNM_ERR_ARG;
+    vitk::weight_prep_batch_kernel<<<total_tiles, 256, 0, static_cast<cudaStream_t>(stream)>>>(descs_dev, n_desc);
     RGBNM_CUDA_CHECK(cudaGetLastError());
     return RGBNM_OK;
 }

@@ -22,6 +22,12 @@ class JpegInfo(C.Structure):
                 ("hsamp", C.c_int32 * 3), ("vsamp", C.c_int32 * 3)]
 
 
+class WPrepDesc(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("w_bf16", C.c_void_p), ("wt_bf16", C.c_void_p), ("bias", C.c_void_p), ("bias_k", C.c_void_p),
+                ("n", C.c_int32), ("k", C.c_int32), ("qkv_heads", C.c_int32), ("head_dim", C.c_int32), ("first_tile", C.c_int32),
+                ("pad", C.c_int32)]
+
+
 class K0Tables(C.Structure):
     _fields_ = [("filters", C.c_void_p), ("posterize_lut", C.c_void_p)]
 
@@ -49,6 +55,7 @@ SIGNATURES = {
     "rgbnm_mixup_bf16": (_i, [_vp, _vp, _vp, _i, C.c_longlong, _vp]),
     "rgbnm_colsum_bf16": (_i, [_vp, C.c_longlong, _i, _i, _vp, _i, _i, _vp]),
     "rgbnm_weight_prep": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "rgbnm_weight_prep_batch": (_i, [_vp, _i, _i, _vp]),
     "rgbnm_qkv_perm_vec": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rgbnm_qkv_unperm_rows_add": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rgbnm_sumsq_f32": (_i, [_vp, C.c_longlong, _vp, _vp]),

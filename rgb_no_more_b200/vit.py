@@ -146,6 +146,7 @@ class ViTEngine:
         self.qkv_tmp = torch.zeros(3 * self.HD, dtype=torch.float32, device=device)
         self.posemb = sincos_posemb(14, 14, self.E, device)
         self._versions = None
+        self._wprep = None
         self.bufs = None
         self.batch = 0
         self.launches = 0
@@ -162,12 +163,26 @@ class ViTEngine:
 
     # -- weights ------------------------------------------------------------------------------------
     def refresh_weights(self) -> None:
-        """fp32 master -> bf16 working copies (+ transposes for dgrad, qkv rows regrouped q|k|v)."""
-        for lin in self._all_lins():
-            K.weight_prep(lin.weight.data, lin.wb, lin.wt, lin.qkv_heads, self.D if lin.qkv_heads else 0)
-            if lin.qkv_heads:
-                K.qkv_perm_vec(lin.bias.data, lin.bias_k, self.H, self.D, inverse=False)
-            self.launches += 1
+        """fp32 master -> bf16 working copies (+ transposes for dgrad, qkv rows and bias regrouped q|k|v): one launch
+        over a device-resident descriptor table (the pointers into the flat buffer never change)."""
+        if self._wprep is None:
+            import ctypes as C
+            import numpy as np
+            lins = self._all_lins()
+            arr = (_lib.WPrepDesc * len(lins))()
+            tiles = 0
+            for i, lin in enumerate(lins):
+                d = arr[i]
+                d.w, d.w_bf16, d.wt_bf16 = lin.weight.data.data_ptr(), lin.wb.data_ptr(), lin.wt.data_ptr()
+                d.bias = lin.bias.data.data_ptr() if lin.qkv_heads else None
+                d.bias_k = lin.bias_k.data_ptr() if lin.qkv_heads else None
+                d.n, d.k, d.qkv_heads, d.head_dim, d.first_tile = lin.n, lin.k, lin.qkv_heads, self.D if lin.qkv_heads else 0, tiles
+                tiles += -(-lin.n // 32) * -(-lin.k // 32)
+            host = torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy())
+            self._wprep = (host.to(self.dev), len(lins), tiles)
+        table, n, tiles = self._wprep
+        _lib.check(self._lib.rgbnm_weight_prep_batch(table.data_ptr(), n, tiles, _lib.stream_ptr()), "rgbnm_weight_prep_batch")
+        self.launches += 1
         self._versions = self._param_versions()
 
     def _param_versions(self):
