@@ -73,3 +73,13 @@ def synth_coefficients(batch: int, hb: int = 64, wb: int = 64, seed: int = SEED,
     y = np.clip(y.astype(np.int32) * q_luma, -1024, 1016) // q_luma
     c = np.clip(c.astype(np.int32) * q_chroma, -1024, 1016) // q_chroma
     return y.astype(np.int16), c.astype(np.int16), q
+
+
+def dequant_clamp_flags(y: np.ndarray, c: np.ndarray, q: np.ndarray) -> np.ndarray:
+    """Per image: 1 iff some dequantised coefficient leaves [-1024, 1016], i.e. the clamp of datasets.py:288-290 is
+    live (what rgbnm_jpeg_decode_batch reports for decoded files; here for generated coefficients)."""
+    n = y.shape[0]
+    yq = y.reshape(n, -1, 64).astype(np.int32) * q[:, 0:1, :].astype(np.int32)
+    cq = c.reshape(n, 2, -1, 64).astype(np.int32) * q[:, 1:3, None, :].astype(np.int32)
+    bad = (yq.min(axis=(1, 2)) < -1024) | (yq.max(axis=(1, 2)) > 1016) | (cq.min(axis=(1, 2, 3)) < -1024) | (cq.max(axis=(1, 2, 3)) > 1016)
+    return bad.astype(np.uint8)
