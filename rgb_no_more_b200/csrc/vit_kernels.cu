@@ -92,15 +92,37 @@ ln_bwd_kernel(const unsigned* __restrict__ dy, const unsigned* __restrict__ x, c
         db[k] = make_float2(0.0f, 0.0f);
         dc[k] = make_float2(0.0f, 0.0f);
     }
-    for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
+    // software-pipelined over the rows of this warp: the loads of the next row are issued before the current row's two
+    // warp reductions, so the ~1 us global-load latency overlaps them (each warp walks ~10 rows; 16 warps per SM)
+    const int stride = gridDim.x * LN_WARPS;
+    int row = blockIdx.x * LN_WARPS + warp;
+    unsigned n_dy[PPL], n_x[PPL], n_dr[PPL];
+    float n_mean = 0.0f, n_rstd = 0.0f;
+    auto issue = [&](int r) {
+        const size_t o = size_t(r) * (E / 2);
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+            n_dy[k] = __ldg(dy + o + k * 32 + lane);
+            n_x[k] = __ldg(x + o + k * 32 + lane);
+            n_dr[k] = dres != nullptr ? __ldg(dres + o + k * 32 + lane) : 0u;
+        }
+        n_mean = mean_in[r];
+        n_rstd = rstd_in[r];
+    };
+    if (row < rows) issue(row);
+    for (; row < rows; row += stride) {
         const size_t off = size_t(row) * (E / 2);
-        const float mean = mean_in[row], rstd = rstd_in[row];
+        const float mean = n_mean, rstd = n_rstd;
+        unsigned c_dy[PPL], c_x[PPL], c_dr[PPL];
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) { c_dy[k] = n_dy[k]; c_x[k] = n_x[k]; c_dr[k] = n_dr[k]; }
+        if (row + stride < rows) issue(row + stride);
         float2 d[PPL], xh[PPL];
         float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
         for (int k = 0; k < PPL; ++k) {
-            d[k] = bf2_to_f2(__ldg(dy + off + k * 32 + lane));
-            const float2 xv = bf2_to_f2(__ldg(x + off + k * 32 + lane));
+            d[k] = bf2_to_f2(c_dy[k]);
+            const float2 xv = bf2_to_f2(c_x[k]);
             xh[k] = make_float2((xv.x - mean) * rstd, (xv.y - mean) * rstd);
             dg[k].x += d[k].x * xh[k].x; dg[k].y += d[k].y * xh[k].y;
             db[k].x += d[k].x; db[k].y += d[k].y;
@@ -114,7 +136,7 @@ ln_bwd_kernel(const unsigned* __restrict__ dy, const unsigned* __restrict__ x, c
         for (int k = 0; k < PPL; ++k) {
             float a = rstd * (d[k].x - s1 - xh[k].x * s2), c = rstd * (d[k].y - s1 - xh[k].y * s2);
             if (dres != nullptr) {
-                const float2 r = bf2_to_f2(__ldg(dres + off + k * 32 + lane));
+                const float2 r = bf2_to_f2(c_dr[k]);
                 a += r.x; c += r.y;
             }
             const unsigned packed = f2_to_bf2(a, c);
@@ -236,14 +258,19 @@ weight_prep_kernel(const float* __restrict__ w, int N, int K, int heads, int hd,
 __global__ void __launch_bounds__(256)
 weight_prep_batch_kernel(const rgbnm_wprep_desc* __restrict__ descs, int n_desc) {
     __shared__ float tile[32][33];
+    __shared__ int s_first[256];
     __shared__ int s_d;
-    if (threadIdx.x == 0) {
-        int d = 0;
-        while (d + 1 < n_desc && int(blockIdx.x) >= descs[d + 1].first_tile) ++d;
-        s_d = d;
+    // block -> descriptor: the first-tile table is fetched by all threads at once (one load latency), then counted
+    for (int i = threadIdx.x; i < n_desc; i += 256) s_first[i] = descs[i].first_tile;
+    if (threadIdx.x == 0) s_d = 0;
+    __syncthreads();
+    {
+        int mine = 0;
+        for (int i = threadIdx.x; i < n_desc; i += 256) mine += (int(blockIdx.x) >= s_first[i]) ? 1 : 0;
+        if (mine) atomicAdd(&s_d, mine);
     }
     __syncthreads();
-    const rgbnm_wprep_desc D = descs[s_d];
+    const rgbnm_wprep_desc D = descs[s_d - 1];
     const int t = int(blockIdx.x) - D.first_tile;
     const int tiles_k = (D.k + 31) / 32;
     const int k0 = (t % tiles_k) * 32, n0 = (t / tiles_k) * 32;
@@ -449,7 +476,7 @@ int rgbnm_weight_prep(const float* w, int n, int k, int qkv_heads, int head_dim,
 }
 
 int rgbnm_weight_prep_batch(const rgbnm_wprep_desc* descs_dev, int n_desc, int total_tiles, void* stream) {
-    if (!descs_dev || n_desc <= 0 || total_tiles <= 0) return RGBNM_ERR_ARG;
+    if (!descs_dev || n_desc <= 0 || n_desc > 256 || total_tiles <= 0) return RGBNM_ERR_ARG;
     vitk::weight_prep_batch_kernel<<<total_tiles, 256, 0, static_cast<cudaStream_t>(stream)>>>(descs_dev, n_desc);
     RGBNM_CUDA_CHECK(cudaGetLastError());
     return RGBNM_OK;

@@ -103,7 +103,8 @@ class TrainStage:
     def step(self, x: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """x: (B,196,384) bf16 from FusedDCT, labels (B,) int64.  Returns the device scalar loss of this step."""
         self._set_hyper()
-        self.x_static.copy_(x, non_blocking=True)
+        if x.data_ptr() != self.x_static.data_ptr():          # FusedDCT can write straight into x_static (out=stage.x_static)
+            self.x_static.copy_(x, non_blocking=True)
         self.y_static.copy_(labels, non_blocking=True)
         if not self.use_graph:
             l0 = self.eng.launches
