@@ -249,9 +249,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer (leader CTA only) =====================
-        if (rank == 0 && lane == 0) {
+        // The whole warp walks the loop (uniform control flow, operands in uniform registers) and only the tcgen05
+        // instructions themselves are issued by one elected lane.  With the loop inside `if (lane == 0)` every descriptor
+        // lived in a per-thread register and each UMMA cost an ELECT / R2UR / PLOP3 / BRA.U.ANY sequence of ~200 cycles
+        // of single-thread latency -- more than the 96..130 cycles the UMMA itself keeps the tensor pipe busy.
+        if (rank == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(BM, BN <= 256 ? BN : 256, A_MN, B_MN);
             constexpr uint32_t idesc_hi = make_idesc_bf16(BM, 128, A_MN, B_MN);          // BN = 384: second UMMA of a step
+            // descriptors of stage 0, K step 0; a stage adds its byte size >> 4, a K step 2 (K-major: 32 B) or 128 (MN-major: 2048 B)
+            const uint64_t da0 = A_MN ? make_smem_desc_sw128(smem_u32(smem + L::OFF_A), BK * 128, 1024)
+                                      : make_smem_desc_sw128(smem_u32(smem + L::OFF_A), 0, 1024);
+            const uint64_t db0 = B_MN ? make_smem_desc_sw128(smem_u32(smem + L::OFF_B), BK * 128, 1024)
+                                      : make_smem_desc_sw128(smem_u32(smem + L::OFF_B), 0, 1024);
+            constexpr uint64_t A_KSTEP = A_MN ? 2048 / 16 : 32 / 16, B_KSTEP = B_MN ? 2048 / 16 : 32 / 16;
+            constexpr uint64_t B_HI = B_MN ? (2 * BK * 128) / 16 : (128 * 128) / 16;      // BN = 384: third 64-wide block of the B tile
+            const bool issuer = elect_one();
             int stage = 0, phase = 0, it = 0;
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
                 const int sp = tile % p.splits;
@@ -264,25 +276,22 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 for (int kb = k0; kb < k1; ++kb) {
                     mbar_wait(full + stage, phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + L::OFF_A + stage * L::A_BYTES);
-                    const uint32_t sb = smem_u32(smem + L::OFF_B + stage * L::B_BYTES);
+                    const uint64_t da = da0 + uint64_t(stage) * (L::A_BYTES / 16);
+                    const uint64_t db = db0 + uint64_t(stage) * (L::B_BYTES / 16);
+                    if (issuer) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, BK * 128, 1024)
-                                                 : make_smem_desc_sw128(sa + k * 32, 0, 1024);
-                        const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, BK * 128, 1024)
-                                                 : make_smem_desc_sw128(sb + k * 32, 0, 1024);
-                        tc_mma_f16_pair(d_tmem, da, db, idesc, (kb != k0) || (k != 0));
-                        if (BN > 256) {     // columns [256, 384): the third 64-wide block of each CTA's B tile
-                            const uint64_t db2 = B_MN ? make_smem_desc_sw128(sb + 2 * BK * 128 + k * 2048, BK * 128, 1024)
-                                                      : make_smem_desc_sw128(sb + 128 * 128 + k * 32, 0, 1024);
-                            tc_mma_f16_pair(d_tmem + 256, da, db2, idesc_hi, (kb != k0) || (k != 0));
+                        for (int k = 0; k < BK / 16; ++k) {
+                            tc_mma_f16_pair(d_tmem, da + k * A_KSTEP, db + k * B_KSTEP, idesc, (kb != k0) || (k != 0));
+                            if (BN > 256)       // columns [256, 384)
+                                tc_mma_f16_pair(d_tmem + 256, da + k * A_KSTEP, db + B_HI + k * B_KSTEP, idesc_hi, (kb != k0) || (k != 0));
                         }
+                        tc_commit_pair(empty + stage);
                     }
-                    tc_commit_pair(empty + stage);
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit_pair(tfull + acc);
+                if (issuer) tc_commit_pair(tfull + acc);
+                __syncwarp();
             }
         }
     } else if (warp == 2) {
