@@ -124,36 +124,47 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            // The whole warp walks the schedule (uniform control flow, descriptors in uniform registers); one elected lane
+            // issues the tcgen05 instructions.  Issued from inside `if (lane == 0)`, each of the 13 small P.V UMMAs cost
+            // ~200 cycles of single-thread ELECT / R2UR latency against the ~48 cycles it occupies the tensor pipe.
             constexpr uint32_t idesc_s = make_idesc_bf16(BM, NK, false, false);
             constexpr uint32_t idesc_o = make_idesc_bf16(BM, HD, false, true);      // B = V is MN-major (keys are the reduction)
             // Issue order  S0(0) S1(0) | PV0(i) S0(i+1) PV1(i) S1(i+1) | ...: a warpgroup gets its next score tile as soon
             // as its own O has left TMEM, without waiting for the other group's softmax, so the two groups drift half an
             // item apart and one group's exponentials cover the other group's MMA / barrier latencies.
             const int n_it = (p.items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+            const bool issuer = elect_one();
+            const uint64_t dq0 = make_smem_desc_sw128(smem_u32(smem), 0, 1024);                           // stage 0: Q0
+            const uint64_t dk0 = make_smem_desc_sw128(smem_u32(smem + 2 * Q_BYTES), 0, 1024);             // stage 0: K
+            const uint64_t dv0 = make_smem_desc_sw128(smem_u32(smem + 2 * Q_BYTES + KV_SLOT), 0, 1024);   // stage 0: V
             auto issue_s = [&](int it, int w) {
                 const int st = it & 1;
-                const uint32_t sq = smem_u32(smem + st * F_STAGE), sk = sq + 2 * Q_BYTES;
                 if (w == 0) mbar_wait(full_qk + st, (it >> 1) & 1);
                 mbar_wait(o_drained + w, (it & 1) ^ 1);              // the previous item's O_w has left this TMEM slot
                 tc_fence_after();
+                const uint64_t dq = dq0 + uint64_t(st) * (F_STAGE / 16) + uint64_t(w) * (Q_BYTES / 16);
+                const uint64_t dk = dk0 + uint64_t(st) * (F_STAGE / 16);
+                if (issuer) {
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
-                    tc_mma_f16(tmem_base + w * 256 + COL_S, make_smem_desc_sw128(sq + w * Q_BYTES + k * 32, 0, 1024),
-                               make_smem_desc_sw128(sk + k * 32, 0, 1024), idesc_s, k != 0);
-                tc_commit(s_full + w);
+                    for (int k = 0; k < HD / 16; ++k) tc_mma_f16(tmem_base + w * 256 + COL_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                    tc_commit(s_full + w);
+                }
+                __syncwarp();
             };
             auto issue_pv = [&](int it, int w) {
                 const int st = it & 1;
-                const uint32_t sv = smem_u32(smem + st * F_STAGE) + 2 * Q_BYTES + KV_SLOT;
                 if (w == 0) mbar_wait(full_v + st, (it >> 1) & 1);
                 mbar_wait(p_ready + w, it & 1);
                 tc_fence_after();
+                const uint64_t dv = dv0 + uint64_t(st) * (F_STAGE / 16);
+                if (issuer) {
 #pragma unroll
-                for (int k = 0; k < NK / 16; ++k)
-                    tc_mma_f16_ts(tmem_base + w * 256 + COL_O, tmem_base + w * 256 + COL_P + k * 8,
-                                  make_smem_desc_sw128(sv + k * 2048, 0, 1024), idesc_o, k != 0);
-                tc_commit(o_full + w);
+                    for (int k = 0; k < NK / 16; ++k)
+                        tc_mma_f16_ts(tmem_base + w * 256 + COL_O, tmem_base + w * 256 + COL_P + k * 8, dv + k * (2048 / 16), idesc_o, k != 0);
+                    tc_commit(o_full + w);
+                }
+                __syncwarp();
             };
             if (n_it > 0) { issue_s(0, 0); issue_s(0, 1); }
             for (int it = 0; it < n_it; ++it) {
@@ -420,13 +431,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmTile, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            // whole warp in uniform control flow, one elected lane issues (see the forward kernel)
             constexpr uint32_t idesc_o = make_idesc_bf16(BM, HD, false, true);
+            constexpr uint32_t idesc_sa = make_idesc_bf16(BM, 96, false, false), idesc_sb = make_idesc_bf16(BM, NK - 96, false, false);
+            const bool issuer = elect_one();
+            const uint64_t d_a0 = make_smem_desc_sw128(smem_u32(smem), 0, 1024);                          // stage 0 tiles
+            const uint64_t d_a1 = make_smem_desc_sw128(smem_u32(smem + Q_BYTES), 0, 1024);
+            const uint64_t d_b0 = make_smem_desc_sw128(smem_u32(smem + 2 * Q_BYTES), 0, 1024);
+            const uint64_t d_b1 = make_smem_desc_sw128(smem_u32(smem + 2 * Q_BYTES + KV_SLOT), 0, 1024);
             int it = 0;
             for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
                 const int st = it & 1;
                 const uint32_t ph = it & 1;
-                const uint32_t a0 = smem_u32(smem + st * B_STAGE), a1 = a0 + Q_BYTES, b0 = a0 + 2 * Q_BYTES, b1 = b0 + KV_SLOT;
+                const uint64_t so = uint64_t(st) * (B_STAGE / 16);
+                const uint64_t a0 = d_a0 + so, a1 = d_a1 + so, b0 = d_b0 + so, b1 = d_b1 + so;
                 mbar_wait(full + st, (it >> 1) & 1);
                 // KV: the second output accumulator aliases dP columns -> the previous item's outputs must have been read out.
                 // !KV: nothing aliases; the score MMAs simply queue behind the previous item's output MMAs.
@@ -434,43 +453,50 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmTile, const __grid_constan
                 tc_fence_after();
                 // scores:  !KV: S = Q K^T, dP = dO V^T      KV: S^T = K Q^T, dP^T = V dO^T.  Two column groups ([0, 96) then
                 // [96, 208)) so the element-wise warps of half 0 start one MMA group earlier.
-                constexpr uint32_t idesc_sa = make_idesc_bf16(BM, 96, false, false), idesc_sb = make_idesc_bf16(BM, NK - 96, false, false);
+                if (issuer) {
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const uint32_t idesc_g = g == 0 ? idesc_sa : idesc_sb;
-                    const uint32_t boff = g * 96 * 128, coff = g * 96;         // B rows (K-major, 128 B each) / accumulator columns
+                    for (int g = 0; g < 2; ++g) {
+                        const uint32_t idesc_g = g == 0 ? idesc_sa : idesc_sb;
+                        const uint64_t boff = uint64_t(g) * (96 * 128 / 16);       // B rows (K-major, 128 B each)
+                        const uint32_t coff = g * 96;                              // accumulator columns
 #pragma unroll
-                    for (int k = 0; k < HD / 16; ++k)
-                        tc_mma_f16(tmem_base + COL_S + coff, make_smem_desc_sw128(a0 + k * 32, 0, 1024),
-                                   make_smem_desc_sw128(b0 + boff + k * 32, 0, 1024), idesc_g, k != 0);
+                        for (int k = 0; k < HD / 16; ++k)
+                            tc_mma_f16(tmem_base + COL_S + coff, a0 + 2 * k, b0 + boff + 2 * k, idesc_g, k != 0);
 #pragma unroll
-                    for (int k = 0; k < HD / 16; ++k)
-                        tc_mma_f16(tmem_base + COL_DP + coff, make_smem_desc_sw128(a1 + k * 32, 0, 1024),
-                                   make_smem_desc_sw128(b1 + boff + k * 32, 0, 1024), idesc_g, k != 0);
-                    tc_commit(s_full + g);
+                        for (int k = 0; k < HD / 16; ++k)
+                            tc_mma_f16(tmem_base + COL_DP + coff, a1 + 2 * k, b1 + boff + 2 * k, idesc_g, k != 0);
+                        tc_commit(s_full + g);
+                    }
                 }
+                __syncwarp();
                 // first output (dQ / dV) into the spare columns: reduction steps 0..5 as soon as half 0 has parked them
                 if (!KV) mbar_wait(acc_free, ph ^ 1);          // the previous item's dQ has been read out of the spare columns
                 mbar_wait(p_ready + 0, ph);
                 tc_fence_after();
-                const uint32_t bo = KV ? b1 : b0;                // reduction-side operand of the first output: dO (KV) / K
-                const int a0col = KV ? COL_P : COL_DS, a1col = KV ? COL_P1 : COL_DS1;
-                for (int k = 0; k < 6; ++k)
-                    tc_mma_f16_ts(tmem_base + COL_OUT, tmem_base + bwd_a_col(a0col, a1col, k),
-                                  make_smem_desc_sw128(bo + k * 2048, 0, 1024), idesc_o, k != 0);
+                const uint64_t bo = KV ? b1 : b0;                // reduction-side operand of the first output: dO (KV) / K
+                constexpr int a0col = KV ? COL_P : COL_DS, a1col = KV ? COL_P1 : COL_DS1;
+                if (issuer) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k)
+                        tc_mma_f16_ts(tmem_base + COL_OUT, tmem_base + bwd_a_col(a0col, a1col, k), bo + k * (2048 / 16), idesc_o, k != 0);
+                }
+                __syncwarp();
                 mbar_wait(p_ready + 1, ph);
                 mbar_wait(p_ready + 2, ph);
                 tc_fence_after();
-                for (int k = 6; k < NK / 16; ++k)
-                    tc_mma_f16_ts(tmem_base + COL_OUT, tmem_base + bwd_a_col(a0col, a1col, k),
-                                  make_smem_desc_sw128(bo + k * 2048, 0, 1024), idesc_o, true);
-                if (KV) {
-                    // dK = dS^T . Q: its accumulator aliases dP columns, so only once every score column has been consumed
-                    for (int k = 0; k < NK / 16; ++k)
-                        tc_mma_f16_ts(tmem_base + COL_OUT2, tmem_base + bwd_a_col(COL_DS, COL_DS1, k),
-                                      make_smem_desc_sw128(b0 + k * 2048, 0, 1024), idesc_o, k != 0);
+                if (issuer) {
+#pragma unroll
+                    for (int k = 6; k < NK / 16; ++k)
+                        tc_mma_f16_ts(tmem_base + COL_OUT, tmem_base + bwd_a_col(a0col, a1col, k), bo + k * (2048 / 16), idesc_o, true);
+                    if (KV) {
+                        // dK = dS^T . Q: its accumulator aliases dP columns, so only once every score column has been consumed
+#pragma unroll
+                        for (int k = 0; k < NK / 16; ++k)
+                            tc_mma_f16_ts(tmem_base + COL_OUT2, tmem_base + bwd_a_col(COL_DS, COL_DS1, k), b0 + k * (2048 / 16), idesc_o, k != 0);
+                    }
+                    tc_commit(o_full);
                 }
-                tc_commit(o_full);
+                __syncwarp();
             }
         }
     } else {
