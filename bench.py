@@ -268,6 +268,9 @@ def run_ours(args):
     ms_eval = timed_loop(step_eval, n_eval, max(args.warmup, 3)) / (n_eval * N_POOL)
     alg_eval = algorithmic_bytes(tf_eval.sample_plans(B), out_bytes)
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     ms_step = ms_total / args.steps
