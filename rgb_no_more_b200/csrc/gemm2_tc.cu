@@ -203,7 +203,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
     if (warp == 0) {
         // ===================================== TMA producer (both CTAs) =========================
-        if (lane == 0) {
+        // whole warp in uniform control flow, one elected lane issues the TMA instructions (operands stay in uniform
+        // registers; from inside `if (lane == 0)` every UTMALDG paid an ELECT / R2UR sequence of single-thread latency)
+        {
+            const bool issuer = elect_one();
             int stage = 0, phase = 0;
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
                 const int sp = tile % p.splits, rest = tile / p.splits;
@@ -214,9 +217,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 k_range(sp, k0, k1);
                 for (int kb = k0; kb < k1; ++kb) {
                     mbar_wait(empty + stage, phase ^ 1);
-                    if (rank == 0) mbar_arrive_expect_tx(full + stage, 2 * (L::A_BYTES + L::B_BYTES));
                     unsigned char* sa = smem + L::OFF_A + stage * L::A_BYTES;
                     unsigned char* sb = smem + L::OFF_B + stage * L::B_BYTES;
+                    if (issuer) {
+                    if (rank == 0) mbar_arrive_expect_tx(full + stage, 2 * (L::A_BYTES + L::B_BYTES));
                     if (!A_MN) {
                         tma_load_2d_pair(sa, &tmA, full + stage, kb * BK, m0);
                     } else {
@@ -243,6 +247,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         tma_load_2d_pair(sb + BK * 128, &tmB, full + stage, nb + int(rank) * 128 + 64, kb * BK);
                         tma_load_2d_pair(sb + 2 * BK * 128, &tmB, full + stage, nb + 256 + int(rank) * 64, kb * BK);
                     }
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -298,19 +304,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // ===================================== epilogue I/O =====================================
         // Sub-tile g (running count over this CTA's tiles) lives in slot g % NBUF.  Hand-out of a slot
         // = (TMA load of the aux sub-tile, completing on stg_ready) or a plain arrive.
-        if (STAGED && lane == 0) {
+        // (whole warp in uniform control flow, one elected lane issues the TMA / mbarrier instructions)
+        if (STAGED) {
+            const bool issuer = elect_one();
             int h_tile = cluster_id, h_s = 0, h_g = 0;                  // hand-out cursor
             auto hand_out = [&]() {
                 if (h_tile >= total_tiles) return;
                 const int slot = h_g % NBUF;
-                if (HAS_AUX) {
-                    const int rest = h_tile / p.splits;
-                    const int n_blk = rest % p.n_tiles, m_blk = rest / p.n_tiles;
-                    mbar_arrive_expect_tx(stg_ready + slot, L::SUB_BYTES);
-                    tma_load_2d(smem + L::OFF_STG + slot * L::SLOT_BYTES, &tmAux, stg_ready + slot, n_blk * BN + h_s * 64,
-                                m_blk * BM + int(rank) * BM_CTA);
-                } else {
-                    mbar_arrive(stg_ready + slot);
+                if (issuer) {
+                    if (HAS_AUX) {
+                        const int rest = h_tile / p.splits;
+                        const int n_blk = rest % p.n_tiles, m_blk = rest / p.n_tiles;
+                        mbar_arrive_expect_tx(stg_ready + slot, L::SUB_BYTES);
+                        tma_load_2d(smem + L::OFF_STG + slot * L::SLOT_BYTES, &tmAux, stg_ready + slot, n_blk * BN + h_s * 64,
+                                    m_blk * BM + int(rank) * BM_CTA);
+                    } else {
+                        mbar_arrive(stg_ready + slot);
+                    }
                 }
                 ++h_g;
                 if (++h_s == NSUB) { h_s = 0; h_tile += n_clusters; }
@@ -325,14 +335,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     const int slot = g % NBUF;
                     mbar_wait(stg_done + slot, (g / NBUF) & 1);
                     unsigned char* src = smem + L::OFF_STG + slot * L::SLOT_BYTES;
-                    tma_store_2d(&tmC, src, n_blk * BN + s * 64, m0);
-                    if (EPI == EPI_GELU) tma_store_2d(&tmC2, src + L::SUB_BYTES, n_blk * BN + s * 64, m0);
-                    tma_store_commit();
-                    // the store of sub-tile g-1 has left its slot -> that slot serves sub-tile g-1+NBUF
-                    if (g >= 1) { tma_store_wait_read<1>(); hand_out(); }
+                    if (issuer) {
+                        tma_store_2d(&tmC, src, n_blk * BN + s * 64, m0);
+                        if (EPI == EPI_GELU) tma_store_2d(&tmC2, src + L::SUB_BYTES, n_blk * BN + s * 64, m0);
+                        tma_store_commit();
+                        // the store of sub-tile g-1 has left its slot -> that slot serves sub-tile g-1+NBUF.  (Measured: letting
+                        // NBUF-2 stores stay in flight instead, at the price of one slot less run-ahead for the math warps, is slower.)
+                        if (g >= 1) tma_store_wait_read<1>();
+                    }
+                    __syncwarp();
+                    if (g >= 1) hand_out();
                 }
             }
-            tma_store_wait<0>();
+            if (issuer) tma_store_wait<0>();
+            __syncwarp();
         }
     } else {
         // ===================================== epilogue math ====================================
