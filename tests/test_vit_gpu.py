@@ -248,6 +248,29 @@ def test_state_dict_roundtrip_and_autograd_surface():
     assert not torch.equal(y1, y2)
 
 
+def test_config0_jpeg_to_logits_end_to_end():
+    """BASELINE config 0 shape (ViT-Ti DCT, batch 8, eval forward on synthetic 512x512 JPEGs) through the whole path:
+    Huffman decode -> K0 (eval geometry) -> ViT-Ti, against the oracle chain on the CPU."""
+    from oracle import dct_oracle as O, vit_oracle as VO
+    from rgb_no_more_b200 import dct_manip as dm, plan as P, synth, transforms as TF
+    B = 8
+    y, c, q, flags = dm.decode_batch(synth.synth_jpeg_set(B), 64, 64, nthreads=4)
+    tf = TF.get_transform("imagenet_dct", "val", dtype=torch.bfloat16, device=DEV)
+    plans = tf.sample_plans(B)
+    x = tf.run(y.to(DEV), c.to(DEV), q.to(DEV), plans, clamp_in=flags.tolist())
+    m = _golden_model().eval()
+    with torch.no_grad():
+        logits = m(x).float().cpu()
+    bank = P.FilterBank()
+    ref_in = torch.stack([O.transform_embed(y[b].reshape(1, 64, 64, 8, 8), c[b].reshape(2, 32, 32, 8, 8), q[b].reshape(3, 8, 8),
+                                            plans[b], bank.table) for b in range(B)])
+    # K0 output (bf16) vs the oracle's fp32 embed input: bf16 rounding plus rare resize-tie LSBs (1/1020 after ToRange)
+    assert float((x.float().cpu() - ref_in).abs().max()) < 4.0 / 1020 + 2 ** -8 * float(ref_in.abs().max())
+    sd = {k: v.detach().float().cpu() for k, v in m.state_dict().items()}
+    ref = VO.forward_embedded(sd, ref_in.reshape(B, 14, 14, 384))
+    assert float((logits - ref).abs().max()) < 2e-2 * float(ref.abs().max())
+
+
 def test_train_stage_loss_decreases():
     from rgb_no_more_b200 import train_step as TS
     st = TS.TrainStage(DEV, arch="vitti", batch=16, warmup_steps=1, total_steps=1000, mixup_alpha=0.0, use_graph=True)
