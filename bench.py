@@ -268,6 +268,26 @@ def run_ours(args):
     ms_eval = timed_loop(step_eval, n_eval, max(args.warmup, 3)) / (n_eval * N_POOL)
     alg_eval = algorithmic_bytes(tf_eval.sample_plans(B), out_bytes)
 
+    # eval-only forward (eval.py:36-38): K0 in the eval geometry -> ViT forward, no gradients
+    eval_fwd_ips = None
+    if stage is not None:
+        x_eval = torch.empty((B, 196, 384), dtype=torch.bfloat16, device=dev)
+        with torch.no_grad():
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                tf_eval.run(*dev_pool[0], None, plans_dev=eplans[0], out=x_eval)
+                stage.eng.forward(x_eval, save=False)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g_fwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_fwd):
+                for k in range(N_POOL):
+                    tf_eval.run(*dev_pool[k], None, plans_dev=eplans[k], out=x_eval)
+                    stage.eng.forward(x_eval, save=False)
+        n_fwd = max(args.steps // 2, 5)
+        ms_fwd = timed_loop(lambda i: g_fwd.replay(), n_fwd, 3) / (n_fwd * N_POOL)
+        eval_fwd_ips = B * world / (ms_fwd * 1e-3)
+
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -300,6 +320,9 @@ def run_ours(args):
                                    "algorithmic_bytes_per_launch": alg_eval, "kernel_ms": ms_eval,
                                    "images_per_s": B / (ms_eval * 1e-3)},
     }
+    if eval_fwd_ips is not None:
+        line["eval_forward"] = {"value": eval_fwd_ips, "unit": UNIT, "what": "K0 (eval geometry) + ViT forward, no gradients, coefficients "
+                                "resident in HBM, CUDA-graph replay"}
     if stage is not None and args.arch in VIT_TRAIN_GFLOP_PER_IMAGE:
         # the ViT part of the step against the measured cuBLAS bf16 rate (sustained figure: timed inside a long step)
         tf_s = VIT_TRAIN_GFLOP_PER_IMAGE[args.arch] * B / ((ms_step - k0_avg_ms) * 1e-3) / 1e3
