@@ -115,6 +115,22 @@ def build_inputs(batch: int, rank: int, from_jpeg: int = 8):
     return pool, flags
 
 
+def host_decode_rate(n_files: int = 64, repeats: int = 3):
+    """Huffman-decode leg (row a1, stays on the host by north_star): rgbnm_jpeg_decode_batch on all host cores over
+    `n_files` synthetic 512x512 Q75 4:2:0 JPEGs -- the rate at which this box can turn JPEG bytes into the coefficient
+    batches the GPU path consumes."""
+    from rgb_no_more_b200 import dct_manip as dm, synth
+    jpegs = synth.synth_jpeg_set(n_files)
+    dm.decode_batch(jpegs, 64, 64, nthreads=0)
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        dm.decode_batch(jpegs, 64, 64, nthreads=0)
+    dt = (time.perf_counter() - t0) / repeats
+    return {"value": n_files / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "jpeg_bytes_mean": int(np.mean([len(j) for j in jpegs])),
+            "what": f"host Huffman decode of {n_files} synthetic 512x512 JPEGs into pinned-layout int16 planes, all cores; the "
+                    "from-JPEG-bytes rate of one rank is min(this / ranks per host, e2e)"}
+
+
 def algorithmic_bytes(plans, out_bytes: int) -> int:
     """int16 coefficients inside the crop window + 384 B tables + plan, + output."""
     total = 0
@@ -331,6 +347,7 @@ def run_ours(args):
                                      "note": "algorithmic GEMM + attention FLOPs of forward + backward over the whole ViT part of the "
                                              "step (LayerNorm, optimiser, bias sums included in the time, not in the FLOPs)"}
     if world == 1 and not args.no_cpu:
+        line["host_decode"] = host_decode_rate()
         line["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(line))
 
