@@ -43,6 +43,10 @@ struct HuffTable {
     // canonical decode tables (T.81 Annex F.2.2.3) + 9-bit lookahead
     int32_t mincode[18], maxcode[18], valptr[18];
     uint16_t look[512];  // (nbits << 8) | symbol, 0 = miss
+    // AC fast path: FAST-bit window that holds a whole (run, size) code AND its magnitude bits:
+    // (value << 8) | (run << 4) | total bits; 0 = not applicable (long code, EOB/ZRL, or value does not fit)
+    static constexpr int FAST = 9;
+    int16_t fast_ac[1 << FAST];
 
     void build() {
         int code = 0, k = 0;
@@ -65,6 +69,16 @@ struct HuffTable {
             }
             code <<= 1;
         }
+        std::memset(fast_ac, 0, sizeof(fast_ac));
+        for (int i = 0; i < (1 << FAST); ++i) {
+            const uint16_t e = look[i >> (FAST - 9)];
+            if (!e) continue;
+            const int len = e >> 8, rs = e & 0xff, run = rs >> 4, magbits = rs & 15;
+            if (magbits == 0 || len + magbits > FAST) continue;
+            int k = ((i << len) & ((1 << FAST) - 1)) >> (FAST - magbits);   // the magnitude bits that follow the code
+            if (k < (1 << (magbits - 1))) k += (-1 << magbits) + 1;           // receive_extend
+            if (k >= -128 && k <= 127) fast_ac[i] = int16_t((k * 256) + (run * 16) + (len + magbits));
+        }
     }
 };
 
@@ -83,6 +97,23 @@ struct BitReader {
     bool hit_marker = false;
 
     inline void fill() {
+        // fast path: 8 source bytes without a 0xFF (no stuffing, no marker) -> append as many whole bytes as fit
+        if (!hit_marker && end - p >= 8) {
+            uint64_t x;
+            std::memcpy(&x, p, 8);
+            x = __builtin_bswap64(x);
+            const uint64_t y = ~x;
+            if (((y - 0x0101010101010101ull) & ~y & 0x8080808080808080ull) == 0) {
+                const int k = (64 - n) >> 3;                 // n <= 56 at every call site -> k >= 1
+                if (k > 0) {
+                    const int bits = k * 8;
+                    acc |= (bits == 64 ? x : (x >> (64 - bits)) << (64 - n - bits));
+                    n += bits;
+                    p += k;
+                }
+                return;
+            }
+        }
         while (n <= 56) {
             uint32_t b = 0;
             if (!hit_marker && p < end) {
@@ -113,8 +144,33 @@ struct BitReader {
         skip(s);
         return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
     }
+    // callers of the *_nofill variants guarantee n >= 32 (one symbol + its magnitude bits need at most 16 + 11)
+    inline int receive_extend_nofill(int s) {
+        const int v = int(peek(s));
+        skip(s);
+        return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+    }
     inline int decode(const HuffTable& t) {
         if (n < 16) fill();
+        uint16_t e = t.look[peek(9)];
+        if (e) {
+            skip(e >> 8);
+            return e & 0xff;
+        }
+        int code = int(peek(9));
+        int l = 9;
+        uint64_t rest = acc << 9;
+        while (true) {
+            ++l;
+            code = (code << 1) | int(rest >> 63);
+            rest <<= 1;
+            if (l > 16) return -1;
+            if (code <= t.maxcode[l] && t.maxcode[l] >= 0) break;
+        }
+        skip(l);
+        return t.vals[t.valptr[l] + code - t.mincode[l]];
+    }
+    inline int decode_nofill(const HuffTable& t) {
         uint16_t e = t.look[peek(9)];
         if (e) {
             skip(e >> 8);
@@ -257,7 +313,17 @@ struct Decoder {
     }
 
     // planes[i]: component i output, wb*hb blocks of 64 int16 (natural order).
-    int decode_scan(size_t pos, int16_t* const planes[3]) {
+    // clamp_live (optional): set to 1 iff some dequantised coefficient leaves [-1024, 1016] (checked as each non-zero
+    // coefficient is stored: x*q >= -1024 <=> x >= -floor(1024/q), x*q <= 1016 <=> x <= floor(1016/q))
+    int decode_scan(size_t pos, int16_t* const planes[3], int* clamp_live = nullptr) {
+        int16_t lim_lo[3][64], lim_hi[3][64];      // indexed by zig-zag position
+        for (int i = 0; i < ncomp; ++i)
+            for (int k = 0; k < 64; ++k) {
+                const int qq = qt[comp[i].tq][kZigzag[k]] ? qt[comp[i].tq][kZigzag[k]] : 1;
+                lim_lo[i][k] = int16_t(-(1024 / qq));
+                lim_hi[i][k] = int16_t(1016 / qq);
+            }
+        int bad = 0;
         for (int i = 0; i < ncomp; ++i) {
             if (!dc[comp[i].td].present || !ac[comp[i].ta].present || !qt_present[comp[i].tq])
                 return RGBNM_ERR_CORRUPT;
@@ -300,8 +366,22 @@ struct Decoder {
                             if (s < 0 || s > 11) return RGBNM_ERR_CORRUPT;
                             c.pred += br.receive_extend(s);
                             blk[0] = int16_t(c.pred);
+                            const int16_t* lo = lim_lo[ci];
+                            const int16_t* hi = lim_hi[ci];
+                            bad |= (c.pred < lo[0]) | (c.pred > hi[0]);
                             for (int k = 1; k < 64;) {
-                                int rs = br.decode(ha);
+                                if (br.n < 32) br.fill();
+                                const int fa = ha.fast_ac[br.peek(HuffTable::FAST)];
+                                if (fa) {                      // code + magnitude inside the FAST-bit window
+                                    k += (fa >> 4) & 15;
+                                    if (k > 63) return RGBNM_ERR_CORRUPT;
+                                    br.skip(fa & 15);
+                                    const int v = fa >> 8;
+                                    bad |= (v < lo[k]) | (v > hi[k]);
+                                    blk[kZigzag[k++]] = int16_t(v);
+                                    continue;
+                                }
+                                int rs = br.decode_nofill(ha);
                                 if (rs < 0) return RGBNM_ERR_CORRUPT;
                                 int r = rs >> 4, sz = rs & 15;
                                 if (sz == 0) {
@@ -311,7 +391,9 @@ struct Decoder {
                                 }
                                 k += r;
                                 if (k > 63) return RGBNM_ERR_CORRUPT;
-                                blk[kZigzag[k]] = int16_t(br.receive_extend(sz));
+                                const int v = br.receive_extend_nofill(sz);
+                                bad |= (v < lo[k]) | (v > hi[k]);
+                                blk[kZigzag[k]] = int16_t(v);
                                 ++k;
                             }
                         }
@@ -320,6 +402,7 @@ struct Decoder {
                 if (restart_interval) --restarts_left;
             }
         }
+        if (clamp_live) *clamp_live = bad;
         return RGBNM_OK;
     }
 };
@@ -339,23 +422,6 @@ int fill_info(const Decoder& d, rgbnm_jpeg_info* info) {
         info->vsamp[i] = d.comp[i].v;
     }
     return RGBNM_OK;
-}
-
-// 1 if any dequantised coefficient leaves [-1024, 1016] (datasets.py:288-290 clamp is then live)
-int clamp_needed(const int16_t* blocks, size_t nblocks, const uint16_t* q) {
-    int lo[64], hi[64];
-    for (int k = 0; k < 64; ++k) {
-        int qq = q[k] ? q[k] : 1;
-        lo[k] = -(1024 / qq);      // x*q >= -1024  <=>  x >= -floor(1024/q)
-        hi[k] = 1016 / qq;         // x*q <=  1016  <=>  x <=  floor(1016/q)
-    }
-    for (size_t b = 0; b < nblocks; ++b) {
-        const int16_t* x = blocks + b * 64;
-        int bad = 0;
-        for (int k = 0; k < 64; ++k) bad |= (x[k] < lo[k]) | (x[k] > hi[k]);
-        if (bad) return 1;
-    }
-    return 0;
 }
 
 // ---------------------------------------------------------------------------------
@@ -523,9 +589,9 @@ int rgbnm_jpeg_read_coefficients(const uint8_t* data, size_t size, int16_t* y, s
         planes[1] = cbcr;
         planes[2] = cbcr + nc;
     }
-    rc = d.decode_scan(sos, planes);
-    if (rc != RGBNM_OK) return rc;
     int flag = 0;
+    rc = d.decode_scan(sos, planes, &flag);
+    if (rc != RGBNM_OK) return rc;
     for (int i = 0; i < d.ncomp; ++i) {
         const uint16_t* q = d.qt[d.comp[i].tq];
         for (int k = 0; k < 64; ++k) quant[i * 64 + k] = int16_t(q[k]);
@@ -533,7 +599,6 @@ int rgbnm_jpeg_read_coefficients(const uint8_t* data, size_t size, int16_t* y, s
             dims[2 * i] = d.comp[i].dsh;
             dims[2 * i + 1] = d.comp[i].dsw;
         }
-        flag |= clamp_needed(planes[i], size_t(d.comp[i].hb) * d.comp[i].wb, q);
     }
     if (clamp_flag) *clamp_flag = flag;
     return RGBNM_OK;
