@@ -62,15 +62,22 @@ def read_coefficients(path: str):
     return read_coefficients_from_bytes(buf)
 
 
-def decode_batch(jpegs: Sequence[bytes], hb: int = 64, wb: int = 64, nthreads: int = 0, pin: bool = False):
+def decode_batch(jpegs: Sequence[bytes], hb: int = 64, wb: int = 64, nthreads: int = 0, pin: bool = False, out=None):
     """Multithreaded batch decode into the layout the fused kernel reads.
-    Returns (y [n,hb,wb,64], cbcr [n,2,hb/2,wb/2,64], quant [n,3,64], clamp_flags uint8 [n])."""
+    Returns (y [n,hb,wb,64], cbcr [n,2,hb/2,wb/2,64], quant [n,3,64], clamp_flags uint8 [n]).
+    `out` = (y, cbcr, quant) of a previous call (e.g. one slot of a pinned staging ring) is written in place."""
     L = _lib.load()
     n = len(jpegs)
     pin = pin and torch.cuda.is_available()
-    y = torch.empty((n, hb, wb, 64), dtype=torch.int16, pin_memory=pin)
-    c = torch.empty((n, 2, hb // 2, wb // 2, 64), dtype=torch.int16, pin_memory=pin)
-    q = torch.empty((n, 3, 64), dtype=torch.int16, pin_memory=pin)
+    if out is not None:
+        y, c, q = out
+        if (y.shape != (n, hb, wb, 64) or c.shape != (n, 2, hb // 2, wb // 2, 64) or q.shape != (n, 3, 64)
+                or any(t.dtype != torch.int16 or not t.is_contiguous() or t.is_cuda for t in (y, c, q))):
+            raise ValueError("rgbnm decode_batch: `out` must be the (y, cbcr, quant) host tensors of a same-sized batch")
+    else:
+        y = torch.empty((n, hb, wb, 64), dtype=torch.int16, pin_memory=pin)
+        c = torch.empty((n, 2, hb // 2, wb // 2, 64), dtype=torch.int16, pin_memory=pin)
+        q = torch.empty((n, 3, 64), dtype=torch.int16, pin_memory=pin)
     flags = torch.empty((n,), dtype=torch.uint8)
     status = torch.zeros((n,), dtype=torch.int32)
     ptrs = (C.c_char_p * n)(*jpegs)

@@ -113,6 +113,12 @@ def test_batch_decode_equals_single_decode_and_reports_the_clamp():
         cq = c1.int() * q1[1:3, None, None].int()
         live = bool(yq.min() < -1024 or yq.max() > 1016 or cq.min() < -1024 or cq.max() > 1016)
         assert fl == live                                            # datasets.py:288-290 clamp is live iff flagged
+    # decoding again into the same staging buffers (a feeder ring slot) gives the same planes
+    y0, c0, q0 = y.clone(), c.clone(), q.clone()
+    y.zero_()
+    y2, c2, q2, flags2 = dm.decode_batch(jpegs, 64, 64, nthreads=2, out=(y, c, q))
+    assert y2.data_ptr() == y.data_ptr() and torch.equal(y2, y0) and torch.equal(c2, c0) and torch.equal(q2, q0)
+    assert torch.equal(flags2, flags)
 
 
 def test_errors_are_runtime_errors_like_the_pybind_module():
