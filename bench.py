@@ -255,6 +255,38 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed_loop(step_e2e, args.steps, args.warmup)
 
+    # ---- from JPEG bytes: host Huffman decode (all cores) -> pinned ring -> copy stream -> K0 -> step ------------------
+    e2e_jpeg = None
+    if world == 1 and not args.no_cpu and stage is not None:
+        from rgb_no_more_b200 import feeder as FD, synth
+        jpegs = synth.synth_jpeg_set(B)
+        fd = FD.JpegFeeder(dev, B, 64, 64, slots=3)
+        fd.submit(jpegs)
+        y0, c0, q0, fl0, s0 = fd.get()
+        fd.release(s0)
+        jplans = torch.from_numpy(P.pack_plans(plan_pool[0], fl0).view(np.uint8).reshape(B, -1).copy()).to(dev)
+
+        def step_jpeg(i):
+            while len(fd.pending) < 2:
+                fd.submit(jpegs)                      # decode of the next batches overlaps this step
+            yj, cj, qj, _, slot = fd.get()
+            x = tf.run(yj, cj, qj, None, plans_dev=jplans, out=out_buf)
+            fd.release(slot)
+            res = stage.step(x, labels_pool[i % N_POOL])
+            result_host.copy_(res.reshape(-1)[:1].float(), non_blocking=True)
+
+        n_j = max(args.steps // 2, 5)
+        ms_jpeg = timed_loop(step_jpeg, n_j, 3)
+        while fd.pending:
+            _, _, _, _, slot = fd.get()
+            fd.release(slot)
+        torch.cuda.synchronize()
+        fd.close()
+        e2e_jpeg = {"value": B / (ms_jpeg / n_j * 1e-3), "unit": UNIT, "jpeg_bytes_per_step": int(sum(len(j) for j in jpegs)),
+                    "h2d_bytes_per_step": int(fd.h2d_bytes), "host_cores": os.cpu_count() or 1,
+                    "what": "same step fed from JPEG byte strings: rgbnm_jpeg_decode_batch on the host cores into a pinned ring, "
+                            "copy stream, K0, train step; decode of the next batches overlaps the GPU"}
+
     # K0 kernel(s) alone: average over the timed region (events on the launching stream)
     k0_avg_ms = float(np.mean([a.elapsed_time(b) for a, b in k0_ms[-args.steps:]]))
     out_bytes = 2 if out_dtype == torch.bfloat16 else 4
@@ -336,6 +368,8 @@ def run_ours(args):
                                    "algorithmic_bytes_per_launch": alg_eval, "kernel_ms": ms_eval,
                                    "images_per_s": B / (ms_eval * 1e-3)},
     }
+    if e2e_jpeg is not None:
+        line["e2e_from_jpeg"] = e2e_jpeg
     if eval_fwd_ips is not None:
         line["eval_forward"] = {"value": eval_fwd_ips, "unit": UNIT, "what": "K0 (eval geometry) + ViT forward, no gradients, coefficients "
                                 "resident in HBM, CUDA-graph replay"}
