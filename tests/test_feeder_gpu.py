@@ -37,3 +37,18 @@ def test_feeder_rejects_wrong_batch_and_corrupt_files():
     with pytest.raises(RuntimeError):
         fd.get()
     fd.close()
+
+
+def test_end_to_end_training_from_jpeg_bytes_learns(monkeypatch):
+    """examples/train_synthetic_dct.py: JPEG bytes -> feeder -> K0 (train recipe) -> mixup -> ViT-Ti -> AdamW.  The class is
+    encoded in the mean colour, so the soft-label cross entropy must fall well below ln(1000) within 40 steps."""
+    import importlib.util
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("train_synthetic_dct", os.path.join(root, "examples", "train_synthetic_dct.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.setattr(sys, "argv", ["train_synthetic_dct.py", "--steps", "40", "--batch", "32", "--files", "64", "--classes", "4"])
+    losses = mod.main()
+    assert losses[0] > 5.0 and losses[-1] < 0.6 * losses[0], losses
