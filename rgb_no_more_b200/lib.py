@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librgbnm_b200.so")
+LIB_PATH = os.environ.get("RGBNM_LIB") or os.path.join(_HERE, "librgbnm_b200.so")     # RGBNM_LIB: A/B builds of the library
 _lib = None
 
 
