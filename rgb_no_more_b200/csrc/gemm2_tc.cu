@@ -561,7 +561,8 @@ extern "C" int rgbnm_gemm_bf16(const rgbnm_gemm_args* args, void* stream) {
     // N = 384 with a long reduction: one 256 x 384 tile per CTA pair (157 FLOP per L2 byte).  Its single TMEM accumulator
     // leaves the epilogue exposed, which only pays off when the main loop is long (K >= 768).
     static const bool no384 = (getenv("RGBNM_GEMM_NO384") != nullptr);
-    const bool tall = (a.N % 384 == 0) && a.K >= 768 && !no384;
+    static const int tall_min_k = getenv("RGBNM_TALL_MINK") ? atoi(getenv("RGBNM_TALL_MINK")) : 768;
+    const bool tall = (a.N % 384 == 0) && a.K >= tall_min_k && !no384;
     switch (a.epilogue) {
         case RGBNM_EPI_STORE:
             if (!a.C || (a.ldc % 8)) return RGBNM_ERR_ARG;
