@@ -135,6 +135,23 @@ int rgbnm_k0_fused(const int16_t* y, const int16_t* cbcr, const int16_t* quant, 
 /* Number of kernels the two calls above launch for one batch (for gpu_launches accounting). */
 int rgbnm_k0_launch_count(void);
 
+/* The same two calls with an explicit output layout.
+ *   RGBNM_K0_LAYOUT_VIT16 (the calls above): planes resized to 28 x 28 luma blocks (crop side 14 / 28 / 56),
+ *     out [n][196][384] = per 16 x 16 patch [Y: A16 . X . A16^T (256) | Cb 64 | Cr 64]       models/plainvit.py:200-216
+ *   RGBNM_K0_LAYOUT_SWIN4: the SwinV2 data path (datasets.py:370-382: RandomResizedCrop_DCT(32) / Resize_DCT(32)):
+ *     planes resized to 32 x 32 luma blocks (crop side 16 / 32 / 64), out [n][64*64][24] = per 4 x 4 patch
+ *     [Y 4x4 (16) | Cb 2x2 (4) | Cr 2x2 (4)]: every 8 x 8 block DECOMPOSED, D = A^T . X . A with A = A(4,2) / A(2,4),
+ *     and read out through the reference's interleaved rearrange "(p1 pdh) (p2 pdw)" -- token (2h + i%2, 2w + j%2)
+ *     takes D[i][j] at feature (i/2)*4 + j/2 (luma; chroma: 4h + i%4, 4w + j%4, (i/4)*2 + j/4)
+ *     models/swinv2.py:505-576, models/plainvit.py:50-88.  INT16_PLANES: [n][(32*32 + 2*16*16)*64]. */
+#define RGBNM_K0_LAYOUT_VIT16 0
+#define RGBNM_K0_LAYOUT_SWIN4 1
+int rgbnm_k0_dcstats_ex(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans,
+                        const rgbnm_k0_tables* tables, float* stats, int n, int hb, int wb, int layout, void* stream);
+int rgbnm_k0_fused_ex(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans,
+                      const rgbnm_k0_tables* tables, const float* stats, void* out, int out_mode, int layout, int n,
+                      int hb, int wb, void* stream);
+
 
 /* ------------------------------------------------------------------------------
  * (K1,K3,K5,K6,K8) Dense bf16 contractions of models/plainvit.py on tcgen05 tensor cores.

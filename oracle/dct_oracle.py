@@ -383,3 +383,38 @@ def transform_embed(y_q, c_q, quant, plan, filters) -> torch.Tensor:
     y, c = transform_int16(y_q, c_q, quant, plan, filters)
     out = embed_input(to_range(y).unsqueeze(0), to_range(c).unsqueeze(0))
     return out.reshape(196, 384)
+
+
+# ---------------------------------------------------------------------------
+# SwinV2 data path: 32-block geometry, patch 4
+# ---------------------------------------------------------------------------
+def embed_input_swin(yf: torch.Tensor, cf: torch.Tensor) -> torch.Tensor:
+    """swinv2.PatchEmbedding_DCT_Group.forward up to (not including) the Linear(24, E)
+    (models/swinv2.py:553-571 with patch 4: combine_Y = combine_C = False): every 8x8 block is DECOMPOSED,
+    D = A^T . X . A (apply_subblock combine=False, plainvit.py:65-68) with A = A(4,2) for luma and A(2,4)
+    for chroma (patch2subblock, plainvit.py:43-47), then the reference's rearrange
+    'b c h w (p1 pdh) (p2 pdw) -> b c (h pdh) (w pdw) p1 p2' (plainvit.py:86) -- note the INTERLEAVED split
+    of the 8 indices (i = p1*pd + pdh) -- collapse 'b c h w i j -> b h w (c i j)' and concat [Y 16 | Cb 4 | Cr 4].
+    yf (B,1,32,32,8,8), cf (B,2,16,16,8,8) fp32 -> (B,64,64,24)."""
+    def decompose(x, small, pd):
+        A = conversion_matrix(pd, small)
+        x = torch.einsum("i o, b c h w o j -> b c h w i j", A.T, x)
+        x = torch.einsum("b c h w i o, o j -> b c h w i j", x, A)
+        b, c, h, w, _, _ = x.shape
+        x = x.reshape(b, c, h, w, small, pd, small, pd)            # (p1 pdh) (p2 pdw)
+        x = x.permute(0, 1, 2, 5, 3, 7, 4, 6)                      # b c h pdh w pdw p1 p2
+        return x.reshape(b, c, h * pd, w * pd, small, small)
+
+    y = decompose(yf, 4, 2)
+    c = decompose(cf, 2, 4)
+    b, _, H, W, _, _ = y.shape
+    y = y.permute(0, 2, 3, 1, 4, 5).reshape(b, H, W, 16)
+    c = c.permute(0, 2, 3, 1, 4, 5).reshape(b, H, W, 8)
+    return torch.cat([y, c], dim=3)
+
+
+def transform_embed_swin(y_q, c_q, quant, plan, filters) -> torch.Tensor:
+    """Full K0 semantics for one image in the SwinV2 layout: (4096, 24) fp32."""
+    y, c = transform_int16(y_q, c_q, quant, plan, filters, out_size=32)
+    out = embed_input_swin(to_range(y).unsqueeze(0), to_range(c).unsqueeze(0))
+    return out.reshape(4096, 24)

@@ -22,16 +22,23 @@ namespace k0 {
 constexpr float KE = 0.707106781f;
 constexpr float CLAMP_LO = -1024.0f;
 constexpr float CLAMP_HI = 1016.0f;
-constexpr int GRID_Y = 28;   // luma blocks per side after resize
-constexpr int GRID_C = 14;
-constexpr int TOKENS = 196;
-constexpr int FEAT = 384;
-constexpr int PLANE_ELEMS = (GRID_Y * GRID_Y + 2 * GRID_C * GRID_C) * 64;
+// Output geometry per layout (include/rgbnm_b200.h RGBNM_K0_LAYOUT_*):
+//   VIT16: 28 x 28 luma blocks -> 196 tokens x [Y 16x16 | Cb 8x8 | Cr 8x8]   (models/plainvit.py:200-216, patch 16)
+//   SWIN4: 32 x 32 luma blocks -> 4096 tokens x [Y 4x4 | Cb 2x2 | Cr 2x2]    (models/swinv2.py:505-576, patch 4)
+template <int LAYOUT>
+struct Geo {
+    static constexpr int GRID_Y = LAYOUT == RGBNM_K0_LAYOUT_SWIN4 ? 32 : 28;   // luma blocks per side after resize
+    static constexpr int GRID_C = GRID_Y / 2;
+    static constexpr int TOKENS = LAYOUT == RGBNM_K0_LAYOUT_SWIN4 ? 4096 : 196;
+    static constexpr int FEAT = LAYOUT == RGBNM_K0_LAYOUT_SWIN4 ? 24 : 384;
+    static constexpr int PLANE_ELEMS = (GRID_Y * GRID_Y + 2 * GRID_C * GRID_C) * 64;
+};
 
 enum Mode { MODE_DOWN2 = 0, MODE_IDENT = 1, MODE_UP2 = 2, MODE_BAD = 3 };
 
-__device__ __forceinline__ int mode_of(int crop_size) {
-    return crop_size == 56 ? MODE_DOWN2 : crop_size == 28 ? MODE_IDENT : crop_size == 14 ? MODE_UP2 : MODE_BAD;
+// crop side -> resize case for a G x G output grid
+__device__ __forceinline__ int mode_of(int crop_size, int G) {
+    return crop_size == 2 * G ? MODE_DOWN2 : crop_size == G ? MODE_IDENT : 2 * crop_size == G ? MODE_UP2 : MODE_BAD;
 }
 
 #define K0_KB_TABLE                                                                                               \
@@ -113,6 +120,62 @@ __device__ __forceinline__ void up2_1d(const float (&x)[8], int child, float (&o
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Block DECOMPOSITION of the SwinV2 patch embedding (models/swinv2.py:505-576, plainvit.py:50-69 with
+// combine=False): D = A^T . X . A with A = A(4,2) for luma (8x8 -> 2x2 sub-blocks of 4x4) and A = A(2,4)
+// for chroma (8x8 -> 4x4 sub-blocks of 2x2).  One call = one 1-D pass: o[j] = sum_k A[k][j] x[k].
+// A(4,2) has the structure of A16 at half the size: A[k][4+j] = (-1)^(k+j) A[k][j], even rows
+// A[2m][j] = delta(j, m) / sqrt(2), odd rows A[2m+1][j] = kB4[m][j] -> 4 mul + 16 fma + 8 add.
+// ---------------------------------------------------------------------------------------
+#define K0_KB4_TABLE                                                                  \
+    {                                                                                 \
+        {0.64072883f, 0.2939689f, -0.052791018f, 0.016183784f},                       \
+        {-0.22499399f, 0.5593675f, 0.36294368f, -0.068974815f},                       \
+        {0.15033615f, -0.24921477f, 0.5431836f, 0.3467599f},                          \
+        {-0.1274489f, 0.19642372f, -0.26539865f, 0.61215854f},                        \
+    }
+__device__ __forceinline__ void decomp_y_1d(const float (&x)[8], float (&o)[8]) {
+    constexpr float B[4][4] = K0_KB4_TABLE;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float w = B[0][j] * x[1];
+        w = fmaf(B[1][j], x[3], w);
+        w = fmaf(B[2][j], x[5], w);
+        w = fmaf(B[3][j], x[7], w);
+        const float e = KE * x[2 * j];
+        o[j] = e + w;
+        o[4 + j] = (j & 1) ? (w - e) : (e - w);
+    }
+}
+// A(2,4) = D8 . blockdiag(D2 x 4)^T, dense (values of dct_ops.generate_conversion_matrix(2, 4), fp32)
+#define K0_A24_TABLE                                                                                                       \
+    {                                                                                                                      \
+        {0.5f, 0.0f, 0.5f, 0.0f, 0.5f, 0.0f, 0.5f, 0.0f},                                                                  \
+        {0.6407289f, 0.052791085f, 0.26539853f, 0.12744892f, -0.26539862f, 0.12744893f, -0.6407289f, 0.05279105f},         \
+        {0.46193975f, 0.1913417f, -0.4619398f, 0.19134171f, -0.46193963f, -0.19134182f, 0.46193984f, -0.19134165f},        \
+        {0.22499405f, 0.36294374f, -0.5431836f, -0.15033633f, 0.54318374f, -0.15033615f, -0.2249942f, 0.3629437f},         \
+        {0.0f, 0.5f, 0.0f, -0.5f, 0.0f, 0.5f, 0.0f, -0.5f},                                                                \
+        {-0.15033624f, 0.5431837f, 0.36294368f, -0.22499393f, -0.36294374f, -0.22499414f, 0.15033603f, 0.5431839f},        \
+        {-0.1913417f, 0.46193975f, 0.19134156f, 0.46193993f, 0.1913418f, -0.4619395f, -0.19134162f, -0.46194f},            \
+        {-0.12744884f, 0.26539847f, -0.052791126f, 0.6407287f, 0.052791115f, 0.6407289f, 0.12744878f, 0.26539934f},        \
+    }
+__device__ __forceinline__ void decomp_c_1d(const float (&x)[8], float (&o)[8]) {
+    constexpr float A[8][8] = K0_A24_TABLE;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        // rows 0 and 4 of A(2,4) are 4-sparse (+-1/2): the zero products are dropped at compile time
+        float acc = 0.0f;
+        bool first = true;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (A[k][j] == 0.0f) continue;
+            acc = first ? A[k][j] * x[k] : fmaf(A[k][j], x[k], acc);
+            first = false;
+        }
+        o[j] = acc;
+    }
+}
+
 __device__ __forceinline__ float rint_magic(float x) {
     // round-half-even for |x| < 2^22 (torch.round semantics), two full-rate FADDs
     return (x + 12582912.0f) - 12582912.0f;
@@ -169,8 +232,9 @@ struct Trace {
     int zero;     // -1, or index of the op that zeroed the block
 };
 
+template <int GRID_Y>
 __device__ __forceinline__ Trace trace_back(const rgbnm_plan& pl, int comp, int r, int c) {
-    const int G = comp == 0 ? GRID_Y : GRID_C;
+    const int G = comp == 0 ? GRID_Y : GRID_Y / 2;
     Trace t{r, c, -1};
     for (int k = pl.n_ops - 1; k >= 0; --k) {
         const rgbnm_plan_op& op = pl.ops[k];

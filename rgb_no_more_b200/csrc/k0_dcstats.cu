@@ -17,9 +17,6 @@
 
 namespace k0 {
 
-constexpr int NY = GRID_Y * GRID_Y;       // 784
-constexpr int NC = 2 * GRID_C * GRID_C;   // 392
-constexpr int NDC = NY + NC;
 constexpr int STATS_THREADS = 256;
 
 // DC of the resized block at post-resize position (r, c) of plane `comp`, computed with the
@@ -79,9 +76,14 @@ __device__ __forceinline__ float block_reduce(float v, int op, float* scratch) {
     return r;
 }
 
+template <int LAYOUT>
 __global__ void __launch_bounds__(STATS_THREADS)
 k0_dcstats_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, const int16_t* __restrict__ quant,
                   const rgbnm_plan* __restrict__ plans, rgbnm_k0_tables tb, float* __restrict__ stats_all, int hb, int wb) {
+    constexpr int GRID_Y = Geo<LAYOUT>::GRID_Y, GRID_C = Geo<LAYOUT>::GRID_C;
+    constexpr int NY = GRID_Y * GRID_Y;       // 784 / 1024
+    constexpr int NC = 2 * GRID_C * GRID_C;   // 392 / 512
+    constexpr int NDC = NY + NC;
     const int img = blockIdx.x;
     __shared__ rgbnm_plan pl;
     __shared__ __align__(16) float qf[192];
@@ -99,7 +101,7 @@ k0_dcstats_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbc
     __syncthreads();
 
     const int hc = hb >> 1, wc = wb >> 1;
-    const int mode = mode_of(pl.crop_size);
+    const int mode = mode_of(pl.crop_size, GRID_Y);
     float* stats = stats_all + size_t(img) * RGBNM_MAX_OPS * 2;
 
     // post-resize, post-flip DC planes (flip only moves blocks: the DC term keeps its sign)
@@ -194,13 +196,23 @@ k0_dcstats_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbc
 
 }  // namespace k0
 
-extern "C" int rgbnm_k0_dcstats(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans,
-                                const rgbnm_k0_tables* tables, float* stats, int n, int hb, int wb, void* stream) {
+extern "C" int rgbnm_k0_dcstats_ex(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans,
+                                   const rgbnm_k0_tables* tables, float* stats, int n, int hb, int wb, int layout, void* stream) {
     using namespace k0;
     if (!y || !cbcr || !quant || !plans || !tables || !stats || n < 0) return RGBNM_ERR_ARG;
     if (hb < 2 || wb < 2 || hb > 255 || wb > 255 || (hb & 1) || (wb & 1)) return RGBNM_ERR_ARG;
+    if (layout != RGBNM_K0_LAYOUT_VIT16 && layout != RGBNM_K0_LAYOUT_SWIN4) return RGBNM_ERR_ARG;
     if (n == 0) return RGBNM_OK;
-    k0_dcstats_kernel<<<n, STATS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(y, cbcr, quant, plans, *tables, stats, hb, wb);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (layout == RGBNM_K0_LAYOUT_VIT16)
+        k0_dcstats_kernel<RGBNM_K0_LAYOUT_VIT16><<<n, STATS_THREADS, 0, st>>>(y, cbcr, quant, plans, *tables, stats, hb, wb);
+    else
+        k0_dcstats_kernel<RGBNM_K0_LAYOUT_SWIN4><<<n, STATS_THREADS, 0, st>>>(y, cbcr, quant, plans, *tables, stats, hb, wb);
     RGBNM_CUDA_CHECK(cudaGetLastError());
     return RGBNM_OK;
+}
+
+extern "C" int rgbnm_k0_dcstats(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans,
+                                const rgbnm_k0_tables* tables, float* stats, int n, int hb, int wb, void* stream) {
+    return rgbnm_k0_dcstats_ex(y, cbcr, quant, plans, tables, stats, n, hb, wb, RGBNM_K0_LAYOUT_VIT16, stream);
 }

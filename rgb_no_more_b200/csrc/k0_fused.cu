@@ -38,8 +38,8 @@
 namespace k0 {
 
 constexpr int WARPS_PER_CTA = 1;
-constexpr int ROWS_PER_IMAGE = 14;       // warp tasks per image (token rows)
-constexpr int PAIRS_PER_ROW = 7;
+// warp tasks per image = chroma block rows (ViT: 14 token rows; Swin: 16 rows of 4 x 64 tokens); one task walks
+// GRID_C / 2 "pairs" (pair = 2 horizontally adjacent chroma positions = 8 luma + 4 chroma post-resize blocks)
 constexpr int RY_TOK = 32 * 16 + 16;     // floats per token in RY (+16: the two tokens land on disjoint banks)
 constexpr int RC_BLK = 136;              // floats per chroma block in RC (16 rows x 8, +8 bank spread)
 constexpr int TT_LD = 20;                // leading dimension of the 16x16 tiles in TT (16-byte rows, conflict-free)
@@ -47,7 +47,9 @@ constexpr int TT_TOK = 16 * TT_LD + 16;
 constexpr int CT_LD = 12;
 constexpr int CT_BLK = 8 * CT_LD + 8;
 
-struct __align__(16) WarpSmem {
+constexpr int SW_RUN = 8 * 24;           // Swin: one output run = 8 consecutive tokens x 24 features
+template <int LAYOUT>
+struct __align__(16) WarpSmemT {
     float RY[2 * RY_TOK];     // luma row-pass output; re-used as TT (A16 . S) after the column pass
     float RC[4 * RC_BLK];     // chroma row-pass output; re-used as CT (finished chroma blocks)
     float qf[3 * 64];         // fp32 quantisation tables of the current image
@@ -55,6 +57,8 @@ struct __align__(16) WarpSmem {
     rgbnm_plan plan;
     int info[12];
     int pad[4];
+    // Swin only: the pair's 4 token rows x 8 tokens x 24 features, staged so that the global stores are contiguous runs
+    float OUTS[LAYOUT == RGBNM_K0_LAYOUT_SWIN4 ? 4 * SW_RUN : 4];
 };
 static_assert(2 * TT_TOK <= 2 * RY_TOK && 4 * CT_BLK <= 4 * RC_BLK, "aliased tiles must fit");
 
@@ -197,7 +201,7 @@ struct RowSrc {
     int inf;
 };
 
-template <int MODE>
+template <int MODE, class WarpSmem>
 __device__ __forceinline__ RowSrc row_src(const WarpSmem& ws, int b, int i, const int16_t* __restrict__ y_img,
                                           const int16_t* __restrict__ c_img, int wb, int hc, int wc) {
     RowSrc r;
@@ -237,7 +241,7 @@ __device__ __forceinline__ void row_compute(const RowSrc& r, const int4& ra, con
 }
 
 // luma block b = tok*4 + bi*2 + bj -> RY[tok][bi*YROWS + i][bj*8 ..];  chroma block b -> RC[b-8][i][..]
-template <int MODE>
+template <int MODE, class WarpSmem>
 __device__ __forceinline__ void row_pass(WarpSmem& ws, int lane, const int16_t* __restrict__ y_img,
                                          const int16_t* __restrict__ c_img, int wb, int hc, int wc, bool clamp) {
     constexpr int YROWS = MODE == MODE_DOWN2 ? 16 : 8;
@@ -293,12 +297,102 @@ __device__ __forceinline__ void col_item(int mode, const float* __restrict__ col
     }
 }
 
-template <int OUT_MODE>
-__device__ __forceinline__ void process_row(WarpSmem& ws, int lane, int img, int th, const int16_t* __restrict__ y_img,
+// ---- Swin tail of one pair: per-block decomposition D = A^T . X . A (A(4,2) luma, A(2,4) chroma), the reference's
+// interleaved "(p1 pdh) (p2 pdw)" read-out, staging of the pair's 4 x 8 tokens x 24 features and contiguous stores.
+// On entry: luma tiles S (two units x 16 x 16, 2 x 2 blocks each) at RY + u * TT_TOK (ld TT_LD), finished chroma
+// blocks (unit u, comp) at RC + (2u + comp-1) * CT_BLK (ld CT_LD).
+template <int OUT_MODE, class WarpSmem>
+__device__ __forceinline__ void swin_out(WarpSmem& ws, int lane, int img, int th, int tp, void* __restrict__ out_) {
+    // column halves, in place (each lane reads and writes only its own column)
+    {
+        float* TT = ws.RY + (lane >> 4) * TT_TOK + (lane & 15);
+#pragma unroll
+        for (int bi = 0; bi < 2; ++bi) {
+            float x[8], o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = TT[(8 * bi + i) * TT_LD];
+            decomp_y_1d(x, o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) TT[(8 * bi + i) * TT_LD] = o[i];
+        }
+        float* CT = ws.RC + (lane >> 3) * CT_BLK + (lane & 7);
+        float x[8], o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = CT[i * CT_LD];
+        decomp_c_1d(x, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) CT[i * CT_LD] = o[i];
+    }
+    __syncwarp();
+    // row halves -> staging OUTS[a = token row 0..3][u][b = token col 0..3][24]
+    {
+        const int u = lane >> 4, r = lane & 15, bi = r >> 3, i = r & 7;
+        const float4* src = reinterpret_cast<const float4*>(ws.RY + u * TT_TOK + r * TT_LD);
+        const float4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
+        const float xs[2][8] = {{q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w}, {q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w}};
+        const int a = 2 * bi + (i & 1), p1 = i >> 1;
+#pragma unroll
+        for (int bj = 0; bj < 2; ++bj) {
+            float o[8];
+            decomp_y_1d(xs[bj], o);
+#pragma unroll
+            for (int pdw = 0; pdw < 2; ++pdw) {
+                float* dst = ws.OUTS + a * SW_RUN + (u * 4 + 2 * bj + pdw) * 24 + p1 * 4;
+                *reinterpret_cast<float4*>(dst) = make_float4(o[pdw], o[2 + pdw], o[4 + pdw], o[6 + pdw]);
+            }
+        }
+    }
+    {
+        const int cb = lane >> 3, i = lane & 7, u = cb >> 1, comp1 = cb & 1;
+        const float4* src = reinterpret_cast<const float4*>(ws.RC + cb * CT_BLK + i * CT_LD);
+        const float4 q0 = src[0], q1 = src[1];
+        const float x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        float o[8];
+        decomp_c_1d(x, o);
+        const int a = i & 3, p1 = i >> 2;
+#pragma unroll
+        for (int pdw = 0; pdw < 4; ++pdw) {
+            float* dst = ws.OUTS + a * SW_RUN + (u * 4 + pdw) * 24 + 16 + comp1 * 4 + p1 * 2;
+            *reinterpret_cast<float2*>(dst) = make_float2(o[pdw], o[4 + pdw]);
+        }
+    }
+    __syncwarp();
+    // contiguous runs: token row 4*th + a, tokens 8*tp .. 8*tp + 7
+    const size_t base = ((size_t(img) * 64 + 4 * th) * 64 + 8 * tp) * 24;
+    if (OUT_MODE == RGBNM_K0_OUT_F32) {
+        float* out = reinterpret_cast<float*>(out_);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int e = k * 32 + lane, a = e / 48, w = e - a * 48;           // 48 float4 per run
+            const float4 v = *reinterpret_cast<const float4*>(ws.OUTS + a * SW_RUN + w * 4);
+            *reinterpret_cast<float4*>(out + base + size_t(a) * 64 * 24 + w * 4) = v;
+        }
+    } else {
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int e = k * 32 + lane, a = e / 24, w = e - a * 24;           // 24 chunks of 8 bf16 per run
+            const float4 v0 = *reinterpret_cast<const float4*>(ws.OUTS + a * SW_RUN + w * 8);
+            const float4 v1 = *reinterpret_cast<const float4*>(ws.OUTS + a * SW_RUN + w * 8 + 4);
+            __nv_bfloat162 x = __floats2bfloat162_rn(v0.x, v0.y), y = __floats2bfloat162_rn(v0.z, v0.w);
+            __nv_bfloat162 z = __floats2bfloat162_rn(v1.x, v1.y), t = __floats2bfloat162_rn(v1.z, v1.w);
+            *reinterpret_cast<uint4*>(out + base + size_t(a) * 64 * 24 + w * 8) =
+                make_uint4(*reinterpret_cast<unsigned*>(&x), *reinterpret_cast<unsigned*>(&y),
+                           *reinterpret_cast<unsigned*>(&z), *reinterpret_cast<unsigned*>(&t));
+        }
+    }
+}
+
+template <int OUT_MODE, int LAYOUT>
+__device__ __forceinline__ void process_row(WarpSmemT<LAYOUT>& ws, int lane, int img, int th, const int16_t* __restrict__ y_img,
                                             const int16_t* __restrict__ c_img, const rgbnm_k0_tables& tb,
                                             const float* __restrict__ stats, void* __restrict__ out_, int wb, int hc, int wc) {
+    constexpr int GRID_Y = Geo<LAYOUT>::GRID_Y, GRID_C = Geo<LAYOUT>::GRID_C;
+    constexpr int TOKENS = Geo<LAYOUT>::TOKENS, FEAT = Geo<LAYOUT>::FEAT, PLANE_ELEMS = Geo<LAYOUT>::PLANE_ELEMS;
+    constexpr int PAIRS_PER_ROW = GRID_C / 2;
+    constexpr bool SWIN = LAYOUT == RGBNM_K0_LAYOUT_SWIN4;
     const rgbnm_plan& pl = ws.plan;
-    const int mode = mode_of(pl.crop_size);
+    const int mode = mode_of(pl.crop_size, GRID_Y);
     const bool clamp = pl.clamp_in != 0;
     const int yrows = mode == MODE_DOWN2 ? 16 : 8;       // row-pass rows per output block
 #pragma unroll 1
@@ -316,7 +410,7 @@ __device__ __forceinline__ void process_row(WarpSmem& ws, int lane, int img, int
                 r = th;
                 c = 2 * tp + ((b - 8) >> 1);
             }
-            const Trace t = trace_back(pl, comp, r, c);
+            const Trace t = trace_back<GRID_Y>(pl, comp, r, c);
             const int ci = comp == 0 ? pl.crop_i : (pl.crop_i >> 1);
             const int cj = comp == 0 ? pl.crop_j : (pl.crop_j >> 1);
             int sr, sc, chr = 0, chc = 0;
@@ -356,6 +450,7 @@ __device__ __forceinline__ void process_row(WarpSmem& ws, int lane, int img, int
                 int blk;
                 if (k < 2) blk = (2 * th + ((b >> 1) & 1)) * GRID_Y + 2 * (2 * tp + k) + (b & 1);
                 else blk = GRID_Y * GRID_Y + ((comp - 1) * GRID_C + th) * GRID_C + 2 * tp + ((b - 8) >> 1);
+                (void)TOKENS; (void)FEAT;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int li = T ? c : i, lj = T ? i : c;
@@ -378,6 +473,11 @@ __device__ __forceinline__ void process_row(WarpSmem& ws, int lane, int img, int
         __syncwarp();
         if (OUT_MODE == RGBNM_K0_OUT_INT16_PLANES) continue;
 
+        if (SWIN) {
+            swin_out<OUT_MODE>(ws, lane, img, th, tp, out_);
+            __syncwarp();
+            continue;
+        }
         // ---- P2b: column half of the sub-block conversion, in place: S -> A16 . S ----------------
         const int tok = lane >> 4;
         float* TT = ws.RY + tok * TT_TOK;
@@ -414,13 +514,15 @@ __device__ __forceinline__ void process_row(WarpSmem& ws, int lane, int img, int
     }
 }
 
-template <int OUT_MODE>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 25)
+template <int OUT_MODE, int LAYOUT>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, LAYOUT == RGBNM_K0_LAYOUT_SWIN4 ? 18 : 25)
 k0_fused_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, const int16_t* __restrict__ quant,
                 const rgbnm_plan* __restrict__ plans, rgbnm_k0_tables tb, const float* __restrict__ stats_all,
                 void* __restrict__ out_, int n_images, int hb, int wb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    using WarpSmem = WarpSmemT<LAYOUT>;
+    constexpr int ROWS_PER_IMAGE = Geo<LAYOUT>::GRID_C;
     WarpSmem& ws = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
     const int task = blockIdx.x * WARPS_PER_CTA + warp;
     if (task >= n_images * ROWS_PER_IMAGE) return;
@@ -442,44 +544,53 @@ k0_fused_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr,
     const int16_t* y_img = y + size_t(img) * hb * wb * 64;
     const int16_t* c_img = cbcr + size_t(img) * 2 * hc * wc * 64;
     const float* stats = stats_all + size_t(img) * RGBNM_MAX_OPS * 2;
-    if (mode_of(ws.plan.crop_size) == MODE_BAD) return;
-    process_row<OUT_MODE>(ws, lane, img, th, y_img, c_img, tb, stats, out_, wb, hc, wc);
+    if (mode_of(ws.plan.crop_size, Geo<LAYOUT>::GRID_Y) == MODE_BAD) return;
+    process_row<OUT_MODE, LAYOUT>(ws, lane, img, th, y_img, c_img, tb, stats, out_, wb, hc, wc);
 }
 
 }  // namespace k0
 
-extern "C" int rgbnm_k0_fused(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans,
-                              const rgbnm_k0_tables* tables, const float* stats, void* out, int out_mode, int n,
-                              int hb, int wb, void* stream) {
+template <int OUT_MODE, int LAYOUT>
+static int launch_k0(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans,
+                     const rgbnm_k0_tables* tables, const float* stats, void* out, int n, int hb, int wb, cudaStream_t st) {
     using namespace k0;
-    if (!y || !cbcr || !quant || !plans || !tables || !stats || !out || n < 0) return RGBNM_ERR_ARG;
-    if (hb < 2 || wb < 2 || hb > 255 || wb > 255 || (hb & 1) || (wb & 1)) return RGBNM_ERR_ARG;
-    if (n == 0) return RGBNM_OK;
     static bool configured = false;
-    const size_t smem = sizeof(WarpSmem) * WARPS_PER_CTA;
+    const size_t smem = sizeof(WarpSmemT<LAYOUT>) * WARPS_PER_CTA;
     if (!configured) {
-        RGBNM_CUDA_CHECK(cudaFuncSetAttribute(k0_fused_kernel<RGBNM_K0_OUT_F32>,
-                                              cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        RGBNM_CUDA_CHECK(cudaFuncSetAttribute(k0_fused_kernel<RGBNM_K0_OUT_BF16>,
-                                              cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        RGBNM_CUDA_CHECK(cudaFuncSetAttribute(k0_fused_kernel<RGBNM_K0_OUT_INT16_PLANES>,
+        RGBNM_CUDA_CHECK(cudaFuncSetAttribute(k0_fused_kernel<OUT_MODE, LAYOUT>,
                                               cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
-    const int tasks = n * ROWS_PER_IMAGE;
+    const int tasks = n * Geo<LAYOUT>::GRID_C;
     const int grid = (tasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const dim3 block(WARPS_PER_CTA * 32);
-    if (out_mode == RGBNM_K0_OUT_F32)
-        k0_fused_kernel<RGBNM_K0_OUT_F32><<<grid, block, smem, st>>>(y, cbcr, quant, plans, *tables, stats, out, n, hb, wb);
-    else if (out_mode == RGBNM_K0_OUT_BF16)
-        k0_fused_kernel<RGBNM_K0_OUT_BF16><<<grid, block, smem, st>>>(y, cbcr, quant, plans, *tables, stats, out, n, hb, wb);
-    else if (out_mode == RGBNM_K0_OUT_INT16_PLANES)
-        k0_fused_kernel<RGBNM_K0_OUT_INT16_PLANES><<<grid, block, smem, st>>>(y, cbcr, quant, plans, *tables, stats, out, n, hb, wb);
-    else
-        return RGBNM_ERR_ARG;
+    k0_fused_kernel<OUT_MODE, LAYOUT><<<grid, dim3(WARPS_PER_CTA * 32), smem, st>>>(y, cbcr, quant, plans, *tables, stats, out, n, hb, wb);
     RGBNM_CUDA_CHECK(cudaGetLastError());
     return RGBNM_OK;
+}
+
+extern "C" int rgbnm_k0_fused_ex(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans,
+                                 const rgbnm_k0_tables* tables, const float* stats, void* out, int out_mode, int layout,
+                                 int n, int hb, int wb, void* stream) {
+    if (!y || !cbcr || !quant || !plans || !tables || !stats || !out || n < 0) return RGBNM_ERR_ARG;
+    if (hb < 2 || wb < 2 || hb > 255 || wb > 255 || (hb & 1) || (wb & 1)) return RGBNM_ERR_ARG;
+    if (n == 0) return RGBNM_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define RGBNM_K0_CASE(OM, LY) \
+    if (out_mode == OM && layout == LY) return launch_k0<OM, LY>(y, cbcr, quant, plans, tables, stats, out, n, hb, wb, st)
+    RGBNM_K0_CASE(RGBNM_K0_OUT_F32, RGBNM_K0_LAYOUT_VIT16);
+    RGBNM_K0_CASE(RGBNM_K0_OUT_BF16, RGBNM_K0_LAYOUT_VIT16);
+    RGBNM_K0_CASE(RGBNM_K0_OUT_INT16_PLANES, RGBNM_K0_LAYOUT_VIT16);
+    RGBNM_K0_CASE(RGBNM_K0_OUT_F32, RGBNM_K0_LAYOUT_SWIN4);
+    RGBNM_K0_CASE(RGBNM_K0_OUT_BF16, RGBNM_K0_LAYOUT_SWIN4);
+    RGBNM_K0_CASE(RGBNM_K0_OUT_INT16_PLANES, RGBNM_K0_LAYOUT_SWIN4);
+#undef RGBNM_K0_CASE
+    return RGBNM_ERR_ARG;
+}
+
+extern "C" int rgbnm_k0_fused(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans,
+                              const rgbnm_k0_tables* tables, const float* stats, void* out, int out_mode, int n,
+                              int hb, int wb, void* stream) {
+    return rgbnm_k0_fused_ex(y, cbcr, quant, plans, tables, stats, out, out_mode, RGBNM_K0_LAYOUT_VIT16, n, hb, wb, stream);
 }
 
 extern "C" int rgbnm_k0_launch_count(void) { return 2; }

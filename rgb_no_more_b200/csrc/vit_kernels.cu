@@ -52,12 +52,23 @@ ln_fwd_kernel(const unsigned* __restrict__ x, const float* __restrict__ gamma, c
         g[k] = *reinterpret_cast<const float2*>(gamma + 2 * (k * 32 + lane));
         b[k] = *reinterpret_cast<const float2*>(beta + 2 * (k * 32 + lane));
     }
-    for (int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5); row < rows; row += gridDim.x * LN_WARPS) {
-        const unsigned* xr = x + size_t(row) * (E / 2);
+    // software-pipelined like the backward kernel: the next row's loads are in flight during this row's two reductions
+    const int stride = gridDim.x * LN_WARPS;
+    int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+    unsigned nx[PPL];
+    if (row < rows) {
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) nx[k] = __ldg(x + size_t(row) * (E / 2) + k * 32 + lane);
+    }
+    for (; row < rows; row += stride) {
         float2 v[PPL];
         float s = 0.0f;
 #pragma unroll
-        for (int k = 0; k < PPL; ++k) { v[k] = bf2_to_f2(__ldg(xr + k * 32 + lane)); s += v[k].x + v[k].y; }
+        for (int k = 0; k < PPL; ++k) { v[k] = bf2_to_f2(nx[k]); s += v[k].x + v[k].y; }
+        if (row + stride < rows) {
+#pragma unroll
+            for (int k = 0; k < PPL; ++k) nx[k] = __ldg(x + size_t(row + stride) * (E / 2) + k * 32 + lane);
+        }
         const float mean = warp_sum(s) * (1.0f / E);
         float q = 0.0f;
 #pragma unroll

@@ -47,6 +47,8 @@ SIGNATURES = {
     "rgbnm_k0_dcstats": (_i, [_vp, _vp, _vp, _vp, C.POINTER(K0Tables), _vp, _i, _i, _i, _vp]),
     "rgbnm_k0_fused": (_i, [_vp, _vp, _vp, _vp, C.POINTER(K0Tables), _vp, _vp, _i, _i, _i, _i, _vp]),
     "rgbnm_k0_launch_count": (_i, []),
+    "rgbnm_k0_dcstats_ex": (_i, [_vp, _vp, _vp, _vp, C.POINTER(K0Tables), _vp, _i, _i, _i, _i, _vp]),
+    "rgbnm_k0_fused_ex": (_i, [_vp, _vp, _vp, _vp, C.POINTER(K0Tables), _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rgbnm_gemm_bf16": (_i, [_vp, _vp]),
     "rgbnm_attention_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_float, _vp]),
     "rgbnm_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.c_float, _vp]),

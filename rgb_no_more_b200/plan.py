@@ -387,7 +387,18 @@ def eval_plan(height: int, width: int, size_resize: int = 32, size_crop: int = 2
     return Plan(crop_i=i, crop_j=j, crop_size=h, flip=False, train=False, ops=[])
 
 
-SUPPORTED_CROPS = {28: (2, 4, 14, 28, 56)}
+def eval_plan_swin(height: int, width: int, size: int = 32) -> Plan:
+    """`get_transform('imagenet_dct_swin','test')` (datasets.py:378-382): Resize_DCT(32) of the whole image
+    (custom_transforms.py:468-513) = a crop window covering every block, resized to `size`."""
+    if height != width:
+        raise NotImplementedError("rgbnm: non-square DCT resizes are outside the hot path")
+    return Plan(crop_i=0, crop_j=0, crop_size=height, flip=False, train=False, ops=[])
+
+
+# crop sides the fused kernel resizes (x2 down / identity / x2 up) per output grid.  28: ViT (datasets.py:355-366),
+# 32: SwinV2 (datasets.py:370-382).  Smaller sides are unreachable for 64x64-block inputs with scale=(0.05, 1):
+# sqrt(0.05 * 4096) = 14.3 snaps to 14 (factors of 28) / 16 (factors of 32).
+SUPPORTED_CROPS = {28: (14, 28, 56), 32: (16, 32, 64)}
 
 
 def pack_plans(plans: Sequence[Plan], clamp_in: Optional[Sequence[bool]] = None, out_size: int = 28) -> np.ndarray:

@@ -19,7 +19,10 @@ from . import lib as _lib
 from . import plan as P
 
 OUT_F32, OUT_BF16, OUT_INT16_PLANES = 0, 1, 2
+LAYOUT_VIT16, LAYOUT_SWIN4 = 0, 1
 PLANE_ELEMS = (28 * 28 + 2 * 14 * 14) * 64
+# out_size (luma blocks per side after the resize) -> (layout, tokens, features per token)
+GEOMETRY = {28: (LAYOUT_VIT16, 196, 384), 32: (LAYOUT_SWIN4, 4096, 24)}
 
 
 class FusedDCT:
@@ -27,12 +30,19 @@ class FusedDCT:
 
     >>> tf = FusedDCT(device, kind="train", ops_list=plan.AUGLIST_VITS, num_ops=2, ops_magnitude=9)
     >>> x = tf(y_q, c_q, quant)            # (B,196,384) operand of the patch-projection Linear
+
+    `out_size=32` selects the SwinV2 data path (datasets.py:370-382, models/swinv2.py:505-576): planes resized to
+    32 x 32 luma blocks, every 8 x 8 block decomposed into 4 x 4 (Y) / 2 x 2 (CbCr) sub-blocks -> (B, 4096, 24).
     """
 
     def __init__(self, device, kind: str = "test", ops_list: Optional[Sequence[str]] = None, num_ops: int = 2,
                  ops_magnitude: int = 10, out_dtype: torch.dtype = torch.float32, out_size: int = 28):
-        if out_size != 28:
-            raise NotImplementedError("rgbnm: only the 28-block (patch 16, 224 px) geometry is on the hot path")
+        if out_size not in GEOMETRY:
+            raise NotImplementedError("rgbnm: only the 28-block (ViT, patch 16) and 32-block (SwinV2, patch 4) geometries "
+                                      "are on the hot path")
+        self.out_size = out_size
+        self.layout, self.tokens, self.feat = GEOMETRY[out_size]
+        self.plane_elems = (out_size * out_size + 2 * (out_size // 2) ** 2) * 64
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.RgbnmError("rgbnm: FusedDCT needs a CUDA device; there is no CPU fallback")
@@ -61,9 +71,9 @@ class FusedDCT:
     def sample_plans(self, n: int, hb: int = 64, wb: int = 64) -> List[P.Plan]:
         """Draw n plans from the torch global CPU RNG in the reference's call order."""
         if self.kind == "train":
-            return [P.sample_train_plan(hb, wb, self.ops_list, self.num_ops, self.ops_magnitude, self.bank)
+            return [P.sample_train_plan(hb, wb, self.ops_list, self.num_ops, self.ops_magnitude, self.bank, size=self.out_size)
                     for _ in range(n)]
-        return [P.eval_plan(hb, wb)] * n
+        return [P.eval_plan(hb, wb) if self.out_size == 28 else P.eval_plan_swin(hb, wb, self.out_size)] * n
 
     # -- launch ---------------------------------------------------------------------------
     def run(self, y_q: torch.Tensor, c_q: torch.Tensor, quant: torch.Tensor, plans, clamp_in=None,
@@ -86,7 +96,7 @@ class FusedDCT:
                 for pl in plans:
                     if pl.crop_i + pl.crop_size > hb or pl.crop_j + pl.crop_size > wb or pl.crop_i < 0 or pl.crop_j < 0:
                         raise ValueError("rgbnm: crop window outside the image")
-                plans = P.pack_plans(plans, clamp_in)
+                plans = P.pack_plans(plans, clamp_in, out_size=self.out_size)
             if len(plans) != B:
                 raise ValueError("rgbnm: one plan per image required")
             plans_dev = torch.from_numpy(plans.view(np.uint8).reshape(B, -1)).to(self.device, non_blocking=True)
@@ -95,17 +105,17 @@ class FusedDCT:
             out_mode = OUT_BF16 if self.out_dtype == torch.bfloat16 else OUT_F32
         if out is None:
             if out_mode == OUT_INT16_PLANES:
-                out = torch.empty((B, PLANE_ELEMS), dtype=torch.int16, device=self.device)
+                out = torch.empty((B, self.plane_elems), dtype=torch.int16, device=self.device)
             else:
-                out = torch.empty((B, 196, 384), dtype=torch.bfloat16 if out_mode == OUT_BF16 else torch.float32,
+                out = torch.empty((B, self.tokens, self.feat), dtype=torch.bfloat16 if out_mode == OUT_BF16 else torch.float32,
                                   device=self.device)
         stats = torch.zeros((B, P.MAX_OPS, 2), dtype=torch.float32, device=self.device)
         st = _lib.stream_ptr()
         L = self._lib
-        _lib.check(L.rgbnm_k0_dcstats(y_q.data_ptr(), c_q.data_ptr(), quant.data_ptr(), plans_dev.data_ptr(),
-                                      C.byref(self._tables), stats.data_ptr(), B, hb, wb, st), "rgbnm_k0_dcstats")
-        _lib.check(L.rgbnm_k0_fused(y_q.data_ptr(), c_q.data_ptr(), quant.data_ptr(), plans_dev.data_ptr(),
-                                    C.byref(self._tables), stats.data_ptr(), out.data_ptr(), out_mode, B, hb, wb, st),
+        _lib.check(L.rgbnm_k0_dcstats_ex(y_q.data_ptr(), c_q.data_ptr(), quant.data_ptr(), plans_dev.data_ptr(),
+                                         C.byref(self._tables), stats.data_ptr(), B, hb, wb, self.layout, st), "rgbnm_k0_dcstats")
+        _lib.check(L.rgbnm_k0_fused_ex(y_q.data_ptr(), c_q.data_ptr(), quant.data_ptr(), plans_dev.data_ptr(),
+                                       C.byref(self._tables), stats.data_ptr(), out.data_ptr(), out_mode, self.layout, B, hb, wb, st),
                    "rgbnm_k0_fused")
         self.last_stats = stats
         return out
@@ -115,11 +125,12 @@ class FusedDCT:
         return self.run(y_q, c_q, quant, plans, clamp_in)
 
 
-def split_planes(planes: torch.Tensor):
-    """INT16_PLANES output -> (Y [B,1,28,28,8,8], CbCr [B,2,14,14,8,8]) in the reference layout."""
+def split_planes(planes: torch.Tensor, out_size: int = 28):
+    """INT16_PLANES output -> (Y [B,1,S,S,8,8], CbCr [B,2,S/2,S/2,8,8]) in the reference layout (S = 28 or 32)."""
     B = planes.shape[0]
-    y = planes[:, : 784 * 64].reshape(B, 1, 28, 28, 8, 8)
-    c = planes[:, 784 * 64:].reshape(B, 2, 14, 14, 8, 8)
+    S, H = out_size, out_size // 2
+    y = planes[:, : S * S * 64].reshape(B, 1, S, S, 8, 8)
+    c = planes[:, S * S * 64:].reshape(B, 2, H, H, 8, 8)
     return y, c
 
 
@@ -127,11 +138,12 @@ def get_transform(dataset: str = "imagenet_dct", type: str = "train", ops_list=N
                   ops_magnitude: int = 10, dtype=torch.float32, device="cuda"):
     """Same selector as the reference's datasets.get_transform (datasets.py:305-390) for the
     DCT datasets; returns a batch transform bound to `device`."""
-    if dataset != "imagenet_dct":
+    if dataset not in ("imagenet_dct", "imagenet_dct_swin"):
         raise NotImplementedError(f"rgbnm: dataset '{dataset}' is outside the B200 hot path (SURVEY.md 8f)")
+    size = 28 if dataset == "imagenet_dct" else 32          # datasets.py:355-366 / :370-382
     if type == "train":
-        return FusedDCT(device, "train", ops_list, num_ops, ops_magnitude, dtype)
+        return FusedDCT(device, "train", ops_list, num_ops, ops_magnitude, dtype, out_size=size)
     if type in ("val", "test"):
-        return FusedDCT(device, "test", None, 0, 0, dtype)
+        return FusedDCT(device, "test", None, 0, 0, dtype, out_size=size)
     print("Unrecognized dataset type! Returning 'None' transform")
     return None

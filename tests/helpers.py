@@ -91,3 +91,25 @@ def golden_vit_inputs(seed):
     yf = torch.rand((2, 1, 28, 28, 8, 8), generator=g) * 2 - 1
     cf = torch.rand((2, 2, 14, 14, 8, 8), generator=g) * 2 - 1
     return yf, cf
+
+
+def seeded_swin_state_dict(model, seed=11997733):
+    """Weight recipe of tools/make_golden_swin.py for SwinV2: `seeded_state_dict`, except that the constructed
+    buffers (relative_coords_table, relative_position_index, attn_mask) keep their values and logit_scale is
+    log(10) + 0.3 * seeded normal (so that both sides of the clamp at log(100), swinv2.py:158, are visited)."""
+    sd = seeded_state_dict(model, seed)
+    own = model.state_dict()
+    for k in own:
+        if "relative_coords_table" in k or "relative_position_index" in k or "attn_mask" in k:
+            sd[k] = own[k]
+        if k.endswith("logit_scale"):
+            g = torch.Generator().manual_seed(len(k))
+            sd[k] = torch.log(10 * torch.ones_like(own[k])) + 0.3 * torch.randn(own[k].shape, generator=g)
+    return sd
+
+
+def golden_swin_inputs(seed, batch=2):
+    g = torch.Generator().manual_seed(int(seed))
+    yf = torch.rand((batch, 1, 32, 32, 8, 8), generator=g) * 2 - 1
+    cf = torch.rand((batch, 2, 16, 16, 8, 8), generator=g) * 2 - 1
+    return yf, cf
