@@ -242,6 +242,31 @@ int rgbnm_attention_fwd(const void* qkv, void* o, float* lse, int B, int N, int 
 int rgbnm_attention_bwd(const void* dout, const void* qkv, const void* o, const float* lse, void* dqkv, float* dvec, int B,
                         int N, int H, int D, float scale, void* stream);
 
+
+/* ------------------------------------------------------------------------------
+ * (a33) SwinV2 DCT forward path (models/swinv2.py).  The dense contractions (qkv / proj / fc1+GELU / fc2 / patch-merging
+ * reduction / head) go through rgbnm_gemm_bf16; these are the memory-bound kernels around them.
+ * ---------------------------------------------------------------------------- */
+/* Post-norm residual of SwinTransformerBlock.forward (swinv2.py:302-306) and plain nn.LayerNorm (patch_embed.norm :568,
+ * PatchMerging.norm :361, final norm :696): y = (res ? res : 0) + LayerNorm(x) * gamma + beta; x, res, y bf16 [rows][emb],
+ * gamma/beta fp32; emb even, <= 1536. */
+int rgbnm_layernorm_res_fwd(const void* x, const float* gamma, const float* beta, const void* res, void* y, int rows,
+                            int emb, float eps, void* stream);
+/* WindowAttention.forward core (swinv2.py:152-177) on tokens kept in image order: window partition, cyclic shift by
+ * `shift` and their inverses (swinv2.py:39-66, 283-300) are folded into the kernel's gather / scatter.
+ *   qkv   bf16 [B*H*W][3*C], columns (which, head, d) as after the qkv Linear (swinv2.py:153-155)
+ *   out   bf16 [B*H*W][C], columns (head, d) = input of the proj Linear
+ *   bias  fp32 [heads][window^2][window^2] = 16 * sigmoid(cpb_mlp(relative_coords_table))[relative_position_index]
+ *   scale fp32 [heads] = exp(min(logit_scale, log(100)))                            (swinv2.py:158-168)
+ * scores = normalize(q) . normalize(k)^T * scale + bias (+ -100 between different shift regions, swinv2.py:227-242),
+ * softmax, . v.  Round 1: window = 8, head dimension C / heads = 32 (SwinV2-T, utils/configs.py:123-137). */
+int rgbnm_window_attention_fwd(const void* qkv, void* out, const float* bias, const float* scale, int B, int H, int W,
+                               int C, int heads, int window, int shift, void* stream);
+/* PatchMerging gather (swinv2.py:353-358): out bf16 [B][H/2][W/2][4*C] = [x(2h,2w) | x(2h+1,2w) | x(2h,2w+1) | x(2h+1,2w+1)] */
+int rgbnm_patch_merge_gather(const void* x, void* out, int B, int H, int W, int C, void* stream);
+/* AdaptiveAvgPool1d(1) over tokens (swinv2.py:697-699): out bf16 [B][C] = mean_l x[b][l][c] */
+int rgbnm_token_mean_bf16(const void* x, void* out, int B, int L, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,10 @@ SIGNATURES = {
     "rgbnm_qkv_perm_vec": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rgbnm_qkv_unperm_rows_add": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rgbnm_sumsq_f32": (_i, [_vp, C.c_longlong, _vp, _vp]),
+    "rgbnm_layernorm_res_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, C.c_float, _vp]),
+    "rgbnm_window_attention_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "rgbnm_patch_merge_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "rgbnm_token_mean_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "rgbnm_adamw_step": (_i, [_vp, _vp, _vp, _vp, C.c_longlong, C.c_longlong, _vp, _vp, _vp]),
 }
 

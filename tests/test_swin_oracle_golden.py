@@ -62,3 +62,66 @@ def test_swin_plan_sampler_crops():
     pl = P.eval_plan_swin(64, 64)
     assert (pl.crop_i, pl.crop_j, pl.crop_size) == (0, 0, 64)
     P.pack_plans([pl], out_size=32)
+
+
+def _swin_shell():
+    from rgb_no_more_b200 import swin as S
+    return S.SwinTransformerV2(img_size=256, patch_size=4, embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24],
+                               window_size=8, mlp_ratio=4, drop_rate=0, attn_drop_rate=0, drop_path_rate=0.2, qkv_bias=True,
+                               ape=False, patch_norm=True, pretrained_window_sizes=[0, 0, 0, 0], device="cpu", pixel_space="dct")
+
+
+def test_swin_state_dict_matches_reference_keys():
+    """The drop-in exposes exactly the reference's state_dict (names, shapes, buffers incl. attn_mask values)."""
+    g = load("swin_model.npz")
+    m = _swin_shell()
+    sd = m.state_dict()
+    assert sorted(sd.keys()) == list(g["state_keys"])
+    for k, shp in zip(g["state_keys"], g["state_shapes"]):
+        assert ",".join(map(str, sd[str(k)].shape)) == str(shp), k
+    from oracle import swin_oracle as SO
+    assert torch.equal(sd["layers.0.blocks.1.attn_mask"], SO.shift_mask(64, 64, 8, 4))
+    t, i = SO.relative_tables(8)
+    assert torch.equal(sd["layers.2.blocks.3.attn.relative_position_index"], i)
+    assert torch.allclose(sd["layers.2.blocks.3.attn.relative_coords_table"], t)
+
+
+def test_swin_oracle_matches_reference():
+    """oracle/swin_oracle.py against the real swinv2.SwinTransformerV2 outputs in swin_model.npz (fp32 CPU both sides)."""
+    from oracle import swin_oracle as SO
+    from tests.helpers import seeded_swin_state_dict
+    g = load("swin_model.npz")
+    sd = seeded_swin_state_dict(_swin_shell())
+    yf, cf = golden_swin_inputs(g["input_seed"])
+    emb = O.embed_input_swin(yf, cf)
+    assert np.abs(SO.tokens(sd, emb)[0].numpy() - g["tokens"]).max() < 2e-5
+    acts = []
+    logits = SO.forward_from_embed(sd, emb, collect=acts)
+    acts = dict(acts)
+    for name, rows in (("l0b0", 512), ("l0b1", 512), ("stage0", 256), ("stage1", 256), ("stage2", 256), ("stage3", 256)):
+        ref = g["act:" + name]
+        got = acts[name][0, :rows].numpy()
+        assert np.abs(got - ref).max() < 2e-4 * max(1.0, np.abs(ref).max()), name
+    assert np.abs(logits.numpy() - g["logits"]).max() < 2e-4
+
+
+def test_swin_no_cpu_fallback():
+    m = _swin_shell().eval()
+    yf, cf = golden_swin_inputs(5, batch=1)
+    import pytest
+    from rgb_no_more_b200.lib import RgbnmError
+    with pytest.raises((RgbnmError, RuntimeError)):
+        with torch.no_grad():
+            m(yf, cf)
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(yf, cf)
+
+
+def test_swin_compat_embed_path_matches_oracle():
+    """forward(y, cbcr)'s torch-op tail (reference-format inputs) equals the oracle's embed input."""
+    from rgb_no_more_b200 import swin as S
+    yf, cf = golden_swin_inputs(9, batch=1)
+    got = S.swin_embed_input_from_planes(yf, cf)
+    ref = O.embed_input_swin(yf, cf).reshape(1, 4096, 24)
+    assert float((got - ref).abs().max()) < 1e-5
