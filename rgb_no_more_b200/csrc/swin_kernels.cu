@@ -6,10 +6,13 @@
 //   token mean                          AdaptiveAvgPool1d(1)                      models/swinv2.py:697-699
 // Window partition / cyclic shift / window reverse (swinv2.py:39-66, 283-300) are index maps: the attention kernel
 // gathers each window's tokens from their image positions and scatters the result back, nothing is materialised.
-// All four are HBM-bound by design; the attention arithmetic (64 x 64 x 32 per window and head) runs on the
-// CUDA cores in fp32 (round 1; a tensor-core version is the next step).
+// All four are HBM-bound by design; the attention arithmetic (64 x 64 x 32 per window and head) runs on warp-level
+// tensor-core MMAs with S / P / O in registers (window_attn_mma_kernel); the first, CUDA-core fp32 version
+// (window_attn_fwd_kernel) is kept behind RGBNM_WATTN_SIMT=1 for A/B runs.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 
 #include "../../include/rgbnm_b200.h"
 #include "common.cuh"
@@ -201,6 +204,193 @@ window_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// The same on warp-level tensor-core MMAs (mma.sync m16n8k16, bf16 x bf16 -> fp32).  64 x 64 x 32 problems sit below the
+// 128-row tcgen05 tile (two windows per UMMA would waste half the MMA on cross-window scores and still pay a TMEM round
+// trip per softmax), so this kernel keeps S, P and O in registers, flash-attention style:
+//   CTA = 4 warps = one (window, head) per iteration, grid-strided over the windows of one head so that the head's
+//   64 x 64 bias tile is staged in shared memory once; warp w owns query rows 16w .. 16w+15.
+//   S = Q K^T on the RAW bf16 q / k (products exact in fp32); the cosine normalisation, logit scale, bias and shift mask
+//   are applied to the fp32 accumulators: s = raw * (scale / |q_i|) * (1 / |k_j|) + bias_ij (+ -100) -- no extra bf16
+//   rounding of normalised operands.  P (bf16) is re-used from the accumulator registers as the A operand of P V;
+//   V sits transposed in shared memory so that every B fragment is one 32-bit load; all fragment loads are conflict-free
+//   (row pitches 80 B / 144 B / 288 B).
+// ------------------------------------------------------------------------------------------
+constexpr int KS_LD = 40;     // bf16 per staged K row (32 + 8 pad)
+constexpr int VT_LD = 72;     // bf16 per row of V^T (64 keys + 8 pad)
+constexpr int BS_LD = 72;     // floats per staged bias row
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float sumsq_bf2(unsigned w) {
+    const float2 f = bf2_to_f2(w);
+    return f.x * f.x + f.y * f.y;
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+
+__global__ void __launch_bounds__(128)
+window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, const float* __restrict__ bias,
+                       const float* __restrict__ scale, int H, int W, int C, int shift, int n_windows) {
+    __shared__ __align__(16) __nv_bfloat16 Ks[WT * KS_LD];
+    __shared__ __align__(16) __nv_bfloat16 Vt[HD * VT_LD];
+    __shared__ __align__(16) float Bs[WT * BS_LD];
+    __shared__ float rk[WT];
+    __shared__ int region[WT];
+    __shared__ int toks[WT];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int head = blockIdx.y;
+    for (int e = tid; e < WT * (WT / 4); e += 128) {
+        const int row = e >> 4, c4 = e & 15;
+        *reinterpret_cast<float4*>(Bs + row * BS_LD + c4 * 4) = __ldg(reinterpret_cast<const float4*>(bias + (size_t(head) * WT + row) * WT) + c4);
+    }
+    const float sc = __ldg(scale + head);
+    const int wpr = W / WS, wpi = (H / WS) * wpr;
+    const int R0 = warp * 16 + g, R1 = R0 + 8;
+
+    for (int win = blockIdx.x; win < n_windows; win += gridDim.x) {
+        __syncthreads();                       // the previous window's shared-memory reads are done (first pass: bias staged)
+        if (tid < WT) {
+            const int img = win / wpi, wrem = win - img * wpi;
+            const int wy = wrem / wpr, wx = wrem - wy * wpr;
+            const int sy = wy * WS + (tid >> 3), sx = wx * WS + (tid & 7);
+            int py = sy + shift, px = sx + shift;
+            if (py >= H) py -= H;
+            if (px >= W) px -= W;
+            toks[tid] = (img * H + py) * W + px;
+            int reg = 0;
+            if (shift > 0) {
+                const int hr = sy < H - WS ? 0 : (sy < H - shift ? 1 : 2);
+                const int wr = sx < W - WS ? 0 : (sx < W - shift ? 1 : 2);
+                reg = 3 * hr + wr;
+            }
+            region[tid] = reg;
+        }
+        __syncthreads();
+        // ---- K, V of the window -> shared memory (K row-major, V transposed); thread = (row, 16-dim half) ----
+        {
+            const int r = tid >> 1, half = tid & 1;
+            const __nv_bfloat16* row = qkv + size_t(toks[r]) * (3 * size_t(C)) + head * HD + half * 16;
+            const uint4 k0 = __ldg(reinterpret_cast<const uint4*>(row + C)), k1 = __ldg(reinterpret_cast<const uint4*>(row + C) + 1);
+            const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(row + 2 * C)), v1 = __ldg(reinterpret_cast<const uint4*>(row + 2 * C) + 1);
+            uint4* kd = reinterpret_cast<uint4*>(Ks + r * KS_LD + half * 16);
+            kd[0] = k0;
+            kd[1] = k1;
+            float n = sumsq_bf2(k0.x) + sumsq_bf2(k0.y) + sumsq_bf2(k0.z) + sumsq_bf2(k0.w) + sumsq_bf2(k1.x) + sumsq_bf2(k1.y) +
+                      sumsq_bf2(k1.z) + sumsq_bf2(k1.w);
+            n += __shfl_xor_sync(0xffffffffu, n, 1);
+            if (half == 0) rk[r] = 1.0f / fmaxf(sqrtf(n), 1e-12f);
+            const unsigned vw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            unsigned short* vt = reinterpret_cast<unsigned short*>(Vt);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                vt[(half * 16 + 2 * e) * VT_LD + r] = static_cast<unsigned short>(vw[e] & 0xffffu);
+                vt[(half * 16 + 2 * e + 1) * VT_LD + r] = static_cast<unsigned short>(vw[e] >> 16);
+            }
+        }
+        // ---- Q fragments of this warp's 16 rows, straight from global ----
+        unsigned qa[2][4];
+        const int tok0 = toks[R0], tok1 = toks[R1];
+        {
+            const unsigned* p0 = reinterpret_cast<const unsigned*>(qkv + size_t(tok0) * (3 * size_t(C)) + head * HD);
+            const unsigned* p1 = reinterpret_cast<const unsigned*>(qkv + size_t(tok1) * (3 * size_t(C)) + head * HD);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                qa[ks][0] = __ldg(p0 + ks * 8 + t);
+                qa[ks][1] = __ldg(p1 + ks * 8 + t);
+                qa[ks][2] = __ldg(p0 + ks * 8 + 4 + t);
+                qa[ks][3] = __ldg(p1 + ks * 8 + 4 + t);
+            }
+        }
+        const float n0 = quad_sum(sumsq_bf2(qa[0][0]) + sumsq_bf2(qa[0][2]) + sumsq_bf2(qa[1][0]) + sumsq_bf2(qa[1][2]));
+        const float n1 = quad_sum(sumsq_bf2(qa[0][1]) + sumsq_bf2(qa[0][3]) + sumsq_bf2(qa[1][1]) + sumsq_bf2(qa[1][3]));
+        const float f0 = sc / fmaxf(sqrtf(n0), 1e-12f), f1 = sc / fmaxf(sqrtf(n1), 1e-12f);
+        __syncthreads();
+
+        // ---- S = Q K^T (raw), 8 key tiles x 2 k-steps ----
+        float s[8][4];
+        const unsigned* ksw = reinterpret_cast<const unsigned*>(Ks);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const int w = (nt * 8 + g) * (KS_LD / 2) + ks * 8 + t;
+                mma16816(s[nt], qa[ks], ksw[w], ksw[w + 4]);
+            }
+        }
+        // ---- cosine normalisation, logit scale, relative position bias, shift mask; row maxima ----
+        const int reg0 = region[R0], reg1 = region[R1];
+        float m0 = -3.0e38f, m1 = -3.0e38f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int col = nt * 8 + 2 * t;
+            const float rk0 = rk[col], rk1 = rk[col + 1];
+            const float2 b0 = *reinterpret_cast<const float2*>(Bs + R0 * BS_LD + col);
+            const float2 b1 = *reinterpret_cast<const float2*>(Bs + R1 * BS_LD + col);
+            s[nt][0] = fmaf(s[nt][0] * rk0, f0, b0.x);
+            s[nt][1] = fmaf(s[nt][1] * rk1, f0, b0.y);
+            s[nt][2] = fmaf(s[nt][2] * rk0, f1, b1.x);
+            s[nt][3] = fmaf(s[nt][3] * rk1, f1, b1.y);
+            if (shift > 0) {
+                const int c0 = region[col], c1 = region[col + 1];
+                if (c0 != reg0) s[nt][0] += -100.0f;
+                if (c1 != reg0) s[nt][1] += -100.0f;
+                if (c0 != reg1) s[nt][2] += -100.0f;
+                if (c1 != reg1) s[nt][3] += -100.0f;
+            }
+            m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+            m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        m0 = quad_max(m0);
+        m1 = quad_max(m1);
+        float l0 = 0.0f, l1 = 0.0f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = __expf(s[nt][0] - m0);
+            s[nt][1] = __expf(s[nt][1] - m0);
+            s[nt][2] = __expf(s[nt][2] - m1);
+            s[nt][3] = __expf(s[nt][3] - m1);
+            l0 += s[nt][0] + s[nt][1];
+            l1 += s[nt][2] + s[nt][3];
+        }
+        l0 = quad_sum(l0);
+        l1 = quad_sum(l1);
+        // ---- O = P V: 4 key steps x 4 dim tiles; P from the accumulator registers ----
+        float o[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.0f;
+        const unsigned* vtw = reinterpret_cast<const unsigned*>(Vt);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const unsigned pa[4] = {f2_to_bf2(s[2 * kk][0], s[2 * kk][1]), f2_to_bf2(s[2 * kk][2], s[2 * kk][3]),
+                                    f2_to_bf2(s[2 * kk + 1][0], s[2 * kk + 1][1]), f2_to_bf2(s[2 * kk + 1][2], s[2 * kk + 1][3])};
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int w = (nt * 8 + g) * (VT_LD / 2) + kk * 8 + t;
+                mma16816(o[nt], pa, vtw[w], vtw[w + 4]);
+            }
+        }
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        unsigned* d0 = reinterpret_cast<unsigned*>(out + size_t(tok0) * C + head * HD);
+        unsigned* d1 = reinterpret_cast<unsigned*>(out + size_t(tok1) * C + head * HD);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            d0[nt * 4 + t] = f2_to_bf2(o[nt][0] * i0, o[nt][1] * i0);
+            d1[nt * 4 + t] = f2_to_bf2(o[nt][2] * i1, o[nt][3] * i1);
+        }
+    }
+}
+
 // out[b][h2][w2][q * C + c] = x[b][2 * h2 + (q & 1)][2 * w2 + (q >> 1)][c]      (x0 | x1 | x2 | x3, swinv2.py:353-358)
 __global__ void __launch_bounds__(256)
 patch_merge_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int H, int W, int C8, size_t total) {
@@ -274,9 +464,20 @@ extern "C" int rgbnm_window_attention_fwd(const void* qkv, void* out, const floa
     if (window != WS || heads <= 0 || C != heads * HD) return RGBNM_ERR_UNSUPPORTED;
     if (H <= 0 || W <= 0 || (H % WS) || (W % WS) || shift < 0 || shift >= WS) return RGBNM_ERR_ARG;
     if (B == 0) return RGBNM_OK;
-    const dim3 grid(unsigned(B) * (H / WS) * (W / WS), heads);
-    window_attn_fwd_kernel<<<grid, WT, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), bias, scale, H, W, C, shift);
+    const int n_windows = B * (H / WS) * (W / WS);
+    static const bool simt = (getenv("RGBNM_WATTN_SIMT") != nullptr);     // the CUDA-core kernel, kept for A/B runs
+    if (simt) {
+        const dim3 grid(n_windows, heads);
+        window_attn_fwd_kernel<<<grid, WT, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), bias, scale, H, W, C, shift);
+    } else {
+        // a CTA keeps its head's bias tile in shared memory and walks windows: enough CTAs for ~8 per SM, at least 2 windows each
+        int ctas = (rgbnm_num_sms() * 8 + heads - 1) / heads;
+        if (ctas > n_windows) ctas = n_windows;
+        const dim3 grid(ctas, heads);
+        window_attn_mma_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), bias, scale, H, W, C, shift, n_windows);
+    }
     RGBNM_CUDA_CHECK(cudaGetLastError());
     return RGBNM_OK;
 }

@@ -57,3 +57,5 @@ def run() -> None:
     except ImportError:
         return
     vit_smoke.run()
+    from . import swin_smoke
+    swin_smoke.run()

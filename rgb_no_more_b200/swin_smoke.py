@@ -1,0 +1,50 @@
+"""Third part of the smoke run: JPEG coefficients -> K0 in the SwinV2 layout -> a two-stage SwinV2 DCT forward on cuda:0
+(window attention with and without the cyclic shift, patch merging, post-norm LayerNorm), logits checked against the CPU
+oracle (oracle/dct_oracle.py + oracle/swin_oracle.py: checkers only)."""
+from __future__ import annotations
+
+import torch
+
+
+def run() -> None:
+    from oracle import dct_oracle as O           # checker only
+    from oracle import swin_oracle as SO         # checker only
+    from . import dct_manip as dm
+    from . import plan as P
+    from . import swin as S
+    from . import synth
+    from . import transforms as TF
+
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(11997733)
+    B = 2
+    y, c, q, flags = dm.decode_batch(synth.synth_jpeg_set(B), 64, 64, nthreads=2)
+    tf = TF.get_transform("imagenet_dct_swin", "test", dtype=torch.float32, device=dev)
+    emb = tf(y.to(dev), c.to(dev), q.to(dev))
+    depths, heads = (2, 2), (3, 6)
+    m = S.SwinTransformerV2(img_size=256, patch_size=4, embed_dim=96, depths=list(depths), num_heads=list(heads), window_size=8,
+                            drop_path_rate=0.0, pretrained_window_sizes=[0, 0], device="cpu", pixel_space="dct")
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.ndim == 1:
+                p.add_(0.2 * torch.randn_like(p))          # the reference zero-initialises the block post-norms
+    sd = {k: v.detach().float().cpu().clone() for k, v in m.state_dict().items()}
+    m.eval().to(dev)
+    with torch.no_grad():
+        logits = m(emb.to(torch.bfloat16)).float().cpu()
+    torch.cuda.synchronize()
+    pl = P.eval_plan_swin(64, 64)
+    worst = 0.0
+    for b in range(B):
+        e = O.transform_embed_swin(y[b].reshape(1, 64, 64, 8, 8), c[b].reshape(2, 32, 32, 8, 8), q[b].reshape(3, 8, 8), pl, None)
+        d = float((emb[b].cpu() - e).abs().max())
+        # resize ties move single int16 LSBs (1/1020 in ToRange units, spread by the orthonormal decomposition)
+        if d > 2e-3:
+            raise AssertionError(f"rgbnm smoke: Swin embed input differs from the oracle by {d}")
+        ref = SO.forward_from_embed(sd, e.reshape(1, 64, 64, 24), depths=depths, heads=heads)
+        err = float((logits[b] - ref[0]).abs().max())
+        rng = float(ref.max() - ref.min())
+        worst = max(worst, err / max(rng, 1e-6))
+        if not err <= 3e-2 * max(rng, 1.0):
+            raise AssertionError(f"rgbnm smoke: SwinV2 logits differ from the oracle by {err} (range {rng})")
+    print(f"rgbnm smoke: SwinV2 DCT forward ok (|dlogits| <= {worst:.3g} of the logit range)")
