@@ -336,6 +336,15 @@ def run_ours(args):
         ms_fwd = timed_loop(lambda i: g_fwd.replay(), n_fwd, 3) / (n_fwd * N_POOL)
         eval_fwd_ips = B * world / (ms_fwd * 1e-3)
 
+    # SwinV2-T DCT eval forward (BASELINE config 5 shape, per GPU): K0 in the Swin layout
+    # (Resize_DCT(32) geometry) -> SwinTransformerV2 forward, same resident coefficient batches, CUDA-graph replay
+    swin_fwd = None
+    if world == 1 and args.stage == "train" and out_dtype == torch.bfloat16 and not args.no_swin:
+        try:
+            swin_fwd = swin_eval_forward(args, dev, dev_pool, clamp_flags, timed_loop)
+        except Exception as ex:  # noqa: BLE001 -- a side measurement must never cost the headline line
+            swin_fwd = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -373,6 +382,8 @@ def run_ours(args):
     if eval_fwd_ips is not None:
         line["eval_forward"] = {"value": eval_fwd_ips, "unit": UNIT, "what": "K0 (eval geometry) + ViT forward, no gradients, coefficients "
                                 "resident in HBM, CUDA-graph replay"}
+    if swin_fwd is not None:
+        line["swin_eval_forward"] = swin_fwd
     if stage is not None and args.arch in VIT_TRAIN_GFLOP_PER_IMAGE:
         # the ViT part of the step against the measured cuBLAS bf16 rate (sustained figure: timed inside a long step)
         tf_s = VIT_TRAIN_GFLOP_PER_IMAGE[args.arch] * B / ((ms_step - k0_avg_ms) * 1e-3) / 1e3
@@ -384,6 +395,55 @@ def run_ours(args):
         line["host_decode"] = host_decode_rate()
         line["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(line))
+
+
+def swin_eval_forward(args, dev, dev_pool, clamp_flags, timed_loop):
+    from rgb_no_more_b200 import plan as P, swin as S, transforms as TF
+    B = args.batch
+    torch.manual_seed(11997733)
+    model = S.SwinTransformerV2(img_size=256, patch_size=4, embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24],
+                                window_size=8, mlp_ratio=4, drop_path_rate=0.2, pretrained_window_sizes=[0, 0, 0, 0],
+                                device="cpu", pixel_space="dct")
+    with torch.no_grad():       # the reference zero-initialises the block post-norms (identity blocks): randomise them
+        for p in model.parameters():
+            if p.ndim == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    model.eval().to(dev)
+    eng = model.prepare(dev)
+    tf = TF.FusedDCT(dev, "test", None, 0, 0, torch.bfloat16, out_size=32)
+    plans = tf.sample_plans(B)
+    pdev = [torch.from_numpy(P.pack_plans(plans, fl, out_size=32).view(np.uint8).reshape(B, -1).copy()).to(dev) for fl in clamp_flags]
+    x = torch.empty((B, 4096, 24), dtype=torch.bfloat16, device=dev)
+    n_pool = len(dev_pool)
+
+    def step(k):
+        tf.run(*dev_pool[k], None, plans_dev=pdev[k], out=x)
+        return eng.forward(x)
+    with torch.no_grad():
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for k in range(2):
+                logits = step(k)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        eng.launches = 0
+        step(0)
+        launches = eng.launches + 2
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for k in range(n_pool):
+                step(k)
+        n = max(args.steps // 2, 5)
+        ms = timed_loop(lambda i: g.replay(), n, 3) / (n * n_pool)
+    fl = 2 * 4096 * 24 * 96 + 2 * 768 * 1000            # algorithmic forward FLOPs per image: contractions + attention MACs x 2
+    for s_, depth in enumerate((2, 2, 6, 2)):
+        T, Cd = 4096 // 4 ** s_, 96 * 2 ** s_
+        fl += depth * (24 * T * Cd * Cd + 256 * T * Cd) + (4 * T * Cd * Cd if s_ < 3 else 0)
+    return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_batch": ms, "batch": B, "gflop_per_image_fwd": fl / 1e9,
+            "achieved_tflops": fl * B / ms / 1e9, "gpu_launches_per_batch": launches, "logits_finite": bool(torch.isfinite(logits).all()),
+            "what": "SwinV2-T DCT (window 8, 256 px) eval forward: K0 in the Swin layout (Resize_DCT(32)) + SwinTransformerV2 forward, "
+                    "no gradients, coefficients resident in HBM, CUDA-graph replay"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -528,6 +588,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly (for ncu launch lists)")
     ap.add_argument("--cpu-sample", type=int, default=32, help="images per CPU step of the reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-swin", action="store_true", help="skip the SwinV2-T eval-forward side measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.stage == "auto":

@@ -169,7 +169,8 @@ enum rgbnm_epilogue {
     RGBNM_EPI_DGELU = 3,        /* C = acc * gelu_erf'(aux)                  backward of the above */
     RGBNM_EPI_POSEMB = 4,       /* C = acc + bias + posemb[row % period]     plainvit.py:194-198, 97-121 */
     RGBNM_EPI_WGRAD_ATOMIC = 5, /* out_f32 += alpha * acc                    fp32 red.add */
-    RGBNM_EPI_F32 = 6           /* out_f32 = acc + bias                      fp32 (logits) */
+    RGBNM_EPI_F32 = 6,          /* out_f32 = acc + bias                      fp32 (logits) */
+    RGBNM_EPI_GELU_ACT = 7      /* C = gelu_erf(acc + bias)                  inference: the pre-activation is not kept (swinv2.py:30-31) */
 };
 
 typedef struct {

@@ -37,7 +37,8 @@ constexpr int FIRST_EPI_WARP = 3;
 constexpr int THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> rank 0's copy
 
-enum Epi : int { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_GELU = 2, EPI_DGELU = 3, EPI_POSEMB = 4, EPI_ATOMIC = 5, EPI_F32 = 6 };
+enum Epi : int { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_GELU = 2, EPI_DGELU = 3, EPI_POSEMB = 4, EPI_ATOMIC = 5, EPI_F32 = 6,
+                 EPI_GELU_ACT = 7 };
 
 struct Params {
     int M, N;
@@ -454,6 +455,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                 else { x[2 * e] *= dgelu_fast(lo); x[2 * e + 1] *= dgelu_fast(hi); }
                             }
                         }
+                        if (EPI == EPI_GELU_ACT) {             // inference: only the activation is stored
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) x[e] = gelu_fast(x[e]);
+                        }
                         *cell = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
                         if (EPI == EPI_GELU) {
                             uint4* cell2 = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(cell) + L::SUB_BYTES);
@@ -573,6 +578,9 @@ extern "C" int rgbnm_gemm_bf16(const rgbnm_gemm_args* args, void* stream) {
         case RGBNM_EPI_GELU:
             if (!a.C || !a.C2 || (a.ldc % 8)) return RGBNM_ERR_ARG;
             return wide ? launch<256, 4, EPI_GELU, false, false>(a, st) : launch<192, 4, EPI_GELU, false, false>(a, st);
+        case RGBNM_EPI_GELU_ACT:
+            if (!a.C || (a.ldc % 8)) return RGBNM_ERR_ARG;
+            return wide ? launch<256, 4, EPI_GELU_ACT, false, false>(a, st) : launch<192, 5, EPI_GELU_ACT, false, false>(a, st);
         case RGBNM_EPI_DGELU:
             if (!a.C || !a.aux || (a.ldc % 8) || (a.ldaux % 8)) return RGBNM_ERR_ARG;
             return wide ? launch<256, 4, EPI_DGELU, false, false>(a, st) : launch<192, 5, EPI_DGELU, false, false>(a, st);

@@ -44,16 +44,30 @@ ln_res_fwd_kernel(const unsigned* __restrict__ x, const float* __restrict__ gamm
     const int lane = threadIdx.x & 31;
     const int pairs = E >> 1;
     const float inv_e = 1.0f / float(E);
-    for (int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5); row < rows; row += gridDim.x * LN_WARPS) {
-        const unsigned* xr = x + size_t(row) * pairs;
-        float2 v[MAXP];
-        float s = 0.0f;
+    const int stride = gridDim.x * LN_WARPS;
+    int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+    // software pipeline over rows: the next row's x / residual loads are in flight during this row's two reductions
+    unsigned nx[MAXP], nr[MAXP];
+    auto fetch = [&](int r) {
 #pragma unroll
         for (int k = 0; k < MAXP; ++k) {
             const int p = k * 32 + lane;
-            v[k] = p < pairs ? bf2_to_f2(__ldg(xr + p)) : make_float2(0.0f, 0.0f);
+            nx[k] = p < pairs ? __ldg(x + size_t(r) * pairs + p) : 0u;
+            nr[k] = (res != nullptr && p < pairs) ? __ldg(res + size_t(r) * pairs + p) : 0u;
+        }
+    };
+    if (row < rows) fetch(row);
+    for (; row < rows; row += stride) {
+        float2 v[MAXP];
+        unsigned cr[MAXP];
+        float s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < MAXP; ++k) {
+            v[k] = bf2_to_f2(nx[k]);
+            cr[k] = nr[k];
             s += v[k].x + v[k].y;
         }
+        if (row + stride < rows) fetch(row + stride);
         const float mean = warp_sum(s) * inv_e;
         float q = 0.0f;
 #pragma unroll
@@ -70,13 +84,9 @@ ln_res_fwd_kernel(const unsigned* __restrict__ x, const float* __restrict__ gamm
             if (p < pairs) {
                 const float2 g = *reinterpret_cast<const float2*>(gamma + 2 * p);
                 const float2 b = *reinterpret_cast<const float2*>(beta + 2 * p);
-                float o0 = (v[k].x - mean) * rstd * g.x + b.x;
-                float o1 = (v[k].y - mean) * rstd * g.y + b.y;
-                if (res != nullptr) {
-                    const float2 r = bf2_to_f2(__ldg(res + size_t(row) * pairs + p));
-                    o0 += r.x;
-                    o1 += r.y;
-                }
+                const float2 r = bf2_to_f2(cr[k]);
+                const float o0 = (v[k].x - mean) * rstd * g.x + b.x + r.x;
+                const float o1 = (v[k].y - mean) * rstd * g.y + b.y + r.y;
                 y[size_t(row) * pairs + p] = f2_to_bf2(o0, o1);
             }
         }
@@ -238,6 +248,43 @@ __device__ __forceinline__ float quad_max(float v) {
     return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
 }
 
+// image token of in-window position j of window `win` (cyclic shift folded in: torch.roll by -shift, swinv2.py:283-286)
+__device__ __forceinline__ int window_token(int win, int j, int H, int W, int wpr, int wpi, int shift) {
+    const int img = win / wpi, wrem = win - img * wpi;
+    const int wy = wrem / wpr, wx = wrem - wy * wpr;
+    int py = wy * WS + (j >> 3) + shift, px = wx * WS + (j & 7) + shift;
+    if (py >= H) py -= H;
+    if (px >= W) px -= W;
+    return (img * H + py) * W + px;
+}
+
+struct WinLoad {          // one thread's share of a window's operands, in flight one window ahead of the arithmetic
+    uint4 k0, k1, v0, v1;
+    unsigned qa[2][4];
+    int tok0, tok1;
+};
+
+__device__ __forceinline__ void window_fetch(WinLoad& L, const __nv_bfloat16* __restrict__ qkv, int win, int head, int C, int H, int W,
+                                             int wpr, int wpi, int shift, int tid, int R0, int t) {
+    const int r = tid >> 1, half = tid & 1;
+    const __nv_bfloat16* row = qkv + size_t(window_token(win, r, H, W, wpr, wpi, shift)) * (3 * size_t(C)) + head * HD + half * 16;
+    L.k0 = __ldg(reinterpret_cast<const uint4*>(row + C));
+    L.k1 = __ldg(reinterpret_cast<const uint4*>(row + C) + 1);
+    L.v0 = __ldg(reinterpret_cast<const uint4*>(row + 2 * C));
+    L.v1 = __ldg(reinterpret_cast<const uint4*>(row + 2 * C) + 1);
+    L.tok0 = window_token(win, R0, H, W, wpr, wpi, shift);
+    L.tok1 = window_token(win, R0 + 8, H, W, wpr, wpi, shift);
+    const unsigned* p0 = reinterpret_cast<const unsigned*>(qkv + size_t(L.tok0) * (3 * size_t(C)) + head * HD);
+    const unsigned* p1 = reinterpret_cast<const unsigned*>(qkv + size_t(L.tok1) * (3 * size_t(C)) + head * HD);
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        L.qa[ks][0] = __ldg(p0 + ks * 8 + t);
+        L.qa[ks][1] = __ldg(p1 + ks * 8 + t);
+        L.qa[ks][2] = __ldg(p0 + ks * 8 + 4 + t);
+        L.qa[ks][3] = __ldg(p1 + ks * 8 + 4 + t);
+    }
+}
+
 __global__ void __launch_bounds__(128)
 window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, const float* __restrict__ bias,
                        const float* __restrict__ scale, int H, int W, int C, int shift, int n_windows) {
@@ -245,8 +292,6 @@ window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
     __shared__ __align__(16) __nv_bfloat16 Vt[HD * VT_LD];
     __shared__ __align__(16) float Bs[WT * BS_LD];
     __shared__ float rk[WT];
-    __shared__ int region[WT];
-    __shared__ int toks[WT];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int head = blockIdx.y;
     for (int e = tid; e < WT * (WT / 4); e += 128) {
@@ -255,41 +300,25 @@ window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
     }
     const float sc = __ldg(scale + head);
     const int wpr = W / WS, wpi = (H / WS) * wpr;
-    const int R0 = warp * 16 + g, R1 = R0 + 8;
+    const int R0 = warp * 16 + g, R1 = R0 + 8;             // in-window rows (2 * warp, g) and (2 * warp + 1, g)
 
-    for (int win = blockIdx.x; win < n_windows; win += gridDim.x) {
+    WinLoad nxt;
+    int win = blockIdx.x;
+    if (win < n_windows) window_fetch(nxt, qkv, win, head, C, H, W, wpr, wpi, shift, tid, R0, t);
+    for (; win < n_windows; win += gridDim.x) {
+        const WinLoad cur = nxt;
         __syncthreads();                       // the previous window's shared-memory reads are done (first pass: bias staged)
-        if (tid < WT) {
-            const int img = win / wpi, wrem = win - img * wpi;
-            const int wy = wrem / wpr, wx = wrem - wy * wpr;
-            const int sy = wy * WS + (tid >> 3), sx = wx * WS + (tid & 7);
-            int py = sy + shift, px = sx + shift;
-            if (py >= H) py -= H;
-            if (px >= W) px -= W;
-            toks[tid] = (img * H + py) * W + px;
-            int reg = 0;
-            if (shift > 0) {
-                const int hr = sy < H - WS ? 0 : (sy < H - shift ? 1 : 2);
-                const int wr = sx < W - WS ? 0 : (sx < W - shift ? 1 : 2);
-                reg = 3 * hr + wr;
-            }
-            region[tid] = reg;
-        }
-        __syncthreads();
         // ---- K, V of the window -> shared memory (K row-major, V transposed); thread = (row, 16-dim half) ----
         {
             const int r = tid >> 1, half = tid & 1;
-            const __nv_bfloat16* row = qkv + size_t(toks[r]) * (3 * size_t(C)) + head * HD + half * 16;
-            const uint4 k0 = __ldg(reinterpret_cast<const uint4*>(row + C)), k1 = __ldg(reinterpret_cast<const uint4*>(row + C) + 1);
-            const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(row + 2 * C)), v1 = __ldg(reinterpret_cast<const uint4*>(row + 2 * C) + 1);
             uint4* kd = reinterpret_cast<uint4*>(Ks + r * KS_LD + half * 16);
-            kd[0] = k0;
-            kd[1] = k1;
-            float n = sumsq_bf2(k0.x) + sumsq_bf2(k0.y) + sumsq_bf2(k0.z) + sumsq_bf2(k0.w) + sumsq_bf2(k1.x) + sumsq_bf2(k1.y) +
-                      sumsq_bf2(k1.z) + sumsq_bf2(k1.w);
+            kd[0] = cur.k0;
+            kd[1] = cur.k1;
+            float n = sumsq_bf2(cur.k0.x) + sumsq_bf2(cur.k0.y) + sumsq_bf2(cur.k0.z) + sumsq_bf2(cur.k0.w) + sumsq_bf2(cur.k1.x) +
+                      sumsq_bf2(cur.k1.y) + sumsq_bf2(cur.k1.z) + sumsq_bf2(cur.k1.w);
             n += __shfl_xor_sync(0xffffffffu, n, 1);
             if (half == 0) rk[r] = 1.0f / fmaxf(sqrtf(n), 1e-12f);
-            const unsigned vw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            const unsigned vw[8] = {cur.v0.x, cur.v0.y, cur.v0.z, cur.v0.w, cur.v1.x, cur.v1.y, cur.v1.z, cur.v1.w};
             unsigned short* vt = reinterpret_cast<unsigned short*>(Vt);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -297,22 +326,10 @@ window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
                 vt[(half * 16 + 2 * e + 1) * VT_LD + r] = static_cast<unsigned short>(vw[e] >> 16);
             }
         }
-        // ---- Q fragments of this warp's 16 rows, straight from global ----
-        unsigned qa[2][4];
-        const int tok0 = toks[R0], tok1 = toks[R1];
-        {
-            const unsigned* p0 = reinterpret_cast<const unsigned*>(qkv + size_t(tok0) * (3 * size_t(C)) + head * HD);
-            const unsigned* p1 = reinterpret_cast<const unsigned*>(qkv + size_t(tok1) * (3 * size_t(C)) + head * HD);
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                qa[ks][0] = __ldg(p0 + ks * 8 + t);
-                qa[ks][1] = __ldg(p1 + ks * 8 + t);
-                qa[ks][2] = __ldg(p0 + ks * 8 + 4 + t);
-                qa[ks][3] = __ldg(p1 + ks * 8 + 4 + t);
-            }
-        }
-        const float n0 = quad_sum(sumsq_bf2(qa[0][0]) + sumsq_bf2(qa[0][2]) + sumsq_bf2(qa[1][0]) + sumsq_bf2(qa[1][2]));
-        const float n1 = quad_sum(sumsq_bf2(qa[0][1]) + sumsq_bf2(qa[0][3]) + sumsq_bf2(qa[1][1]) + sumsq_bf2(qa[1][3]));
+        // the next window's operands start their trip now and land during this window's arithmetic
+        if (win + int(gridDim.x) < n_windows) window_fetch(nxt, qkv, win + gridDim.x, head, C, H, W, wpr, wpi, shift, tid, R0, t);
+        const float n0 = quad_sum(sumsq_bf2(cur.qa[0][0]) + sumsq_bf2(cur.qa[0][2]) + sumsq_bf2(cur.qa[1][0]) + sumsq_bf2(cur.qa[1][2]));
+        const float n1 = quad_sum(sumsq_bf2(cur.qa[0][1]) + sumsq_bf2(cur.qa[0][3]) + sumsq_bf2(cur.qa[1][1]) + sumsq_bf2(cur.qa[1][3]));
         const float f0 = sc / fmaxf(sqrtf(n0), 1e-12f), f1 = sc / fmaxf(sqrtf(n1), 1e-12f);
         __syncthreads();
 
@@ -325,15 +342,22 @@ window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 const int w = (nt * 8 + g) * (KS_LD / 2) + ks * 8 + t;
-                mma16816(s[nt], qa[ks], ksw[w], ksw[w + 4]);
+                mma16816(s[nt], cur.qa[ks], ksw[w], ksw[w + 4]);
             }
         }
         // ---- cosine normalisation, logit scale, relative position bias, shift mask; row maxima ----
-        const int reg0 = region[R0], reg1 = region[R1];
+        // shift regions (img_mask of swinv2.py:227-238, in shifted coordinates): only the last window row / column is
+        // split, at in-window coordinate 8 - shift: region = 3 * hr + wr with hr, wr in {0 | 1, 2}
+        const int wrem = win % wpi;
+        const bool last_y = shift > 0 && (wrem / wpr) == (H / WS) - 1, last_x = shift > 0 && (wrem % wpr) == wpr - 1;
+        const int cut = WS - shift;
+        const int hr0 = last_y ? (2 * warp < cut ? 1 : 2) : 0, hr1 = last_y ? (2 * warp + 1 < cut ? 1 : 2) : 0;
+        const int wrr = last_x ? (g < cut ? 1 : 2) : 0;                          // both rows of this thread sit at column g
+        const int wc0 = last_x ? (2 * t < cut ? 1 : 2) : 0, wc1 = last_x ? (2 * t + 1 < cut ? 1 : 2) : 0;
         float m0 = -3.0e38f, m1 = -3.0e38f;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            const int col = nt * 8 + 2 * t;
+            const int col = nt * 8 + 2 * t;                                      // key at in-window (nt, 2t) and (nt, 2t + 1)
             const float rk0 = rk[col], rk1 = rk[col + 1];
             const float2 b0 = *reinterpret_cast<const float2*>(Bs + R0 * BS_LD + col);
             const float2 b1 = *reinterpret_cast<const float2*>(Bs + R1 * BS_LD + col);
@@ -341,12 +365,12 @@ window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
             s[nt][1] = fmaf(s[nt][1] * rk1, f0, b0.y);
             s[nt][2] = fmaf(s[nt][2] * rk0, f1, b1.x);
             s[nt][3] = fmaf(s[nt][3] * rk1, f1, b1.y);
-            if (shift > 0) {
-                const int c0 = region[col], c1 = region[col + 1];
-                if (c0 != reg0) s[nt][0] += -100.0f;
-                if (c1 != reg0) s[nt][1] += -100.0f;
-                if (c0 != reg1) s[nt][2] += -100.0f;
-                if (c1 != reg1) s[nt][3] += -100.0f;
+            if (last_y || last_x) {
+                const int hc = last_y ? (nt < cut ? 1 : 2) : 0;
+                if (hc != hr0 || wc0 != wrr) s[nt][0] += -100.0f;                // attn_mask value of swinv2.py:242
+                if (hc != hr0 || wc1 != wrr) s[nt][1] += -100.0f;
+                if (hc != hr1 || wc0 != wrr) s[nt][2] += -100.0f;
+                if (hc != hr1 || wc1 != wrr) s[nt][3] += -100.0f;
             }
             m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
             m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
@@ -381,8 +405,8 @@ window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
             }
         }
         const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-        unsigned* d0 = reinterpret_cast<unsigned*>(out + size_t(tok0) * C + head * HD);
-        unsigned* d1 = reinterpret_cast<unsigned*>(out + size_t(tok1) * C + head * HD);
+        unsigned* d0 = reinterpret_cast<unsigned*>(out + size_t(cur.tok0) * C + head * HD);
+        unsigned* d1 = reinterpret_cast<unsigned*>(out + size_t(cur.tok1) * C + head * HD);
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
             d0[nt * 4 + t] = f2_to_bf2(o[nt][0] * i0, o[nt][1] * i0);
@@ -471,8 +495,14 @@ extern "C" int rgbnm_window_attention_fwd(const void* qkv, void* out, const floa
         window_attn_fwd_kernel<<<grid, WT, 0, static_cast<cudaStream_t>(stream)>>>(
             static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), bias, scale, H, W, C, shift);
     } else {
-        // a CTA keeps its head's bias tile in shared memory and walks windows: enough CTAs for ~8 per SM, at least 2 windows each
-        int ctas = (rgbnm_num_sms() * 8 + heads - 1) / heads;
+        // a CTA keeps its head's bias tile in shared memory and walks windows: exactly one resident wave of CTAs
+        static int occ = 0;
+        if (occ == 0) {
+            RGBNM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, window_attn_mma_kernel, 128, 0));
+            if (occ < 1) occ = 1;
+        }
+        int ctas = rgbnm_num_sms() * occ / heads;
+        if (ctas < 1) ctas = 1;
         if (ctas > n_windows) ctas = n_windows;
         const dim3 grid(ctas, heads);
         window_attn_mma_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(

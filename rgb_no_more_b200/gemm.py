@@ -11,7 +11,7 @@ import torch
 
 from . import lib as _lib
 
-EPI_STORE, EPI_RESIDUAL, EPI_GELU, EPI_DGELU, EPI_POSEMB, EPI_WGRAD_ATOMIC, EPI_F32 = range(7)
+EPI_STORE, EPI_RESIDUAL, EPI_GELU, EPI_DGELU, EPI_POSEMB, EPI_WGRAD_ATOMIC, EPI_F32, EPI_GELU_ACT = range(8)
 
 
 class GemmArgs(C.Structure):

@@ -164,7 +164,7 @@ class SwinEngine:
         bufs = {"stages": []}
         for st in self.stages:
             T, Cd = B * st["res"] ** 2, st["dim"]
-            d = dict(xa=bf(T, Cd), xb=bf(T, Cd), qkv=bf(T, 3 * Cd), att=bf(T, Cd), tmp=bf(T, Cd), u=bf(T, 4 * Cd), f=bf(T, 4 * Cd))
+            d = dict(xa=bf(T, Cd), xb=bf(T, Cd), qkv=bf(T, 3 * Cd), att=bf(T, Cd), tmp=bf(T, Cd), f=bf(T, 4 * Cd))
             if st["down"] is not None:
                 d["gath"] = bf(T // 4, 4 * Cd)
                 d["red"] = bf(T // 4, 2 * Cd)
@@ -216,7 +216,7 @@ class SwinEngine:
                 self._attn(b["qkv"], b["att"], blk, B, H, Cd)
                 self._gemm(b["att"], blk["proj"], G.EPI_STORE, bias=blk["proj_b"], out=b["tmp"])
                 x1 = self._ln(b["tmp"], blk["n1"], x, other)                       # x + norm1(attn(x))
-                self._gemm(x1, blk["fc1"], G.EPI_GELU, bias=blk["fc1_b"], out=b["u"], out2=b["f"])
+                self._gemm(x1, blk["fc1"], G.EPI_GELU_ACT, bias=blk["fc1_b"], out=b["f"])       # only gelu(fc1) is kept (inference)
                 self._gemm(b["f"], blk["fc2"], G.EPI_STORE, bias=blk["fc2_b"], out=b["tmp"])
                 x = self._ln(b["tmp"], blk["n2"], x1, x)                           # x1 + norm2(mlp(x1)); rows are independent
                 if collect is not None:

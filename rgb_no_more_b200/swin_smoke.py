@@ -28,7 +28,7 @@ def run() -> None:
         for p in m.parameters():
             if p.ndim == 1:
                 p.add_(0.2 * torch.randn_like(p))          # the reference zero-initialises the block post-norms
-    sd = {k: v.detach().float().cpu().clone() for k, v in m.state_dict().items()}
+    sd = {k: (v.detach().float() if v.is_floating_point() else v.detach()).cpu().clone() for k, v in m.state_dict().items()}
     m.eval().to(dev)
     with torch.no_grad():
         logits = m(emb.to(torch.bfloat16)).float().cpu()

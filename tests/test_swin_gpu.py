@@ -156,3 +156,16 @@ def test_swin_end_to_end_from_jpeg_coefficients():
     rng = float(ref.max() - ref.min())
     assert float((logits - ref).abs().max()) < 3e-2 * rng
     assert torch.equal(logits.argmax(1), ref.argmax(1))
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 384, 96), (2048, 1536, 384), (300, 768, 192)])
+def test_gemm_gelu_act_epilogue(M, N, K):
+    """RGBNM_EPI_GELU_ACT (inference: only gelu(acc + bias) is stored) against torch's exact-erf GELU."""
+    from rgb_no_more_b200 import gemm as G
+    g = torch.Generator().manual_seed(M + N)
+    a = (torch.randn(M, K, generator=g) * 0.7).bfloat16().to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().to(DEV)
+    bias = (torch.randn(N, generator=g) * 0.2).to(DEV)
+    got = G.gemm(a, w, G.EPI_GELU_ACT, bias=bias).float()
+    ref = F.gelu(a.float() @ w.float().T + bias)
+    assert float((got - ref).abs().max()) < 1e-2 * max(1.0, float(ref.abs().max()))
