@@ -170,7 +170,9 @@ enum rgbnm_epilogue {
     RGBNM_EPI_POSEMB = 4,       /* C = acc + bias + posemb[row % period]     plainvit.py:194-198, 97-121 */
     RGBNM_EPI_WGRAD_ATOMIC = 5, /* out_f32 += alpha * acc                    fp32 red.add */
     RGBNM_EPI_F32 = 6,          /* out_f32 = acc + bias                      fp32 (logits) */
-    RGBNM_EPI_GELU_ACT = 7      /* C = gelu_erf(acc + bias)                  inference: the pre-activation is not kept (swinv2.py:30-31) */
+    RGBNM_EPI_GELU_ACT = 7,     /* C = gelu_erf(acc + bias)                  inference: the pre-activation is not kept (swinv2.py:30-31) */
+    RGBNM_EPI_LNRES = 8         /* C = aux + LayerNorm_N(acc + bias) * ln_gamma + ln_beta   post-norm residual, swinv2.py:302-306;
+                                   N <= 384, N % 32 == 0 (the row statistics are taken inside one output tile) */
 };
 
 typedef struct {
@@ -186,6 +188,9 @@ typedef struct {
     int trans_out;              /* WGRAD_ATOMIC: out_f32[n * ldo + m] += ... (lets the caller put the longer side on M) */
     int perm_heads;             /* WGRAD_ATOMIC: > 0: the M index is in the kernel's qkv order (q|k|v head-major, rgbnm_weight_prep); */
     int perm_head_dim;          /*   results are added at the reference row h*3D + d*3 + which ("(h d qkv)", plainvit.py:447) */
+    const float* ln_gamma;      /* LNRES: fp32 [N], 16-byte aligned */
+    const float* ln_beta;
+    float ln_eps;
 } rgbnm_gemm_args;
 
 int rgbnm_gemm_bf16(const rgbnm_gemm_args* args, void* stream);

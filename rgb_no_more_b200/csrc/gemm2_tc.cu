@@ -38,7 +38,7 @@ constexpr int THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> rank 0's copy
 
 enum Epi : int { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_GELU = 2, EPI_DGELU = 3, EPI_POSEMB = 4, EPI_ATOMIC = 5, EPI_F32 = 6,
-                 EPI_GELU_ACT = 7 };
+                 EPI_GELU_ACT = 7, EPI_LNRES = 8 };
 
 struct Params {
     int M, N;
@@ -54,7 +54,14 @@ struct Params {
     int trans_out;            // atomic epilogue: out[n * ldo + m] instead of out[m * ldo + n]
     int vec_ok;               // atomic epilogue: 16-byte aligned rows -> red.global.add.v4.f32
     int perm_heads, perm_hd;  // atomic epilogue: M index is in kernel qkv order (q|k|v head-major) -> reference row h*3D + d*3 + which
+    const float* ln_gamma;    // EPI_LNRES: C = aux + LayerNorm(acc + bias) * gamma + beta over the N columns of a row
+    const float* ln_beta;
+    float ln_eps;
 };
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
 // ---- PTX pieces that only the CTA-pair kernel needs ------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -135,7 +142,7 @@ __device__ __forceinline__ float dgelu_fast(float x) {
 template <int BN, int STAGES, int EPI, bool B_MN>
 struct Cfg {
     static constexpr bool STAGED = (EPI != EPI_ATOMIC && EPI != EPI_F32);
-    static constexpr bool HAS_AUX = (EPI == EPI_RESIDUAL || EPI == EPI_DGELU);
+    static constexpr bool HAS_AUX = (EPI == EPI_RESIDUAL || EPI == EPI_DGELU || EPI == EPI_LNRES);
     static constexpr int NOUT = EPI == EPI_GELU ? 2 : (STAGED ? 1 : 0);
     static constexpr int NSUB = BN / 64;                        // 64-column sub-tiles of the CTA's 128 x BN output
     static constexpr int NBUF = !STAGED ? 0 : (NOUT == 2 ? 3 : 4);
@@ -147,7 +154,9 @@ struct Cfg {
     static constexpr int OFF_BAR = OFF_STG + NBUF * SLOT_BYTES;
     static constexpr int NBARS = 2 * STAGES + 4 + 2 * (NBUF > 0 ? NBUF : 1);
     static constexpr int OFF_TMEM = OFF_BAR + NBARS * 8;
-    static constexpr int TOTAL = OFF_TMEM + 16 + 1024;
+    static constexpr int OFF_LN = OFF_TMEM + 16;                // EPI_LNRES: row-statistics exchange between the two column halves
+    static constexpr int LN_BYTES = EPI == EPI_LNRES ? 2 * 8 * 32 * 4 : 0;
+    static constexpr int TOTAL = OFF_LN + LN_BYTES + 1024;
     static constexpr int NACC = 2 * BN <= 512 ? 2 : 1;          // TMEM accumulator buffers (BN = 384: one, the epilogue is not overlapped)
     static_assert(BN % 64 == 0 && BN <= 512 && (BN / 2) % 8 == 0, "tile shape");
     static_assert(BN <= 256 || BN == 384, "BN = 384: two UMMAs per step (N = 256 + 128)");
@@ -365,6 +374,42 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const int n0 = n_blk * BN, m0 = m_blk * BM + int(rank) * BM_CTA;
             mbar_wait(tfull + acc, (L::NACC == 2 ? (it >> 1) : it) & 1);
             tc_fence_after();
+            // EPI_LNRES (post-norm residual, models/swinv2.py:302-306): the whole row (N <= BN columns) sits in this CTA's
+            // accumulator, thread = row; its columns are split between this warp and the warp of the other column half.
+            // Two extra passes over TMEM give the row mean and the centred second moment (exchanged through shared memory).
+            float ln_mean = 0.0f, ln_rstd = 1.0f;
+            if (EPI == EPI_LNRES) {
+                float* sc1 = reinterpret_cast<float*>(smem + L::OFF_LN);
+                float* sc2 = sc1 + 8 * 32;
+                const float inv_n = 1.0f / float(p.N);
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    float part = 0.0f;
+#pragma unroll 1
+                    for (int s = 0; s < NSUB; ++s) {
+                        const int c = 2 * s + half;
+                        const int col0 = n0 + c * 32;
+                        if (col0 + 32 <= p.N) {                         // warp-uniform
+                            uint32_t r[32];
+                            tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + c * 32, r);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float x = __uint_as_float(r[j]);
+                                if (p.bias != nullptr) x += __ldg(p.bias + col0 + j);
+                                const float d = x - ln_mean;            // pass 0: ln_mean == 0
+                                part += pass == 0 ? x : d * d;
+                            }
+                        }
+                    }
+                    float* sc = pass == 0 ? sc1 : sc2;
+                    sc[ew * 32 + lane] = part;
+                    named_bar_sync(1 + quad, 64);                       // the two warps of this TMEM lane quadrant
+                    const float total = part + sc[(ew ^ 4) * 32 + lane];
+                    if (pass == 0) ln_mean = total * inv_n;
+                    else ln_rstd = rsqrtf(total * inv_n + p.ln_eps);
+                }
+            }
 #pragma unroll 1
             for (int s = 0; s < NSUB; ++s, ++g) {
                 const int c = 2 * s + half;              // 32-column chunk of the tile
@@ -396,6 +441,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     } else if (p.bias != nullptr) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+                    }
+                }
+                if (EPI == EPI_LNRES && col0 + 32 <= p.N) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col0 + j));
+                        const float4 e4 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col0 + j));
+                        v[j] = fmaf((v[j] - ln_mean) * ln_rstd, g4.x, e4.x);
+                        v[j + 1] = fmaf((v[j + 1] - ln_mean) * ln_rstd, g4.y, e4.y);
+                        v[j + 2] = fmaf((v[j + 2] - ln_mean) * ln_rstd, g4.z, e4.z);
+                        v[j + 3] = fmaf((v[j + 3] - ln_mean) * ln_rstd, g4.w, e4.w);
                     }
                 }
                 if (EPI == EPI_POSEMB && col0 + 32 <= p.N) {
@@ -451,7 +507,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const float lo = __uint_as_float(aw[e] << 16), hi = __uint_as_float(aw[e] & 0xffff0000u);
-                                if (EPI == EPI_RESIDUAL) { x[2 * e] += lo; x[2 * e + 1] += hi; }
+                                if (EPI == EPI_RESIDUAL || EPI == EPI_LNRES) { x[2 * e] += lo; x[2 * e + 1] += hi; }
                                 else { x[2 * e] *= dgelu_fast(lo); x[2 * e + 1] *= dgelu_fast(hi); }
                             }
                         }
@@ -541,6 +597,7 @@ static int launch(const rgbnm_gemm_args& a, cudaStream_t st) {
     p.out_f32 = a.out_f32; p.ldo = a.ldo; p.alpha = a.alpha;
     p.trans_out = a.trans_out;
     p.perm_heads = a.perm_heads; p.perm_hd = a.perm_head_dim;
+    p.ln_gamma = a.ln_gamma; p.ln_beta = a.ln_beta; p.ln_eps = a.ln_eps;
     if (a.perm_heads > 0 && (a.perm_head_dim <= 0 || a.M != 3 * a.perm_heads * a.perm_head_dim)) return RGBNM_ERR_ARG;
     p.vec_ok = (!a.trans_out && (reinterpret_cast<uintptr_t>(a.out_f32) % 16 == 0) && (a.ldo % 4 == 0) && (a.N % 4 == 0)) ? 1 : 0;
     const int tiles = p.m_tiles * p.n_tiles * p.splits;
@@ -578,6 +635,12 @@ extern "C" int rgbnm_gemm_bf16(const rgbnm_gemm_args* args, void* stream) {
         case RGBNM_EPI_GELU:
             if (!a.C || !a.C2 || (a.ldc % 8)) return RGBNM_ERR_ARG;
             return wide ? launch<256, 4, EPI_GELU, false, false>(a, st) : launch<192, 4, EPI_GELU, false, false>(a, st);
+        case RGBNM_EPI_LNRES:
+            // the whole row must sit in one tile: N <= 384, whole 32-column chunks; gamma / beta read as float4
+            if (!a.C || !a.aux || !a.ln_gamma || !a.ln_beta || (a.ldc % 8) || (a.ldaux % 8) || (a.N % 32) || a.N > 384 ||
+                (reinterpret_cast<uintptr_t>(a.ln_gamma) & 15) || (reinterpret_cast<uintptr_t>(a.ln_beta) & 15))
+                return RGBNM_ERR_ARG;
+            return a.N > 192 ? launch<384, 3, EPI_LNRES, false, false>(a, st) : launch<192, 5, EPI_LNRES, false, false>(a, st);
         case RGBNM_EPI_GELU_ACT:
             if (!a.C || (a.ldc % 8)) return RGBNM_ERR_ARG;
             return wide ? launch<256, 4, EPI_GELU_ACT, false, false>(a, st) : launch<192, 5, EPI_GELU_ACT, false, false>(a, st);

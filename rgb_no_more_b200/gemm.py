@@ -11,7 +11,7 @@ import torch
 
 from . import lib as _lib
 
-EPI_STORE, EPI_RESIDUAL, EPI_GELU, EPI_DGELU, EPI_POSEMB, EPI_WGRAD_ATOMIC, EPI_F32, EPI_GELU_ACT = range(8)
+EPI_STORE, EPI_RESIDUAL, EPI_GELU, EPI_DGELU, EPI_POSEMB, EPI_WGRAD_ATOMIC, EPI_F32, EPI_GELU_ACT, EPI_LNRES = range(9)
 
 
 class GemmArgs(C.Structure):
@@ -20,7 +20,8 @@ class GemmArgs(C.Structure):
                 ("lda", C.c_longlong), ("ldb", C.c_longlong), ("ldc", C.c_longlong), ("ldaux", C.c_longlong),
                 ("ldo", C.c_longlong), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("epilogue", C.c_int),
                 ("pos_period", C.c_int), ("splits", C.c_int), ("alpha", C.c_float), ("trans_out", C.c_int),
-                ("perm_heads", C.c_int), ("perm_head_dim", C.c_int)]
+                ("perm_heads", C.c_int), ("perm_head_dim", C.c_int),
+                ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float)]
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -35,7 +36,8 @@ def _check_bf16(t, name):
 def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int = EPI_STORE, bias: Optional[torch.Tensor] = None,
          aux: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
          posemb: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None, splits: int = 0,
-         alpha: float = 1.0, trans_out: bool = False, perm_heads: int = 0, perm_head_dim: int = 0):
+         alpha: float = 1.0, trans_out: bool = False, perm_heads: int = 0, perm_head_dim: int = 0,
+         ln: Optional[tuple] = None, ln_eps: float = 1e-5):
     """Forward / dgrad form: a [M,K], b [N,K] (both row-major, K contiguous) -> out [M,N].
     For EPI_WGRAD_ATOMIC: a [T,M] and b [T,N] (T = reduction/token index) -> out_f32 [M,N] += alpha * a^T b
     (trans_out: out_f32 [N,M] += alpha * b^T a, so the caller can put the longer side on the 256-row tile axis);
@@ -82,9 +84,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int = EPI_STORE, bias: Opti
                 raise ValueError("rgbnm gemm: out and out2 must share the leading dimension")
             args.C2 = out2.data_ptr()
             ret = (out, out2)
-        if epilogue in (EPI_RESIDUAL, EPI_DGELU):
+        if epilogue in (EPI_RESIDUAL, EPI_DGELU, EPI_LNRES):
             _check_bf16(aux, "aux")
             args.aux, args.ldaux = aux.data_ptr(), aux.stride(0)
+        if epilogue == EPI_LNRES:       # out = aux + LayerNorm(a b^T + bias) * gamma + beta; ln = (gamma, beta) fp32 [N]
+            gamma, beta = ln
+            if gamma.dtype != torch.float32 or beta.dtype != torch.float32 or gamma.numel() != N or beta.numel() != N:
+                raise ValueError("rgbnm gemm: ln = (gamma, beta) must be fp32 [N]")
+            args.ln_gamma, args.ln_beta, args.ln_eps = gamma.data_ptr(), beta.data_ptr(), ln_eps
     if bias is not None:
         if bias.dtype != torch.float32 or bias.numel() != N:
             raise ValueError("rgbnm gemm: bias must be fp32 [N]")

@@ -26,6 +26,9 @@ import torch.nn.functional as F
 from . import gemm as G
 from . import lib as _lib
 
+import os
+
+_NOFUSE = os.environ.get("RGBNM_SWIN_NOFUSE") is not None      # A/B: separate LayerNorm kernels instead of the fused GEMM epilogue
 RES = 64          # tokens per side for img_size 256 / patch 4
 IN_FEAT = 24      # 4x4 luma + 2x2 Cb + 2x2 Cr
 
@@ -214,11 +217,17 @@ class SwinEngine:
                 other = b["xb"] if x is b["xa"] else b["xa"]
                 self._gemm(x, blk["qkv"], G.EPI_STORE, bias=blk["qkv_bias"], out=b["qkv"])
                 self._attn(b["qkv"], b["att"], blk, B, H, Cd)
-                self._gemm(b["att"], blk["proj"], G.EPI_STORE, bias=blk["proj_b"], out=b["tmp"])
-                x1 = self._ln(b["tmp"], blk["n1"], x, other)                       # x + norm1(attn(x))
-                self._gemm(x1, blk["fc1"], G.EPI_GELU_ACT, bias=blk["fc1_b"], out=b["f"])       # only gelu(fc1) is kept (inference)
-                self._gemm(b["f"], blk["fc2"], G.EPI_STORE, bias=blk["fc2_b"], out=b["tmp"])
-                x = self._ln(b["tmp"], blk["n2"], x1, x)                           # x1 + norm2(mlp(x1)); rows are independent
+                if Cd <= 384 and not _NOFUSE:
+                    # x + norm1(proj(.)) and x1 + norm2(fc2(.)) inside the GEMM epilogue (RGBNM_EPI_LNRES): the row fits one tile
+                    x1 = self._gemm(b["att"], blk["proj"], G.EPI_LNRES, bias=blk["proj_b"], aux=x, ln=blk["n1"], out=other)
+                    self._gemm(x1, blk["fc1"], G.EPI_GELU_ACT, bias=blk["fc1_b"], out=b["f"])   # only gelu(fc1) is kept (inference)
+                    x = self._gemm(b["f"], blk["fc2"], G.EPI_LNRES, bias=blk["fc2_b"], aux=x1, ln=blk["n2"], out=x)
+                else:
+                    self._gemm(b["att"], blk["proj"], G.EPI_STORE, bias=blk["proj_b"], out=b["tmp"])
+                    x1 = self._ln(b["tmp"], blk["n1"], x, other)                   # x + norm1(attn(x))
+                    self._gemm(x1, blk["fc1"], G.EPI_GELU_ACT, bias=blk["fc1_b"], out=b["f"])
+                    self._gemm(b["f"], blk["fc2"], G.EPI_STORE, bias=blk["fc2_b"], out=b["tmp"])
+                    x = self._ln(b["tmp"], blk["n2"], x1, x)                       # x1 + norm2(mlp(x1)); rows are independent
                 if collect is not None:
                     collect.append((f"l{li}b{bi}", x.view(B, H * H, Cd).float().clone()))
             if st["down"] is not None:

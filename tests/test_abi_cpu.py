@@ -33,8 +33,9 @@ def test_struct_sizes_match_the_header():
     from rgb_no_more_b200 import gemm as G, plan as P
     assert P.PLAN_DTYPE.itemsize == 112                      # rgbnm_plan
     assert C.sizeof(L.WPrepDesc) == 64                       # rgbnm_wprep_desc
-    assert C.sizeof(G.GemmArgs) == 8 * 8 + 5 * 8 + 10 * 4    # rgbnm_gemm_args: 8 pointers, 5 long long, 9 int + 1 float
-    assert L.load().rgbnm_abi_version() == 3
+    # rgbnm_gemm_args: 8 pointers, 5 long long, 9 int + 1 float, then (ABI 4) 2 pointers + 1 float (+ 4 bytes tail padding)
+    assert C.sizeof(G.GemmArgs) == 8 * 8 + 5 * 8 + 10 * 4 + 2 * 8 + 8
+    assert L.load().rgbnm_abi_version() == 4
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

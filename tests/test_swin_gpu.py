@@ -169,3 +169,23 @@ def test_gemm_gelu_act_epilogue(M, N, K):
     got = G.gemm(a, w, G.EPI_GELU_ACT, bias=bias).float()
     ref = F.gelu(a.float() @ w.float().T + bias)
     assert float((got - ref).abs().max()) < 1e-2 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 96, 96), (2048, 192, 768), (1000, 384, 1536), (300, 96, 384), (8192, 384, 384)])
+def test_gemm_lnres_epilogue(M, N, K):
+    """RGBNM_EPI_LNRES: out = aux + LayerNorm(a w^T + bias) * gamma + beta inside the GEMM epilogue (swinv2.py:302-306),
+    incl. N = 96 (half-filled 192-wide tile), ragged M and the 384-wide single-accumulator tile."""
+    from rgb_no_more_b200 import gemm as G
+    g = torch.Generator().manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g) * 0.7).bfloat16().to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().to(DEV)
+    bias = (torch.randn(N, generator=g) * 0.5 + 0.3).to(DEV)
+    aux = torch.randn(M, N, generator=g).bfloat16().to(DEV)
+    gamma = (1 + 0.2 * torch.randn(N, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(N, generator=g)).to(DEV)
+    got = G.gemm(a, w, G.EPI_LNRES, bias=bias, aux=aux, ln=(gamma, beta)).float()
+    ref = aux.float() + F.layer_norm(a.float() @ w.float().T + bias, (N,), gamma, beta, 1e-5)
+    assert float((got - ref).abs().max()) < 1e-2 * max(1.0, float(ref.abs().max()))
+    with pytest.raises(Exception):
+        G.gemm(a, w.repeat(8, 1)[: 768], G.EPI_LNRES, bias=None, aux=aux.repeat(1, 8)[:, :768].contiguous(),
+               ln=(gamma.repeat(8)[:768].contiguous(), beta.repeat(8)[:768].contiguous()))      # N = 768 > one tile
