@@ -171,8 +171,9 @@ enum rgbnm_epilogue {
     RGBNM_EPI_WGRAD_ATOMIC = 5, /* out_f32 += alpha * acc                    fp32 red.add */
     RGBNM_EPI_F32 = 6,          /* out_f32 = acc + bias                      fp32 (logits) */
     RGBNM_EPI_GELU_ACT = 7,     /* C = gelu_erf(acc + bias)                  inference: the pre-activation is not kept (swinv2.py:30-31) */
-    RGBNM_EPI_LNRES = 8         /* C = aux + LayerNorm_N(acc + bias) * ln_gamma + ln_beta   post-norm residual, swinv2.py:302-306;
+    RGBNM_EPI_LNRES = 8,        /* C = aux + LayerNorm_N(acc + bias) * ln_gamma + ln_beta   post-norm residual, swinv2.py:302-306;
                                    N <= 384, N % 32 == 0 (the row statistics are taken inside one output tile) */
+    RGBNM_EPI_LN = 9            /* C = LayerNorm_N(acc + bias) * ln_gamma + ln_beta         patch_embed.norm (swinv2.py:568), PatchMerging.norm (:361) */
 };
 
 typedef struct {

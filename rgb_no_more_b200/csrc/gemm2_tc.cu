@@ -38,7 +38,7 @@ constexpr int THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> rank 0's copy
 
 enum Epi : int { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_GELU = 2, EPI_DGELU = 3, EPI_POSEMB = 4, EPI_ATOMIC = 5, EPI_F32 = 6,
-                 EPI_GELU_ACT = 7, EPI_LNRES = 8 };
+                 EPI_GELU_ACT = 7, EPI_LNRES = 8, EPI_LN = 9 };
 
 struct Params {
     int M, N;
@@ -155,7 +155,7 @@ struct Cfg {
     static constexpr int NBARS = 2 * STAGES + 4 + 2 * (NBUF > 0 ? NBUF : 1);
     static constexpr int OFF_TMEM = OFF_BAR + NBARS * 8;
     static constexpr int OFF_LN = OFF_TMEM + 16;                // EPI_LNRES: row-statistics exchange between the two column halves
-    static constexpr int LN_BYTES = EPI == EPI_LNRES ? 2 * 8 * 32 * 4 : 0;
+    static constexpr int LN_BYTES = (EPI == EPI_LNRES || EPI == EPI_LN) ? 2 * 8 * 32 * 8 : 0;
     static constexpr int TOTAL = OFF_LN + LN_BYTES + 1024;
     static constexpr int NACC = 2 * BN <= 512 ? 2 : 1;          // TMEM accumulator buffers (BN = 384: one, the epilogue is not overlapped)
     static_assert(BN % 64 == 0 && BN <= 512 && (BN / 2) % 8 == 0, "tile shape");
@@ -378,37 +378,55 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             // accumulator, thread = row; its columns are split between this warp and the warp of the other column half.
             // Two extra passes over TMEM give the row mean and the centred second moment (exchanged through shared memory).
             float ln_mean = 0.0f, ln_rstd = 1.0f;
-            if (EPI == EPI_LNRES) {
-                float* sc1 = reinterpret_cast<float*>(smem + L::OFF_LN);
-                float* sc2 = sc1 + 8 * 32;
-                const float inv_n = 1.0f / float(p.N);
+            if (EPI == EPI_LNRES || EPI == EPI_LN) {
+                // one extra pass over TMEM: shifted sums (shift = the first value this thread sees) -> (mean, M2) of this warp's
+                // columns; the two halves are merged with the parallel-variance formula (no E[x^2] - mean^2 cancellation).
+                // Exchange slots are double-buffered by tile parity: a warp may be one tile ahead of its partner.
+                float2* sc = reinterpret_cast<float2*>(smem + L::OFF_LN) + (it & 1) * (8 * 32);
+                float shift = 0.0f, s1 = 0.0f, s2 = 0.0f;
+                int cnt = 0;
 #pragma unroll 1
-                for (int pass = 0; pass < 2; ++pass) {
-                    float part = 0.0f;
-#pragma unroll 1
-                    for (int s = 0; s < NSUB; ++s) {
-                        const int c = 2 * s + half;
-                        const int col0 = n0 + c * 32;
-                        if (col0 + 32 <= p.N) {                         // warp-uniform
-                            uint32_t r[32];
-                            tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + c * 32, r);
-                            tmem_ld_wait();
+                for (int s = 0; s < NSUB; ++s) {
+                    const int c = 2 * s + half;
+                    const int col0 = n0 + c * 32;
+                    if (col0 + 32 <= p.N) {                             // warp-uniform
+                        uint32_t r[32];
+                        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + c * 32, r);
+                        float4 b4[8];
+                        const bool hb = p.bias != nullptr;
+                        if (hb) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                float x = __uint_as_float(r[j]);
-                                if (p.bias != nullptr) x += __ldg(p.bias + col0 + j);
-                                const float d = x - ln_mean;            // pass 0: ln_mean == 0
-                                part += pass == 0 ? x : d * d;
-                            }
+                            for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
                         }
+                        tmem_ld_wait();
+                        float x[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
+                        if (hb) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { x[4 * j] += b4[j].x; x[4 * j + 1] += b4[j].y; x[4 * j + 2] += b4[j].z; x[4 * j + 3] += b4[j].w; }
+                        }
+                        if (cnt == 0) shift = x[0];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float d = x[j] - shift;
+                            s1 += d;
+                            s2 = fmaf(d, d, s2);
+                        }
+                        cnt += 32;
                     }
-                    float* sc = pass == 0 ? sc1 : sc2;
-                    sc[ew * 32 + lane] = part;
-                    named_bar_sync(1 + quad, 64);                       // the two warps of this TMEM lane quadrant
-                    const float total = part + sc[(ew ^ 4) * 32 + lane];
-                    if (pass == 0) ln_mean = total * inv_n;
-                    else ln_rstd = rsqrtf(total * inv_n + p.ln_eps);
                 }
+                const float na = float(cnt);
+                const float mean_a = cnt ? shift + s1 / na : 0.0f;
+                const float m2_a = cnt ? s2 - s1 * s1 / na : 0.0f;
+                sc[ew * 32 + lane] = make_float2(mean_a, m2_a);
+                named_bar_sync(1 + quad, 64);                           // the two warps of this TMEM lane quadrant
+                const float2 o = sc[(ew ^ 4) * 32 + lane];
+                const float n_all = float(p.N), nb = n_all - na;
+                const float delta = o.x - mean_a;
+                ln_mean = (na * mean_a + nb * o.x) / n_all;
+                const float m2 = m2_a + o.y + delta * delta * (na * nb / n_all);
+                ln_rstd = rsqrtf(m2 / n_all + p.ln_eps);
             }
 #pragma unroll 1
             for (int s = 0; s < NSUB; ++s, ++g) {
@@ -443,7 +461,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
                     }
                 }
-                if (EPI == EPI_LNRES && col0 + 32 <= p.N) {
+                if ((EPI == EPI_LNRES || EPI == EPI_LN) && col0 + 32 <= p.N) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col0 + j));
@@ -640,7 +658,14 @@ extern "C" int rgbnm_gemm_bf16(const rgbnm_gemm_args* args, void* stream) {
             if (!a.C || !a.aux || !a.ln_gamma || !a.ln_beta || (a.ldc % 8) || (a.ldaux % 8) || (a.N % 32) || a.N > 384 ||
                 (reinterpret_cast<uintptr_t>(a.ln_gamma) & 15) || (reinterpret_cast<uintptr_t>(a.ln_beta) & 15))
                 return RGBNM_ERR_ARG;
+            if (a.N <= 128) return launch<128, 6, EPI_LNRES, false, false>(a, st);       // N = 96: a 128-wide tile wastes 25 %, not 50 %
             return a.N > 192 ? launch<384, 3, EPI_LNRES, false, false>(a, st) : launch<192, 5, EPI_LNRES, false, false>(a, st);
+        case RGBNM_EPI_LN:
+            if (!a.C || !a.ln_gamma || !a.ln_beta || (a.ldc % 8) || (a.N % 32) || a.N > 384 ||
+                (reinterpret_cast<uintptr_t>(a.ln_gamma) & 15) || (reinterpret_cast<uintptr_t>(a.ln_beta) & 15))
+                return RGBNM_ERR_ARG;
+            if (a.N <= 128) return launch<128, 6, EPI_LN, false, false>(a, st);
+            return a.N > 192 ? launch<384, 3, EPI_LN, false, false>(a, st) : launch<192, 5, EPI_LN, false, false>(a, st);
         case RGBNM_EPI_GELU_ACT:
             if (!a.C || (a.ldc % 8)) return RGBNM_ERR_ARG;
             return wide ? launch<256, 4, EPI_GELU_ACT, false, false>(a, st) : launch<192, 5, EPI_GELU_ACT, false, false>(a, st);

@@ -11,7 +11,7 @@ import torch
 
 from . import lib as _lib
 
-EPI_STORE, EPI_RESIDUAL, EPI_GELU, EPI_DGELU, EPI_POSEMB, EPI_WGRAD_ATOMIC, EPI_F32, EPI_GELU_ACT, EPI_LNRES = range(9)
+EPI_STORE, EPI_RESIDUAL, EPI_GELU, EPI_DGELU, EPI_POSEMB, EPI_WGRAD_ATOMIC, EPI_F32, EPI_GELU_ACT, EPI_LNRES, EPI_LN = range(10)
 
 
 class GemmArgs(C.Structure):
@@ -87,7 +87,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int = EPI_STORE, bias: Opti
         if epilogue in (EPI_RESIDUAL, EPI_DGELU, EPI_LNRES):
             _check_bf16(aux, "aux")
             args.aux, args.ldaux = aux.data_ptr(), aux.stride(0)
-        if epilogue == EPI_LNRES:       # out = aux + LayerNorm(a b^T + bias) * gamma + beta; ln = (gamma, beta) fp32 [N]
+        if epilogue in (EPI_LNRES, EPI_LN):       # out = (aux +) LayerNorm(a b^T + bias) * gamma + beta; ln = (gamma, beta) fp32 [N]
             gamma, beta = ln
             if gamma.dtype != torch.float32 or beta.dtype != torch.float32 or gamma.numel() != N or beta.numel() != N:
                 raise ValueError("rgbnm gemm: ln = (gamma, beta) must be fp32 [N]")

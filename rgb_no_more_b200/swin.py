@@ -29,6 +29,10 @@ from . import lib as _lib
 import os
 
 _NOFUSE = os.environ.get("RGBNM_SWIN_NOFUSE") is not None      # A/B: separate LayerNorm kernels instead of the fused GEMM epilogue
+# Measured (profiles/r01_swin_eval_v4_launches.txt): folding the norm into the GEMM pays where the layer is memory-bound
+# (dims 96 / 192: -39 .. -93 us per block at batch 256) and costs where the 384-wide single-accumulator tile exposes the
+# longer epilogue (dim 384: +5 .. +30 us) -> fused up to 192 channels.
+_FUSE_MAX_DIM = int(os.environ.get("RGBNM_SWIN_FUSE_MAX_DIM", "192"))
 RES = 64          # tokens per side for img_size 256 / patch 4
 IN_FEAT = 24      # 4x4 luma + 2x2 Cb + 2x2 Cr
 
@@ -208,8 +212,11 @@ class SwinEngine:
         bufs = self._alloc(B)
         s0 = bufs["stages"][0]
         wE, bE, gE, beE = self.embed
-        self._gemm(x_in, wE, G.EPI_STORE, bias=bE, out=s0["tmp"])
-        x = self._ln(s0["tmp"], (gE, beE), None, s0["xa"])
+        if not _NOFUSE:
+            x = self._gemm(x_in, wE, G.EPI_LN, bias=bE, ln=(gE, beE), out=s0["xa"])         # Linear(24, 96) + patch_embed.norm
+        else:
+            self._gemm(x_in, wE, G.EPI_STORE, bias=bE, out=s0["tmp"])
+            x = self._ln(s0["tmp"], (gE, beE), None, s0["xa"])
         for li, st in enumerate(self.stages):
             b = bufs["stages"][li]
             H, Cd = st["res"], st["dim"]
@@ -217,7 +224,7 @@ class SwinEngine:
                 other = b["xb"] if x is b["xa"] else b["xa"]
                 self._gemm(x, blk["qkv"], G.EPI_STORE, bias=blk["qkv_bias"], out=b["qkv"])
                 self._attn(b["qkv"], b["att"], blk, B, H, Cd)
-                if Cd <= 384 and not _NOFUSE:
+                if Cd <= _FUSE_MAX_DIM and not _NOFUSE:
                     # x + norm1(proj(.)) and x1 + norm2(fc2(.)) inside the GEMM epilogue (RGBNM_EPI_LNRES): the row fits one tile
                     x1 = self._gemm(b["att"], blk["proj"], G.EPI_LNRES, bias=blk["proj_b"], aux=x, ln=blk["n1"], out=other)
                     self._gemm(x1, blk["fc1"], G.EPI_GELU_ACT, bias=blk["fc1_b"], out=b["f"])   # only gelu(fc1) is kept (inference)
@@ -234,8 +241,11 @@ class SwinEngine:
                 _lib.check(self.L.rgbnm_patch_merge_gather(x.data_ptr(), b["gath"].data_ptr(), B, H, H, Cd, _lib.stream_ptr()),
                            "rgbnm_patch_merge_gather")
                 self.launches += 1
-                self._gemm(b["gath"], st["down"]["red"], G.EPI_STORE, out=b["red"])
-                x = self._ln(b["red"], st["down"]["norm"], None, bufs["stages"][li + 1]["xa"])
+                if 2 * Cd <= _FUSE_MAX_DIM and not _NOFUSE:
+                    x = self._gemm(b["gath"], st["down"]["red"], G.EPI_LN, ln=st["down"]["norm"], out=bufs["stages"][li + 1]["xa"])
+                else:
+                    self._gemm(b["gath"], st["down"]["red"], G.EPI_STORE, out=b["red"])
+                    x = self._ln(b["red"], st["down"]["norm"], None, bufs["stages"][li + 1]["xa"])
                 if collect is not None:
                     collect.append((f"stage{li}", x.view(B, (H // 2) ** 2, 2 * Cd).float().clone()))
             elif collect is not None:

@@ -189,3 +189,19 @@ def test_gemm_lnres_epilogue(M, N, K):
     with pytest.raises(Exception):
         G.gemm(a, w.repeat(8, 1)[: 768], G.EPI_LNRES, bias=None, aux=aux.repeat(1, 8)[:, :768].contiguous(),
                ln=(gamma.repeat(8)[:768].contiguous(), beta.repeat(8)[:768].contiguous()))      # N = 768 > one tile
+
+
+@pytest.mark.parametrize("M,N,K", [(8192, 96, 24), (2048, 192, 384), (1024, 384, 768)])
+def test_gemm_ln_epilogue(M, N, K):
+    """RGBNM_EPI_LN: LayerNorm(a w^T (+ bias)) inside the GEMM epilogue (patch_embed.norm, PatchMerging.norm)."""
+    from rgb_no_more_b200 import gemm as G
+    g = torch.Generator().manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g) * 0.7).bfloat16().to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().to(DEV)
+    bias = (torch.randn(N, generator=g) * 0.5 + 0.3).to(DEV) if K == 24 else None
+    gamma = (1 + 0.2 * torch.randn(N, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(N, generator=g)).to(DEV)
+    got = G.gemm(a, w, G.EPI_LN, bias=bias, ln=(gamma, beta)).float()
+    pre = a.float() @ w.float().T
+    ref = F.layer_norm(pre + bias if bias is not None else pre, (N,), gamma, beta, 1e-5)
+    assert float((got - ref).abs().max()) < 1e-2 * max(1.0, float(ref.abs().max()))
