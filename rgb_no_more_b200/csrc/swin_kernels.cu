@@ -229,6 +229,7 @@ window_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
 constexpr int KS_LD = 40;     // bf16 per staged K row (32 + 8 pad)
 constexpr int VT_LD = 72;     // bf16 per row of V^T (64 keys + 8 pad)
 constexpr int BS_LD = 72;     // floats per staged bias row
+constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -238,6 +239,11 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const unsigned (&a)[4], 
 __device__ __forceinline__ float sumsq_bf2(unsigned w) {
     const float2 f = bf2_to_f2(w);
     return f.x * f.x + f.y * f.y;
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 __device__ __forceinline__ float quad_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -285,7 +291,7 @@ __device__ __forceinline__ void window_fetch(WinLoad& L, const __nv_bfloat16* __
     }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, const float* __restrict__ bias,
                        const float* __restrict__ scale, int H, int W, int C, int shift, int n_windows) {
     __shared__ __align__(16) __nv_bfloat16 Ks[WT * KS_LD];
@@ -296,9 +302,12 @@ window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
     const int head = blockIdx.y;
     for (int e = tid; e < WT * (WT / 4); e += 128) {
         const int row = e >> 4, c4 = e & 15;
-        *reinterpret_cast<float4*>(Bs + row * BS_LD + c4 * 4) = __ldg(reinterpret_cast<const float4*>(bias + (size_t(head) * WT + row) * WT) + c4);
+        // scores are kept in log2 units (bias, logit scale and the mask value carry log2(e)): the softmax is one EX2 per element
+        float4 b = __ldg(reinterpret_cast<const float4*>(bias + (size_t(head) * WT + row) * WT) + c4);
+        b.x *= LOG2E; b.y *= LOG2E; b.z *= LOG2E; b.w *= LOG2E;
+        *reinterpret_cast<float4*>(Bs + row * BS_LD + c4 * 4) = b;
     }
-    const float sc = __ldg(scale + head);
+    const float sc = __ldg(scale + head) * LOG2E;
     const int wpr = W / WS, wpi = (H / WS) * wpr;
     const int R0 = warp * 16 + g, R1 = R0 + 8;             // in-window rows (2 * warp, g) and (2 * warp + 1, g)
 
@@ -367,10 +376,10 @@ window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
             s[nt][3] = fmaf(s[nt][3] * rk1, f1, b1.y);
             if (last_y || last_x) {
                 const int hc = last_y ? (nt < cut ? 1 : 2) : 0;
-                if (hc != hr0 || wc0 != wrr) s[nt][0] += -100.0f;                // attn_mask value of swinv2.py:242
-                if (hc != hr0 || wc1 != wrr) s[nt][1] += -100.0f;
-                if (hc != hr1 || wc0 != wrr) s[nt][2] += -100.0f;
-                if (hc != hr1 || wc1 != wrr) s[nt][3] += -100.0f;
+                if (hc != hr0 || wc0 != wrr) s[nt][0] += -100.0f * LOG2E;        // attn_mask value of swinv2.py:242
+                if (hc != hr0 || wc1 != wrr) s[nt][1] += -100.0f * LOG2E;
+                if (hc != hr1 || wc0 != wrr) s[nt][2] += -100.0f * LOG2E;
+                if (hc != hr1 || wc1 != wrr) s[nt][3] += -100.0f * LOG2E;
             }
             m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
             m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
@@ -380,10 +389,10 @@ window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
         float l0 = 0.0f, l1 = 0.0f;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            s[nt][0] = __expf(s[nt][0] - m0);
-            s[nt][1] = __expf(s[nt][1] - m0);
-            s[nt][2] = __expf(s[nt][2] - m1);
-            s[nt][3] = __expf(s[nt][3] - m1);
+            s[nt][0] = ex2_fast(s[nt][0] - m0);
+            s[nt][1] = ex2_fast(s[nt][1] - m0);
+            s[nt][2] = ex2_fast(s[nt][2] - m1);
+            s[nt][3] = ex2_fast(s[nt][3] - m1);
             l0 += s[nt][0] + s[nt][1];
             l1 += s[nt][2] + s[nt][3];
         }
