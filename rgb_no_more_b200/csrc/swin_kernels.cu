@@ -291,7 +291,10 @@ __device__ __forceinline__ void window_fetch(WinLoad& L, const __nv_bfloat16* __
     }
 }
 
-__global__ void __launch_bounds__(128, 6)
+#ifndef RGBNM_WATTN_MINBLOCKS
+#define RGBNM_WATTN_MINBLOCKS 5      // resident CTAs per SM the register allocation aims at; A/B in one box (profiles/r01_swin_ab_minblocks.log): 5 -> 7.17-7.29 ms, 6 -> 7.24-7.32, 8 -> 8.0
+#endif
+__global__ void __launch_bounds__(128, RGBNM_WATTN_MINBLOCKS)
 window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, const float* __restrict__ bias,
                        const float* __restrict__ scale, int H, int W, int C, int shift, int n_windows) {
     __shared__ __align__(16) __nv_bfloat16 Ks[WT * KS_LD];

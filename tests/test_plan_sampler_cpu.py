@@ -1,0 +1,50 @@
+"""CPU: the host plan sampler replays the reference's RNG draw order (SURVEY.md 8a "RNG contract").  The golden files hold,
+per case, the seed the reference's transform classes ran under and the plan our sampler resolved under the same seed when
+the file was made; the oracle reproduces the reference's outputs from those plans (tests/test_oracle_golden.py,
+tests/test_swin_oracle_golden.py).  Here the sampler is re-run under the stored seeds and must give the stored plans again.
+RandAugment_dct rebuilds its op list with list(set(...)) after a chroma op (custom_transforms.py:1115-1119), so the order of
+the remaining ops -- in the reference as here -- depends on the interpreter's string-hash seed: the golden files were made
+with PYTHONHASHSEED=0, and the re-run happens in a subprocess with the same setting."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests.helpers import ROOT, load
+
+SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+from rgb_no_more_b200 import plan as P
+g = np.load(sys.argv[2], allow_pickle=False)
+size = int(sys.argv[3])
+bank = P.FilterBank()
+plans = []
+for k, (img, seed, mag) in enumerate(g["cases"]):
+    if seed < 0:
+        plans.append(P.eval_plan(64, 64) if size == 28 else P.eval_plan_swin(64, 64))
+        continue
+    n = k - int((g["cases"][:, 1] < 0).sum())
+    if size == 28:
+        ops = P.AUGLIST_VITS if n % 2 == 0 else P.AUGLIST_VITTI
+    else:
+        ops = P.AUGLIST_VITS if n % 4 < 2 else P.AUGLIST_VITTI
+    torch.manual_seed(int(seed))
+    plans.append(P.sample_train_plan(64, 64, list(ops), 2, int(mag), bank, size=size))
+packed = P.pack_plans(plans, out_size=size)
+same = packed.tobytes() == g["plans"].tobytes()
+print("SAME" if same else "DIFF", len(plans), int(np.abs(bank.table - g["filters"]).max() == 0))
+"""
+
+
+@pytest.mark.parametrize("name,size", [("pipeline.npz", 28), ("swin_pipeline.npz", 32)])
+def test_sampler_reproduces_golden_plans(name, size):
+    env = dict(os.environ, PYTHONHASHSEED="0")
+    r = subprocess.run([sys.executable, "-c", SCRIPT, ROOT, os.path.join(ROOT, "tests", "golden", name), str(size)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    verdict, n, filters_same = r.stdout.split()[-3:]
+    assert verdict == "SAME", r.stdout
+    assert int(n) == len(load(name)["cases"]) and int(filters_same) == 1

@@ -21,7 +21,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
 sys.path.insert(0, ROOT)
 sys.path.insert(1, REF)
-os.environ.setdefault("PYTHONHASHSEED", "0")
+if os.environ.get("PYTHONHASHSEED") != "0":
+    # RandAugment_dct's list(set(...)) op order depends on the interpreter's string-hash seed (custom_transforms.py:1115-1119):
+    # the vectors are made under PYTHONHASHSEED=0, which only takes effect at interpreter start -> re-exec
+    os.environ["PYTHONHASHSEED"] = "0"
+    os.execv(sys.executable, [sys.executable] + sys.argv)
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
