@@ -236,6 +236,19 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const unsigned (&a)[4], 
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// four 8x8 bf16 matrices from shared memory, one row address per lane (lanes 8m .. 8m+7 address the rows of matrix m);
+// thread (g = lane / 4, t = lane % 4) receives elements [g][2t], [g][2t+1] of each matrix (.trans: [2t][g], [2t+1][g])
+__device__ __forceinline__ void ldmatrix_x4(unsigned (&r)[4], const void* p) {
+    const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(p));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(unsigned (&r)[4], const void* p) {
+    const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(p));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+#ifndef RGBNM_WATTN_LDMATRIX
+#define RGBNM_WATTN_LDMATRIX 1       // 0: 32-bit fragment loads + transposed V stores (first MMA version), kept for A/B builds
+#endif
 __device__ __forceinline__ float sumsq_bf2(unsigned w) {
     const float2 f = bf2_to_f2(w);
     return f.x * f.x + f.y * f.y;
@@ -298,7 +311,11 @@ __global__ void __launch_bounds__(128, RGBNM_WATTN_MINBLOCKS)
 window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, const float* __restrict__ bias,
                        const float* __restrict__ scale, int H, int W, int C, int shift, int n_windows) {
     __shared__ __align__(16) __nv_bfloat16 Ks[WT * KS_LD];
+#if RGBNM_WATTN_LDMATRIX
+    __shared__ __align__(16) __nv_bfloat16 Vs[WT * KS_LD];          // V row-major like K; B fragments through ldmatrix.trans
+#else
     __shared__ __align__(16) __nv_bfloat16 Vt[HD * VT_LD];
+#endif
     __shared__ __align__(16) float Bs[WT * BS_LD];
     __shared__ float rk[WT];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -330,6 +347,11 @@ window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
                       sumsq_bf2(cur.k1.y) + sumsq_bf2(cur.k1.z) + sumsq_bf2(cur.k1.w);
             n += __shfl_xor_sync(0xffffffffu, n, 1);
             if (half == 0) rk[r] = 1.0f / fmaxf(sqrtf(n), 1e-12f);
+#if RGBNM_WATTN_LDMATRIX
+            uint4* vd = reinterpret_cast<uint4*>(Vs + r * KS_LD + half * 16);
+            vd[0] = cur.v0;
+            vd[1] = cur.v1;
+#else
             const unsigned vw[8] = {cur.v0.x, cur.v0.y, cur.v0.z, cur.v0.w, cur.v1.x, cur.v1.y, cur.v1.z, cur.v1.w};
             unsigned short* vt = reinterpret_cast<unsigned short*>(Vt);
 #pragma unroll
@@ -337,6 +359,7 @@ window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
                 vt[(half * 16 + 2 * e) * VT_LD + r] = static_cast<unsigned short>(vw[e] & 0xffffu);
                 vt[(half * 16 + 2 * e + 1) * VT_LD + r] = static_cast<unsigned short>(vw[e] >> 16);
             }
+#endif
         }
         // the next window's operands start their trip now and land during this window's arithmetic
         if (win + int(gridDim.x) < n_windows) window_fetch(nxt, qkv, win + gridDim.x, head, C, H, W, wpr, wpi, shift, tid, R0, t);
@@ -347,6 +370,17 @@ window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
 
         // ---- S = Q K^T (raw), 8 key tiles x 2 k-steps ----
         float s[8][4];
+#if RGBNM_WATTN_LDMATRIX
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+            // matrices m = 0..3: keys nt*8 .. +7 (rows), dims 8m .. 8m+7 -> {b0, b1} of k-step 0 and of k-step 1
+            unsigned kb[4];
+            ldmatrix_x4(kb, Ks + (nt * 8 + (lane & 7)) * KS_LD + (lane >> 3) * 8);
+            mma16816(s[nt], cur.qa[0], kb[0], kb[1]);
+            mma16816(s[nt], cur.qa[1], kb[2], kb[3]);
+        }
+#else
         const unsigned* ksw = reinterpret_cast<const unsigned*>(Ks);
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
@@ -357,6 +391,7 @@ window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
                 mma16816(s[nt], cur.qa[ks], ksw[w], ksw[w + 4]);
             }
         }
+#endif
         // ---- cosine normalisation, logit scale, relative position bias, shift mask; row maxima ----
         // shift regions (img_mask of swinv2.py:227-238, in shifted coordinates): only the last window row / column is
         // split, at in-window coordinate 8 - shift: region = 3 * hr + wr with hr, wr in {0 | 1, 2}
@@ -405,16 +440,31 @@ window_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
         float o[4][4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.0f;
+#if !RGBNM_WATTN_LDMATRIX
         const unsigned* vtw = reinterpret_cast<const unsigned*>(Vt);
+#endif
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             const unsigned pa[4] = {f2_to_bf2(s[2 * kk][0], s[2 * kk][1]), f2_to_bf2(s[2 * kk][2], s[2 * kk][3]),
                                     f2_to_bf2(s[2 * kk + 1][0], s[2 * kk + 1][1]), f2_to_bf2(s[2 * kk + 1][2], s[2 * kk + 1][3])};
+#if RGBNM_WATTN_LDMATRIX
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                // matrices m = 0..3 (transposed on load): keys kk*16 + 8*(m & 1) .. +7 (rows), dims (2*np + (m >> 1))*8 .. +7
+                // -> {b0, b1} of dim tile 2*np and of dim tile 2*np + 1
+                unsigned vb[4];
+                const int m = lane >> 3;
+                ldmatrix_x4_trans(vb, Vs + (kk * 16 + (m & 1) * 8 + (lane & 7)) * KS_LD + (2 * np + (m >> 1)) * 8);
+                mma16816(o[2 * np], pa, vb[0], vb[1]);
+                mma16816(o[2 * np + 1], pa, vb[2], vb[3]);
+            }
+#else
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 const int w = (nt * 8 + g) * (VT_LD / 2) + kk * 8 + t;
                 mma16816(o[nt], pa, vtw[w], vtw[w + 4]);
             }
+#endif
         }
         const float i0 = 1.0f / l0, i1 = 1.0f / l1;
         unsigned* d0 = reinterpret_cast<unsigned*>(out + size_t(cur.tok0) * C + head * HD);
