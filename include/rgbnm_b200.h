@@ -90,7 +90,8 @@ enum rgbnm_op {
     RGBNM_OP_CUTOUT = 4, RGBNM_OP_BRIGHTNESS = 5, RGBNM_OP_CONTRAST = 6, RGBNM_OP_COLOR = 7,
     RGBNM_OP_AUTOCONTRAST = 8, RGBNM_OP_AUTOSATURATION = 9, RGBNM_OP_POSTERIZE = 10,
     RGBNM_OP_SHARPNESS = 11, RGBNM_OP_MIDFREQ = 12, RGBNM_OP_GRAYSCALE = 13,
-    RGBNM_OP_CHROMADROP = 14, RGBNM_OP_SOLARIZE_ADD = 15, RGBNM_OP_INVERT = 16
+    RGBNM_OP_CHROMADROP = 14, RGBNM_OP_SOLARIZE_ADD = 15, RGBNM_OP_INVERT = 16,
+    RGBNM_OP_FREQ_ENHANCE = 17   /* every coefficient but the DC term * f, Y and CbCr (dct_ops.py:1015-1034) */
 };
 #define RGBNM_MAX_OPS 4
 #define RGBNM_FILTER_SLOTS 48

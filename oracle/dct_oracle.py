@@ -229,6 +229,13 @@ def block_filter(x: torch.Tensor, filt: torch.Tensor) -> torch.Tensor:
     return torch.round(z).to(x.dtype)
 
 
+def freq_enhance(x: torch.Tensor, factor_f32: float) -> torch.Tensor:
+    # freq_enhance_dct, dct_ops.py:1015-1034: every coefficient except DCT[0,0] times `magnitude` in fp32, rounded
+    z = x.to(torch.float32).reshape(*x.shape[:3], 64).clone()
+    z[:, :, :, 1:] *= factor_f32
+    return torch.round(z).reshape(x.shape).to(x.dtype)
+
+
 def to_range(x: torch.Tensor) -> torch.Tensor:
     # ToRange(-1, 1, -1024, 1016)  custom_transforms.py:448-452
     z = x.to(torch.float32)
@@ -279,6 +286,8 @@ def apply_op(y: torch.Tensor, c: torch.Tensor, op, filters: np.ndarray):
         y = solarize_add(y, p[0])
     elif name == "Invert":
         y, c = y * -1, c * -1
+    elif name == "FreqEnhance":
+        y, c = freq_enhance(y, op.f), freq_enhance(c, op.f)
     elif name == "Identity":
         pass
     else:

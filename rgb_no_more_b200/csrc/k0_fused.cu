@@ -119,6 +119,11 @@ __device__ __forceinline__ bool run_ops(float (&v)[8], const rgbnm_plan& pl, int
         } else if (code == RGBNM_OP_INVERT) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = clamp_hi(-v[i]);
+        } else if (code == RGBNM_OP_FREQ_ENHANCE) {
+            // every coefficient but DCT[0,0] (physical (row 0, column 0) whatever the transpose flag) * f, rounded, clamped
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i != 0 || c != 0) v[i] = clampf(rint_magic(v[i] * op.f));
         } else if (c == 0) {
             // DC-only ops: one value of one lane in eight
             float d = v[0];

@@ -51,6 +51,7 @@ OP_GRAYSCALE = 13
 OP_CHROMADROP = 14
 OP_SOLARIZE_ADD = 15
 OP_INVERT = 16
+OP_FREQ_ENHANCE = 17
 
 OP_NAMES = {
     "Identity": OP_NOP, "TranslateX": OP_TRANSLATE_X, "TranslateY": OP_TRANSLATE_Y,
@@ -59,10 +60,11 @@ OP_NAMES = {
     "AutoSaturation": OP_AUTOSATURATION, "Posterize": OP_POSTERIZE,
     "Sharpness": OP_SHARPNESS, "MidfreqAug": OP_MIDFREQ, "Grayscale": OP_GRAYSCALE,
     "ChromaDrop": OP_CHROMADROP, "SolarizeAdd": OP_SOLARIZE_ADD, "Invert": OP_INVERT,
+    "FreqEnhance": OP_FREQ_ENHANCE,
 }
 # Dispatchable in the reference but outside every default DCT AUGLIST
 # (utils/configs.py:29,93): arbitrary-angle DCT->DFT warps and histogram ops.
-UNSUPPORTED_OPS = ("Rotate", "ShearX", "ShearY", "Equalize", "Solarize", "FreqEnhance")
+UNSUPPORTED_OPS = ("Rotate", "ShearX", "ShearY", "Equalize", "Solarize")
 
 MAX_OPS = 4          # plan slots per image (reference default num_ops = 2)
 N_FILTER_SLOTS = 48  # distinct 8x8 multiplicative filters per launch
@@ -332,6 +334,8 @@ def resolve_op(op_name: str, magnitude: float, grid: int, bank: FilterBank) -> P
         op.p[0] = 0 if torch.rand(1).item() > 0.5 else 1   # >0.5 drops Cb, else Cr (:1012-1015)
     elif code == OP_SOLARIZE_ADD:
         op.p[0] = int(magnitude)
+    elif code == OP_FREQ_ENHANCE:
+        op.f = float(np.float32(1.0 + magnitude))     # freq_enhance_dct(coeff, 1.0 + magnitude): fp32 multiply (dct_ops.py:1029)
     return op
 
 

@@ -196,6 +196,26 @@ def test_properties_full_batch():
     assert torch.equal(fc, (rc.flip(3) * sign).clamp(-1024, 1016))
 
 
+@pytest.mark.parametrize("out_size,crop", [(28, 28), (28, 56), (32, 32), (32, 16)])
+def test_freq_enhance_and_rot90_combinations(out_size, crop):
+    """FreqEnhance (every coefficient but the DC term * f, rounded, clamped; dct_ops.py:1015-1034) alone and around a
+    Rotate90 (the in-block transpose must not move the untouched DC term), both layouts: bit-exact vs the oracle ops applied
+    to K0's own resized planes."""
+    B = 8
+    y, c, q = _random_batch(B, 61 + crop, True)
+    tf = TF.FusedDCT(DEV, "train", P.AUGLIST_VITS, 4, 9, out_size=out_size)
+    fe = lambda f: P.PlanOp(code=P.OP_FREQ_ENHANCE, f=float(np.float32(f)), name="FreqEnhance")
+    rot = lambda d: P.PlanOp(code=P.OP_ROT90, p=[d] + [0] * 7, name="Rotate90")
+    ops_sets = [[fe(1.81)], [fe(0.19)], [rot(1), fe(1.27)], [fe(1.81), rot(-1), fe(0.73)]]
+    plans = [P.Plan(crop_i=2 * (b % 2), crop_j=4, crop_size=crop, flip=bool(b & 1), train=True, ops=ops_sets[b % 4]) for b in range(B)]
+    yd, cd, qd = y.to(DEV), c.to(DEV), q.to(DEV)
+    got = TF.split_planes(tf.run(yd, cd, qd, plans, out_mode=TF.OUT_INT16_PLANES).cpu(), out_size)
+    res = TF.split_planes(tf.run(yd, cd, qd, [_resize_only(p) for p in plans], out_mode=TF.OUT_INT16_PLANES).cpu(), out_size)
+    for b, pl in enumerate(plans):
+        fy, fc = O.transform_from_resized(res[0][b].clone(), res[1][b].clone(), pl, tf.bank.table)
+        assert torch.equal(got[0][b], fy) and torch.equal(got[1][b], fc), (b, [o.name for o in pl.ops])
+
+
 def test_linearity_of_embed_input():
     """Without rounding stages (crop 28, no ops) K0 is affine in the dequantised coefficients:
     out(a) + out(b) - out(0) == out(a + b) up to fp32 rounding."""

@@ -122,3 +122,15 @@ def test_vit_oracle_matches_reference():
               "classhead.ch_linear2.weight", "encoder.5.0.fn.eb_lrnorm1.weight"):
         got = params[k].grad.reshape(-1)[:4096].numpy()
         assert np.abs(got - g["grad:" + k]).max() < 1e-4 * max(1.0, np.abs(g["grad:" + k]).max()), k
+
+
+def test_ops_extra_bit_exact():
+    """FreqEnhance (dct_ops.py:1015-1034; dispatchable, outside the default AUGLISTs) against the reference's own output."""
+    g = load("ops_extra.npz")
+    y, c = torch.from_numpy(g["y"]), torch.from_numpy(g["c"])
+    bank = P.FilterBank()
+    for k, (name, mag) in enumerate(zip(g["case_names"], g["case_mags"])):
+        op = P.resolve_op(str(name), float(mag), 8, bank)
+        oy, oc = O.apply_op(y.clone(), c.clone(), op, bank.table)
+        assert np.array_equal(oy.numpy(), g[f"{name}_{k}_y"]), (name, mag)
+        assert np.array_equal(oc.numpy(), g[f"{name}_{k}_c"]), (name, mag)

@@ -106,6 +106,26 @@ def gen_ops_small():
     print("ops_small:", len(cases), "cases")
 
 
+def gen_ops_extra():
+    """Ops added after ops_small.npz was frozen: FreqEnhance (dct_ops.py:1015-1034), same input blocks as gen_ops_small."""
+    g = torch.Generator().manual_seed(1)
+    y = torch.randint(-1024, 1017, (1, 8, 8, 8, 8), generator=g, dtype=torch.int16)
+    c = torch.randint(-1024, 1017, (2, 4, 4, 8, 8), generator=g, dtype=torch.int16)
+    y[0, :, :, 0, 0] = torch.randint(-900, 900, (8, 8), generator=g, dtype=torch.int16)
+    out = {"y": y.numpy(), "c": c.numpy()}
+    lin = torch.linspace(0.0, 0.9, 11)
+    cases = []
+    for m in (float(lin[9]), -float(lin[9]), float(lin[3]), -float(lin[3]), float(lin[10]), -float(lin[10])):
+        res = ctrans._apply_op_dct([y.clone(), c.clone()], "FreqEnhance", m, pad=2 ** 0.5, conv_Ls=[None, None], conv_Ms=[None, None])
+        key = f"FreqEnhance_{len(cases)}"
+        out[key + "_y"], out[key + "_c"] = res[0].numpy(), res[1].numpy()
+        cases.append(("FreqEnhance", m))
+    out["case_names"] = np.array([n for n, _ in cases])
+    out["case_mags"] = np.array([m for _, m in cases], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "ops_extra.npz"), **out)
+    print("ops_extra:", len(cases), "cases")
+
+
 def gen_resize():
     g = torch.Generator().manual_seed(2)
     out = {}
@@ -242,9 +262,8 @@ def gen_embed_vit():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    gen_ops_small()
-    gen_resize()
-    gen_pipeline()
-    gen_embed_vit()
+    todo = sys.argv[1:] or ["ops_small", "ops_extra", "resize", "pipeline", "embed_vit"]
+    for name in todo:
+        globals()["gen_" + name]()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
