@@ -229,6 +229,24 @@ def block_filter(x: torch.Tensor, filt: torch.Tensor) -> torch.Tensor:
     return torch.round(z).to(x.dtype)
 
 
+def equalize(x: torch.Tensor) -> torch.Tensor:
+    """equalize_dct / scale_channel_dct (dct_ops.py:916-955), CPU branch (torch.bincount): histogram equalisation of the DC
+    plane of every channel.  One distinct DC value divides by zero in the reference (NaN -> undefined int16 cast); the B200
+    path defines that case as "leave unchanged"."""
+    x = x.clone()
+    for ch in range(x.shape[0]):
+        dc = x[ch, :, :, 0, 0].clone() - CLAMP_MIN
+        hist = torch.bincount(dc.reshape(-1).to(torch.int64), minlength=(CLAMP_MAX - CLAMP_MIN) + 1)
+        nz = hist[hist != 0]
+        if nz.numel() < 2:
+            continue
+        mn_minus_min = nz[1:].sum()
+        cdf = torch.cumsum(hist, 0)
+        eq = torch.round((cdf - nz[0]) / mn_minus_min * (CLAMP_MAX - CLAMP_MIN - 1))
+        x[ch, :, :, 0, 0] = eq[dc.to(torch.int64)].to(x.dtype) + CLAMP_MIN
+    return x
+
+
 def freq_enhance(x: torch.Tensor, factor_f32: float) -> torch.Tensor:
     # freq_enhance_dct, dct_ops.py:1015-1034: every coefficient except DCT[0,0] times `magnitude` in fp32, rounded
     z = x.to(torch.float32).reshape(*x.shape[:3], 64).clone()
@@ -286,6 +304,8 @@ def apply_op(y: torch.Tensor, c: torch.Tensor, op, filters: np.ndarray):
         y = solarize_add(y, p[0])
     elif name == "Invert":
         y, c = y * -1, c * -1
+    elif name == "Equalize":
+        y = equalize(y)
     elif name == "FreqEnhance":
         y, c = freq_enhance(y, op.f), freq_enhance(c, op.f)
     elif name == "Identity":

@@ -15,5 +15,5 @@ void rgbnm_set_cuda_error(cudaError_t e, const char* where) {
 
 extern "C" {
 const char* rgbnm_last_cuda_error(void) { return g_last_cuda_error; }
-int rgbnm_abi_version(void) { return 4; }
+int rgbnm_abi_version(void) { return 5; }
 }

@@ -90,6 +90,8 @@ k0_dcstats_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbc
     __shared__ __align__(16) float cqf[192];
     __shared__ float dc[2][NDC];
     __shared__ float scratch[STATS_THREADS / 32];
+    __shared__ int eq[2048];                 // Equalize: histogram of the luma DC plane, then the value -> value mapping
+    __shared__ int iscratch[STATS_THREADS / 32 + 2];
     if (threadIdx.x < int(sizeof(rgbnm_plan) / 4))
         reinterpret_cast<int*>(&pl)[threadIdx.x] = __ldg(reinterpret_cast<const int*>(plans + img) + threadIdx.x);
     __syncthreads();
@@ -140,6 +142,50 @@ k0_dcstats_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbc
             for (int e = lo_e + threadIdx.x; e < hi_e; e += STATS_THREADS) { mn = fminf(mn, src[e]); mx = fmaxf(mx, src[e]); }
             s0 = block_reduce(mn, 1, scratch);
             s1 = block_reduce(mx, 2, scratch);
+        } else if (code == RGBNM_OP_EQUALIZE) {
+            // scale_channel_dct (dct_ops.py:916-940): hist = bincount(dc + 1024); cdf = cumsum(hist);
+            // map[v] = round((cdf[v] - hist[first non-empty bin]) / (N - that) * 2039) - 1024, fp32 like torch's int / int
+            for (int i = threadIdx.x; i < 2048; i += STATS_THREADS) eq[i] = 0;
+            __syncthreads();
+            for (int e = threadIdx.x; e < NY; e += STATS_THREADS) atomicAdd(&eq[int(src[e]) + 1024], 1);
+            __syncthreads();
+            int loc[8], sum = 0, first = 4096;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                loc[j] = eq[threadIdx.x * 8 + j];
+                if (loc[j] != 0 && first == 4096) first = threadIdx.x * 8 + j;
+                sum += loc[j];
+            }
+            // block-wide exclusive scan of `sum` and minimum of `first`
+            int incl = sum, fmin = first;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((threadIdx.x & 31) >= o) incl += t;
+            }
+            for (int o = 16; o > 0; o >>= 1) fmin = min(fmin, __shfl_xor_sync(0xffffffffu, fmin, o));
+            if ((threadIdx.x & 31) == 31) iscratch[threadIdx.x >> 5] = incl;
+            __syncthreads();
+            int base = 0;
+            for (int w = 0; w < int(threadIdx.x >> 5); ++w) base += iscratch[w];
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) iscratch[threadIdx.x >> 5] = fmin;
+            __syncthreads();
+            for (int w = 0; w < STATS_THREADS / 32; ++w) fmin = min(fmin, iscratch[w]);
+            const int h0 = eq[fmin];                       // every thread reads it before the table is overwritten
+            const int mn = NY - h0;
+            __syncthreads();
+            int running = base + incl - sum;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int b = threadIdx.x * 8 + j;
+                running += loc[j];
+                int val = b - 1024;                        // one distinct DC value (0 / 0 in the reference): unchanged
+                if (mn > 0) val = int(rint_magic(__fdiv_rn(float(running - h0), float(mn)) * 2039.0f)) - 1024;
+                eq[b] = val;
+                if (tb.equalize_lut != nullptr)
+                    tb.equalize_lut[(size_t(img) * RGBNM_MAX_OPS + k) * 2048 + b] = int16_t(max(-32768, min(32767, val)));
+            }
+            __syncthreads();
         }
         if (threadIdx.x == 0) { stats[2 * k] = s0; stats[2 * k + 1] = s1; }
         // ---- then apply op k to the DC planes ----
@@ -186,6 +232,8 @@ k0_dcstats_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbc
                 if (comp == 0 && v < 0.0f) v += float(op.p[0]);
             } else if (code == RGBNM_OP_INVERT) {
                 v = -v;
+            } else if (code == RGBNM_OP_EQUALIZE) {
+                if (comp == 0) v = float(eq[int(v) + 1024]);
             }
             dst[e] = clampf(v);
         }

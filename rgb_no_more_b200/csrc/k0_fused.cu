@@ -74,7 +74,7 @@ __device__ __forceinline__ float clamp_hi(float x) { return fminf(x, CLAMP_HI); 
 // the entry clamp every value is inside [-1024, 1016], so the per-op clamp can only act on
 // values the op has just changed -- negations (-(-1024) = 1024) and the DC term.
 __device__ __forceinline__ bool run_ops(float (&v)[8], const rgbnm_plan& pl, int comp, int c, int zero,
-                                        const rgbnm_k0_tables& tb, const float* __restrict__ stats) {
+                                        const rgbnm_k0_tables& tb, const float* __restrict__ stats, int img) {
     bool T = false;
     int start = 0;
     if (zero >= 0) {
@@ -144,6 +144,10 @@ __device__ __forceinline__ bool run_ops(float (&v)[8], const rgbnm_plan& pl, int
                 d = float(tb.posterize_lut[op.p[0] * 2048 + int(d) + 1024]);
             } else if (code == RGBNM_OP_SOLARIZE_ADD) {
                 if (comp == 0 && d < 0.0f) d += float(op.p[0]);
+            } else if (code == RGBNM_OP_EQUALIZE) {
+                // per-image DC mapping built by the statistics pre-pass (histogram equalisation, dct_ops.py:916-955)
+                if (comp == 0 && tb.equalize_lut != nullptr)
+                    d = float(tb.equalize_lut[(size_t(img) * RGBNM_MAX_OPS + k) * 2048 + int(d) + 1024]);
             }
             v[0] = clampf(d);
         }
@@ -448,7 +452,7 @@ __device__ __forceinline__ void process_row(WarpSmemT<LAYOUT>& ws, int lane, int
                 col_item(mode, colp, k < 2 ? 16 : 8, inf, v);
             }
             __syncwarp();                                         // this round's RY / RC reads are done: S / CT may overwrite
-            T = run_ops(v, pl, comp, c, zero, tb, stats);
+            T = run_ops(v, pl, comp, c, zero, tb, stats, img);
 
             if (OUT_MODE == RGBNM_K0_OUT_INT16_PLANES) {
                 int16_t* o16 = reinterpret_cast<int16_t*>(out_) + size_t(img) * PLANE_ELEMS;

@@ -29,7 +29,7 @@ class WPrepDesc(C.Structure):
 
 
 class K0Tables(C.Structure):
-    _fields_ = [("filters", C.c_void_p), ("posterize_lut", C.c_void_p)]
+    _fields_ = [("filters", C.c_void_p), ("posterize_lut", C.c_void_p), ("equalize_lut", C.c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol include/rgbnm_b200.h declares.

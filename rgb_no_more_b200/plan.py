@@ -52,6 +52,7 @@ OP_CHROMADROP = 14
 OP_SOLARIZE_ADD = 15
 OP_INVERT = 16
 OP_FREQ_ENHANCE = 17
+OP_EQUALIZE = 18
 
 OP_NAMES = {
     "Identity": OP_NOP, "TranslateX": OP_TRANSLATE_X, "TranslateY": OP_TRANSLATE_Y,
@@ -60,11 +61,11 @@ OP_NAMES = {
     "AutoSaturation": OP_AUTOSATURATION, "Posterize": OP_POSTERIZE,
     "Sharpness": OP_SHARPNESS, "MidfreqAug": OP_MIDFREQ, "Grayscale": OP_GRAYSCALE,
     "ChromaDrop": OP_CHROMADROP, "SolarizeAdd": OP_SOLARIZE_ADD, "Invert": OP_INVERT,
-    "FreqEnhance": OP_FREQ_ENHANCE,
+    "FreqEnhance": OP_FREQ_ENHANCE, "Equalize": OP_EQUALIZE,
 }
 # Dispatchable in the reference but outside every default DCT AUGLIST
 # (utils/configs.py:29,93): arbitrary-angle DCT->DFT warps and histogram ops.
-UNSUPPORTED_OPS = ("Rotate", "ShearX", "ShearY", "Equalize", "Solarize")
+UNSUPPORTED_OPS = ("Rotate", "ShearX", "ShearY", "Solarize")
 
 MAX_OPS = 4          # plan slots per image (reference default num_ops = 2)
 N_FILTER_SLOTS = 48  # distinct 8x8 multiplicative filters per launch
@@ -110,7 +111,7 @@ class Plan:
 
     @property
     def needs_stats(self) -> bool:
-        return any(o.code in (OP_BRIGHTNESS, OP_AUTOCONTRAST, OP_AUTOSATURATION) for o in self.ops)
+        return any(o.code in (OP_BRIGHTNESS, OP_AUTOCONTRAST, OP_AUTOSATURATION, OP_EQUALIZE) for o in self.ops)
 
 
 # --------------------------------------------------------------------------

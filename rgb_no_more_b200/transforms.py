@@ -57,6 +57,7 @@ class FusedDCT:
         self._filters_n = -1
         self._lut = torch.from_numpy(P.posterize_lut()).to(self.device)
         self._tables = _lib.K0Tables()
+        self._eq_lut = None
         self._sync_tables()
 
     # -- tables ---------------------------------------------------------------------------
@@ -110,6 +111,9 @@ class FusedDCT:
                 out = torch.empty((B, self.tokens, self.feat), dtype=torch.bfloat16 if out_mode == OUT_BF16 else torch.float32,
                                   device=self.device)
         stats = torch.zeros((B, P.MAX_OPS, 2), dtype=torch.float32, device=self.device)
+        if self._eq_lut is None or self._eq_lut.shape[0] < B:      # scratch of the Equalize op (per image and op slot)
+            self._eq_lut = torch.empty((B, P.MAX_OPS, 2048), dtype=torch.int16, device=self.device)
+        self._tables.equalize_lut = self._eq_lut.data_ptr()
         st = _lib.stream_ptr()
         L = self._lib
         _lib.check(L.rgbnm_k0_dcstats_ex(y_q.data_ptr(), c_q.data_ptr(), quant.data_ptr(), plans_dev.data_ptr(),

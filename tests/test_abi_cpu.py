@@ -35,7 +35,7 @@ def test_struct_sizes_match_the_header():
     assert C.sizeof(L.WPrepDesc) == 64                       # rgbnm_wprep_desc
     # rgbnm_gemm_args: 8 pointers, 5 long long, 9 int + 1 float, then (ABI 4) 2 pointers + 1 float (+ 4 bytes tail padding)
     assert C.sizeof(G.GemmArgs) == 8 * 8 + 5 * 8 + 10 * 4 + 2 * 8 + 8
-    assert L.load().rgbnm_abi_version() == 4
+    assert L.load().rgbnm_abi_version() == 5
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

@@ -216,6 +216,30 @@ def test_freq_enhance_and_rot90_combinations(out_size, crop):
         assert torch.equal(got[0][b], fy) and torch.equal(got[1][b], fc), (b, [o.name for o in pl.ops])
 
 
+@pytest.mark.parametrize("out_size,crop", [(28, 28), (28, 56), (32, 32)])
+def test_equalize_with_neighbouring_stats_ops(out_size, crop):
+    """Equalize (histogram equalisation of the luma DC plane, dct_ops.py:916-955): its per-image mapping is built by the
+    statistics pre-pass from the DC plane AS IT STANDS when the op runs, and later statistics ops must see its output --
+    bit-exact vs the oracle applied to K0's own resized planes.  One image has a flat DC plane (single histogram bin)."""
+    B = 8
+    y, c, q = _random_batch(B, 71 + crop, False)
+    y[7, :, :, 0] = 5                                   # flat luma DC: the reference divides by zero, here: unchanged
+    tf = TF.FusedDCT(DEV, "train", P.AUGLIST_VITS, 4, 9, out_size=out_size)
+    eqz = lambda: P.PlanOp(code=P.OP_EQUALIZE, name="Equalize")
+    op = lambda name, p=None, f=0.0: P.PlanOp(code=P.OP_NAMES[name], p=(p or [0] * 8), f=f, name=name)
+    ops_sets = [[eqz()], [op("Brightness", f=0.27), eqz()], [eqz(), op("AutoContrast")],
+                [op("TranslateX", [4, 2] + [0] * 6), eqz(), op("Rotate90", [1] + [0] * 7), op("Brightness", f=-0.5)]]
+    plans = [P.Plan(crop_i=2 * (b % 2), crop_j=4, crop_size=crop, flip=bool(b & 1), train=True, ops=ops_sets[b % 4]) for b in range(B)]
+    assert all(pl.needs_stats for pl in plans)
+    yd, cd, qd = y.to(DEV), c.to(DEV), q.to(DEV)
+    got = TF.split_planes(tf.run(yd, cd, qd, plans, out_mode=TF.OUT_INT16_PLANES).cpu(), out_size)
+    res = TF.split_planes(tf.run(yd, cd, qd, [_resize_only(p) for p in plans], out_mode=TF.OUT_INT16_PLANES).cpu(), out_size)
+    for b, pl in enumerate(plans):
+        fy, fc = O.transform_from_resized(res[0][b].clone(), res[1][b].clone(), pl, tf.bank.table)
+        assert torch.equal(got[0][b], fy) and torch.equal(got[1][b], fc), (b, [o.name for o in pl.ops], lsb_report(got[0][b].numpy(), fy.numpy()))
+    assert int((got[0][0] != res[0][0]).sum()) > 100   # the op did something
+
+
 def test_linearity_of_embed_input():
     """Without rounding stages (crop 28, no ops) K0 is affine in the dequantised coefficients:
     out(a) + out(b) - out(0) == out(a + b) up to fp32 rounding."""

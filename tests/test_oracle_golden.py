@@ -134,3 +134,15 @@ def test_ops_extra_bit_exact():
         oy, oc = O.apply_op(y.clone(), c.clone(), op, bank.table)
         assert np.array_equal(oy.numpy(), g[f"{name}_{k}_y"]), (name, mag)
         assert np.array_equal(oc.numpy(), g[f"{name}_{k}_c"]), (name, mag)
+
+
+def test_equalize_quantised_dc_plane():
+    g = load("ops_extra.npz")
+    y2, c = torch.from_numpy(g["y2"]), torch.from_numpy(g["c"])
+    op = P.resolve_op("Equalize", 0.0, 8, P.FilterBank())
+    oy, oc = O.apply_op(y2.clone(), c.clone(), op, None)
+    assert np.array_equal(oy.numpy(), g["Equalize_y2_y"]) and np.array_equal(oc.numpy(), g["Equalize_y2_c"])
+    # one distinct DC value: the reference divides by zero; here the plane is left unchanged
+    flat = y2.clone()
+    flat[0, :, :, 0, 0] = 37
+    assert torch.equal(O.equalize(flat), flat)

@@ -120,6 +120,16 @@ def gen_ops_extra():
         key = f"FreqEnhance_{len(cases)}"
         out[key + "_y"], out[key + "_c"] = res[0].numpy(), res[1].numpy()
         cases.append(("FreqEnhance", m))
+    res = ctrans._apply_op_dct([y.clone(), c.clone()], "Equalize", 0.0, pad=2 ** 0.5, conv_Ls=[None, None], conv_Ms=[None, None])
+    key = f"Equalize_{len(cases)}"
+    out[key + "_y"], out[key + "_c"] = res[0].numpy(), res[1].numpy()
+    cases.append(("Equalize", 0.0))
+    # a DC plane with repeated values (ties in the histogram) and a few distinct levels only
+    y2 = y.clone()
+    y2[0, :, :, 0, 0] = (y2[0, :, :, 0, 0] // 200) * 200
+    res = ctrans._apply_op_dct([y2.clone(), c.clone()], "Equalize", 0.0, pad=2 ** 0.5, conv_Ls=[None, None], conv_Ms=[None, None])
+    out["y2"] = y2.numpy()
+    out["Equalize_y2_y"], out["Equalize_y2_c"] = res[0].numpy(), res[1].numpy()
     out["case_names"] = np.array([n for n, _ in cases])
     out["case_mags"] = np.array([m for _, m in cases], dtype=np.float64)
     np.savez_compressed(os.path.join(OUT, "ops_extra.npz"), **out)
