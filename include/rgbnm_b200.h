@@ -92,7 +92,8 @@ enum rgbnm_op {
     RGBNM_OP_SHARPNESS = 11, RGBNM_OP_MIDFREQ = 12, RGBNM_OP_GRAYSCALE = 13,
     RGBNM_OP_CHROMADROP = 14, RGBNM_OP_SOLARIZE_ADD = 15, RGBNM_OP_INVERT = 16,
     RGBNM_OP_FREQ_ENHANCE = 17,  /* every coefficient but the DC term * f, Y and CbCr (dct_ops.py:1015-1034) */
-    RGBNM_OP_EQUALIZE = 18       /* histogram equalisation of the luma DC plane (dct_ops.py:916-955) */
+    RGBNM_OP_EQUALIZE = 18,      /* histogram equalisation of the luma DC plane (dct_ops.py:916-955) */
+    RGBNM_OP_SOLARIZE = 19       /* blocks whose luma DC > f inverted; chroma block (r,c) follows luma block (2r,2c) (dct_ops.py:631-651) */
 };
 #define RGBNM_MAX_OPS 4
 #define RGBNM_FILTER_SLOTS 48
@@ -119,7 +120,8 @@ typedef struct {
     const float* filters;        /* [RGBNM_FILTER_SLOTS][64] multiplicative 8x8 filters */
     const int16_t* posterize_lut;/* [6][2048] */
     int16_t* equalize_lut;       /* [n][RGBNM_MAX_OPS][2048] scratch: rgbnm_k0_dcstats writes the per-image DC mapping of every
-                                    Equalize op, rgbnm_k0_fused reads it; may be NULL when no plan holds an Equalize op */
+                                    Equalize op (and the per-block 0/1 mask of every Solarize op, index r * grid + c),
+                                    rgbnm_k0_fused reads it; may be NULL when no plan holds such an op */
 } rgbnm_k0_tables;
 
 #define RGBNM_K0_OUT_F32 0

@@ -229,6 +229,16 @@ def block_filter(x: torch.Tensor, filt: torch.Tensor) -> torch.Tensor:
     return torch.round(z).to(x.dtype)
 
 
+def solarize(y: torch.Tensor, c: torch.Tensor, threshold_f32: float):
+    """solarize_dct on Y and, with the luma mask sub-sampled [::2, ::2], on CbCr (dct_ops.py:631-651,
+    custom_transforms.py:980-982): every coefficient of a block is negated where the luma DC term exceeds the threshold."""
+    y, c = y.clone(), c.clone()
+    mask = y[:, :, :, 0, 0] > threshold_f32
+    y[mask] *= -1
+    c[mask[:, ::2, ::2].repeat(2, 1, 1)] *= -1
+    return y, c
+
+
 def equalize(x: torch.Tensor) -> torch.Tensor:
     """equalize_dct / scale_channel_dct (dct_ops.py:916-955), CPU branch (torch.bincount): histogram equalisation of the DC
     plane of every channel.  One distinct DC value divides by zero in the reference (NaN -> undefined int16 cast); the B200
@@ -304,6 +314,8 @@ def apply_op(y: torch.Tensor, c: torch.Tensor, op, filters: np.ndarray):
         y = solarize_add(y, p[0])
     elif name == "Invert":
         y, c = y * -1, c * -1
+    elif name == "Solarize":
+        y, c = solarize(y, c, op.f)
     elif name == "Equalize":
         y = equalize(y)
     elif name == "FreqEnhance":

@@ -264,4 +264,23 @@ __device__ __forceinline__ Trace trace_back(const rgbnm_plan& pl, int comp, int 
     return t;
 }
 
+// Position of the block that ends at final-grid position (r, c) at the moment op `k` runs: the geometric ops after k
+// walked backwards (zeroing ops do not move blocks).  Used by ops that look at another block (Solarize: chroma follows the
+// luma block at twice its coordinates).
+template <int GRID_Y>
+__device__ __forceinline__ void position_at_op(const rgbnm_plan& pl, int comp, int k, int& r, int& c) {
+    const int G = comp == 0 ? GRID_Y : GRID_Y / 2;
+    for (int j = pl.n_ops - 1; j > k; --j) {
+        const rgbnm_plan_op& op = pl.ops[j];
+        const int code = op.code;
+        if (code == RGBNM_OP_TRANSLATE_X) c -= op.p[comp == 0 ? 0 : 1];
+        else if (code == RGBNM_OP_TRANSLATE_Y) r -= op.p[comp == 0 ? 0 : 1];
+        else if (code == RGBNM_OP_ROT90) {
+            const int rr = r, cc = c;
+            if (op.p[0] > 0) { r = cc; c = G - 1 - rr; }
+            else             { r = G - 1 - cc; c = rr; }
+        }
+    }
+}
+
 }  // namespace k0

@@ -187,6 +187,15 @@ k0_dcstats_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbc
             }
             __syncthreads();
         }
+        else if (code == RGBNM_OP_SOLARIZE) {
+            // mask plane: luma DC above the threshold as the op runs (dct_ops.py:646); kept in `eq` and handed to the fused kernel
+            for (int e = threadIdx.x; e < NY; e += STATS_THREADS) {
+                const int m = src[e] > op.f ? 1 : 0;
+                eq[e] = m;
+                if (tb.equalize_lut != nullptr) tb.equalize_lut[(size_t(img) * RGBNM_MAX_OPS + k) * 2048 + e] = int16_t(m);
+            }
+            __syncthreads();
+        }
         if (threadIdx.x == 0) { stats[2 * k] = s0; stats[2 * k + 1] = s1; }
         // ---- then apply op k to the DC planes ----
         for (int e = threadIdx.x; e < NDC; e += STATS_THREADS) {
@@ -234,6 +243,8 @@ k0_dcstats_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbc
                 v = -v;
             } else if (code == RGBNM_OP_EQUALIZE) {
                 if (comp == 0) v = float(eq[int(v) + 1024]);
+            } else if (code == RGBNM_OP_SOLARIZE) {
+                if (eq[comp == 0 ? e : (2 * r) * GRID_Y + 2 * c] != 0) v = -v;
             }
             dst[e] = clampf(v);
         }

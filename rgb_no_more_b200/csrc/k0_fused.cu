@@ -74,7 +74,8 @@ __device__ __forceinline__ float clamp_hi(float x) { return fminf(x, CLAMP_HI); 
 // the entry clamp every value is inside [-1024, 1016], so the per-op clamp can only act on
 // values the op has just changed -- negations (-(-1024) = 1024) and the DC term.
 __device__ __forceinline__ bool run_ops(float (&v)[8], const rgbnm_plan& pl, int comp, int c, int zero,
-                                        const rgbnm_k0_tables& tb, const float* __restrict__ stats, int img) {
+                                        const rgbnm_k0_tables& tb, const float* __restrict__ stats, int img, int fr, int fc,
+                                        int grid_y) {
     bool T = false;
     int start = 0;
     if (zero >= 0) {
@@ -119,6 +120,19 @@ __device__ __forceinline__ bool run_ops(float (&v)[8], const rgbnm_plan& pl, int
         } else if (code == RGBNM_OP_INVERT) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = clamp_hi(-v[i]);
+        } else if (code == RGBNM_OP_SOLARIZE) {
+            // mask plane of this op (luma DC > threshold when the op ran) from the statistics pre-pass; a chroma block follows
+            // the luma block at twice its coordinates AT THAT TIME: walk the later geometric ops back from (fr, fc)
+            if (tb.equalize_lut != nullptr) {
+                int r = fr, cc = fc;
+                if (grid_y == 32) position_at_op<32>(pl, comp, k, r, cc); else position_at_op<28>(pl, comp, k, r, cc);
+                if (comp != 0) { r *= 2; cc *= 2; }
+                const bool inside = r >= 0 && cc >= 0 && r < grid_y && cc < grid_y;
+                if (inside && tb.equalize_lut[(size_t(img) * RGBNM_MAX_OPS + k) * 2048 + r * grid_y + cc] != 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = clamp_hi(-v[i]);
+                }
+            }
         } else if (code == RGBNM_OP_FREQ_ENHANCE) {
             // every coefficient but DCT[0,0] (physical (row 0, column 0) whatever the transpose flag) * f, rounded, clamped
 #pragma unroll
@@ -452,7 +466,10 @@ __device__ __forceinline__ void process_row(WarpSmemT<LAYOUT>& ws, int lane, int
                 col_item(mode, colp, k < 2 ? 16 : 8, inf, v);
             }
             __syncwarp();                                         // this round's RY / RC reads are done: S / CT may overwrite
-            T = run_ops(v, pl, comp, c, zero, tb, stats, img);
+            int fr, fc;            // final-grid position of this lane's block
+            if (k < 2) { fr = 2 * th + ((b >> 1) & 1); fc = 2 * (2 * tp + k) + (b & 1); }
+            else { fr = th; fc = 2 * tp + ((b - 8) >> 1); }
+            T = run_ops(v, pl, comp, c, zero, tb, stats, img, fr, fc, GRID_Y);
 
             if (OUT_MODE == RGBNM_K0_OUT_INT16_PLANES) {
                 int16_t* o16 = reinterpret_cast<int16_t*>(out_) + size_t(img) * PLANE_ELEMS;

@@ -53,6 +53,7 @@ OP_SOLARIZE_ADD = 15
 OP_INVERT = 16
 OP_FREQ_ENHANCE = 17
 OP_EQUALIZE = 18
+OP_SOLARIZE = 19
 
 OP_NAMES = {
     "Identity": OP_NOP, "TranslateX": OP_TRANSLATE_X, "TranslateY": OP_TRANSLATE_Y,
@@ -61,11 +62,11 @@ OP_NAMES = {
     "AutoSaturation": OP_AUTOSATURATION, "Posterize": OP_POSTERIZE,
     "Sharpness": OP_SHARPNESS, "MidfreqAug": OP_MIDFREQ, "Grayscale": OP_GRAYSCALE,
     "ChromaDrop": OP_CHROMADROP, "SolarizeAdd": OP_SOLARIZE_ADD, "Invert": OP_INVERT,
-    "FreqEnhance": OP_FREQ_ENHANCE, "Equalize": OP_EQUALIZE,
+    "FreqEnhance": OP_FREQ_ENHANCE, "Equalize": OP_EQUALIZE, "Solarize": OP_SOLARIZE,
 }
 # Dispatchable in the reference but outside every default DCT AUGLIST
 # (utils/configs.py:29,93): arbitrary-angle DCT->DFT warps and histogram ops.
-UNSUPPORTED_OPS = ("Rotate", "ShearX", "ShearY", "Solarize")
+UNSUPPORTED_OPS = ("Rotate", "ShearX", "ShearY")
 
 MAX_OPS = 4          # plan slots per image (reference default num_ops = 2)
 N_FILTER_SLOTS = 48  # distinct 8x8 multiplicative filters per launch
@@ -111,7 +112,7 @@ class Plan:
 
     @property
     def needs_stats(self) -> bool:
-        return any(o.code in (OP_BRIGHTNESS, OP_AUTOCONTRAST, OP_AUTOSATURATION, OP_EQUALIZE) for o in self.ops)
+        return any(o.code in (OP_BRIGHTNESS, OP_AUTOCONTRAST, OP_AUTOSATURATION, OP_EQUALIZE, OP_SOLARIZE) for o in self.ops)
 
 
 # --------------------------------------------------------------------------
@@ -335,6 +336,8 @@ def resolve_op(op_name: str, magnitude: float, grid: int, bank: FilterBank) -> P
         op.p[0] = 0 if torch.rand(1).item() > 0.5 else 1   # >0.5 drops Cb, else Cr (:1012-1015)
     elif code == OP_SOLARIZE_ADD:
         op.p[0] = int(magnitude)
+    elif code == OP_SOLARIZE:
+        op.f = float(np.float32(magnitude))           # threshold on the luma DC term: `dcBlocks > threshold` (dct_ops.py:646)
     elif code == OP_FREQ_ENHANCE:
         op.f = float(np.float32(1.0 + magnitude))     # freq_enhance_dct(coeff, 1.0 + magnitude): fp32 multiply (dct_ops.py:1029)
     return op

@@ -240,6 +240,35 @@ def test_equalize_with_neighbouring_stats_ops(out_size, crop):
     assert int((got[0][0] != res[0][0]).sum()) > 100   # the op did something
 
 
+@pytest.mark.parametrize("out_size,crop", [(28, 28), (28, 14), (32, 64)])
+def test_solarize_follows_luma_blocks_through_geometry(out_size, crop):
+    """Solarize (dct_ops.py:631-651): blocks whose luma DC exceeds the threshold are negated, chroma block (r, c) follows
+    luma block (2r, 2c) as the planes stand WHEN THE OP RUNS -- also when later ops move the blocks (translate, rot90) or
+    zero only one of the two planes (cutout rectangles differ between Y and CbCr).  Bit-exact vs the oracle."""
+    B = 12
+    G = out_size
+    y, c, q = _random_batch(B, 81 + crop, False)
+    tf = TF.FusedDCT(DEV, "train", P.AUGLIST_VITS, 4, 9, out_size=out_size)
+    sol = lambda t: P.PlanOp(code=P.OP_SOLARIZE, f=float(np.float32(t)), name="Solarize")
+    op = lambda name, p=None, f=0.0: P.PlanOp(code=P.OP_NAMES[name], p=(p or [0] * 8), f=f, name=name)
+    cut = lambda: op("Cutout", list(P.cutout_rect(4, 10, 12, G, G)) + list(P.cutout_rect(2, 5, 6, G // 2, G // 2)))
+    ops_sets = [[sol(0.0)], [op("Rotate90", [1] + [0] * 7), sol(100.0)],
+                [sol(-200.0), op("TranslateX", [4, 2] + [0] * 6), op("Rotate90", [-1] + [0] * 7)],
+                [cut(), sol(-50.0)], [sol(163.6), cut(), op("TranslateY", [-6, -3] + [0] * 6)],
+                [op("Brightness", f=0.45), sol(0.0), op("AutoContrast"), sol(327.2)]]
+    plans = [P.Plan(crop_i=2 * (b % 2), crop_j=0 if crop == 64 else 4, crop_size=crop, flip=bool(b & 1), train=True, ops=ops_sets[b % 6])
+             for b in range(B)]
+    yd, cd, qd = y.to(DEV), c.to(DEV), q.to(DEV)
+    got = TF.split_planes(tf.run(yd, cd, qd, plans, out_mode=TF.OUT_INT16_PLANES).cpu(), out_size)
+    res = TF.split_planes(tf.run(yd, cd, qd, [_resize_only(p) for p in plans], out_mode=TF.OUT_INT16_PLANES).cpu(), out_size)
+    for b, pl in enumerate(plans):
+        fy, fc = O.transform_from_resized(res[0][b].clone(), res[1][b].clone(), pl, tf.bank.table)
+        names = [o.name for o in pl.ops]
+        assert torch.equal(got[0][b], fy), (b, names, lsb_report(got[0][b].numpy(), fy.numpy()))
+        assert torch.equal(got[1][b], fc), (b, names, lsb_report(got[1][b].numpy(), fc.numpy()))
+    assert int((got[1][0] != res[1][0]).sum()) > 100   # chroma blocks were inverted
+
+
 def test_linearity_of_embed_input():
     """Without rounding stages (crop 28, no ops) K0 is affine in the dequantised coefficients:
     out(a) + out(b) - out(0) == out(a + b) up to fp32 rounding."""

@@ -124,6 +124,11 @@ def gen_ops_extra():
     key = f"Equalize_{len(cases)}"
     out[key + "_y"], out[key + "_c"] = res[0].numpy(), res[1].numpy()
     cases.append(("Equalize", 0.0))
+    for m in (654.4, 0.0, -327.2, 818.0, -818.0):
+        res = ctrans._apply_op_dct([y.clone(), c.clone()], "Solarize", float(m), pad=2 ** 0.5, conv_Ls=[None, None], conv_Ms=[None, None])
+        key = f"Solarize_{len(cases)}"
+        out[key + "_y"], out[key + "_c"] = res[0].numpy(), res[1].numpy()
+        cases.append(("Solarize", float(m)))
     # a DC plane with repeated values (ties in the histogram) and a few distinct levels only
     y2 = y.clone()
     y2[0, :, :, 0, 0] = (y2[0, :, :, 0, 0] // 200) * 200
