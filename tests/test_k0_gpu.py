@@ -256,7 +256,8 @@ def test_solarize_follows_luma_blocks_through_geometry(out_size, crop):
                 [sol(-200.0), op("TranslateX", [4, 2] + [0] * 6), op("Rotate90", [-1] + [0] * 7)],
                 [cut(), sol(-50.0)], [sol(163.6), cut(), op("TranslateY", [-6, -3] + [0] * 6)],
                 [op("Brightness", f=0.45), sol(0.0), op("AutoContrast"), sol(327.2)]]
-    plans = [P.Plan(crop_i=2 * (b % 2), crop_j=0 if crop == 64 else 4, crop_size=crop, flip=bool(b & 1), train=True, ops=ops_sets[b % 6])
+    plans = [P.Plan(crop_i=0 if crop == 64 else 2 * (b % 2), crop_j=0 if crop == 64 else 4, crop_size=crop, flip=bool(b & 1), train=True,
+                    ops=ops_sets[b % 6])
              for b in range(B)]
     yd, cd, qd = y.to(DEV), c.to(DEV), q.to(DEV)
     got = TF.split_planes(tf.run(yd, cd, qd, plans, out_mode=TF.OUT_INT16_PLANES).cpu(), out_size)
