@@ -125,3 +125,30 @@ def test_swin_compat_embed_path_matches_oracle():
     got = S.swin_embed_input_from_planes(yf, cf)
     ref = O.embed_input_swin(yf, cf).reshape(1, 4096, 24)
     assert float((got - ref).abs().max()) < 1e-5
+
+
+def test_swin_oracle_training_gradients_match_reference():
+    """Groundwork for the SwinV2 backward: autograd through oracle/swin_oracle.py reproduces the loss and
+    the gradients of the reference model in train() mode (stochastic depth off), incl. the logit scale, the cpb_mlp behind
+    the position bias, q / v biases, post-norm weights and the patch-merging reduction."""
+    from oracle import swin_oracle as SO
+    from tests.helpers import seeded_swin_state_dict
+    g = load("swin_train.npz")
+    sd = seeded_swin_state_dict(_swin_shell())
+    yf, cf = golden_swin_inputs(g["input_seed"])
+    params = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "relative_coords_table" not in k and "attn_mask" not in k
+                  else v.clone()) for k, v in sd.items()}
+    labels = torch.zeros((2, 1000))
+    labels[0, 3], labels[0, 7], labels[1, 999] = 0.7, 0.3, 1.0
+    logits = SO.forward(params, yf, cf)
+    loss = torch.nn.CrossEntropyLoss()(logits, labels)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-4
+    assert np.abs(logits.detach().numpy() - g["logits"]).max() < 2e-4
+    keys = [k[5:] for k in g.files if k.startswith("grad:")]
+    assert len(keys) == 10
+    for k in keys:
+        got = params[k].grad.reshape(-1)[:4096].numpy()
+        ref = g["grad:" + k]
+        assert np.abs(got - ref).max() < 1e-4 * max(1.0, np.abs(ref).max()) + 2e-6, (k, np.abs(got - ref).max())
+        assert abs(float(params[k].grad.norm()) - float(g["gradnorm:" + k])) < 1e-3 * max(1e-3, float(g["gradnorm:" + k])), k
