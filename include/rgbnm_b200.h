@@ -280,6 +280,23 @@ int rgbnm_patch_merge_gather(const void* x, void* out, int B, int H, int W, int 
 /* AdaptiveAvgPool1d(1) over tokens (swinv2.py:697-699): out bf16 [B][C] = mean_l x[b][l][c] */
 int rgbnm_token_mean_bf16(const void* x, void* out, int B, int L, int C, void* stream);
 
+/* ---- SwinV2 training (first correct CUDA versions of the backward kernels; fp32 arithmetic on the CUDA cores) ---- */
+/* Post-norm residual with stochastic depth (swinv2.py:302-306, DropPath): y = (res ? res : 0) + s * (LayerNorm(x) * gamma + beta),
+ * s = row_scale ? row_scale[row / rows_per_scale] : 1 (row_scale: fp32 per image = mask / keep_prob).  emb even, <= 768. */
+int rgbnm_layernorm_res_scaled_fwd(const void* x, const float* gamma, const float* beta, const void* res, const float* row_scale,
+                                   int rows_per_scale, void* y, int rows, int emb, float eps, void* stream);
+/* Backward of the LayerNorm branch of the above: dx bf16 = d loss / d x from dy (= d loss / d y; the residual's gradient is
+ * dy itself), dgamma / dbeta fp32 [emb] +=.  Statistics are recomputed from x. */
+int rgbnm_layernorm_res_bwd(const void* dy, const void* x, const float* gamma, const float* row_scale, int rows_per_scale,
+                            void* dx, float* dgamma, float* dbeta, int rows, int emb, float eps, void* stream);
+/* Backward of rgbnm_window_attention_fwd: dqkv bf16 [B*H*W][3*C] from dout bf16 [B*H*W][C] (P is recomputed from qkv);
+ * dbias fp32 [heads][64][64] += d loss / d bias tile (the caller differentiates 16 * sigmoid(cpb_mlp(.))[index] through it),
+ * dscale fp32 [heads] += d loss / d scale (scale = exp(min(logit_scale, log 100))). */
+int rgbnm_window_attention_bwd(const void* qkv, const void* dout, const float* bias, const float* scale, void* dqkv, float* dbias,
+                               float* dscale, int B, int H, int W, int C, int heads, int window, int shift, void* stream);
+/* Inverse of rgbnm_patch_merge_gather: dx bf16 [B][H][W][C] from dy bf16 [B][H/2][W/2][4*C] */
+int rgbnm_patch_merge_scatter(const void* dy, void* dx, int B, int H, int W, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
