@@ -10,8 +10,9 @@ writes in the Swin layout.  The forward pass runs on hand-written sm_100a kernel
     window attention incl. window partition / cyclic shift / reverse                 rgbnm_window_attention_fwd
     patch-merging gather, token mean                                                 rgbnm_patch_merge_gather, rgbnm_token_mean_bf16
 
-Round 1 covers inference (eval / --benchmark); training SwinV2 (backward of the window attention, stochastic depth) is
-not built yet and raises.  There is no CPU fallback.
+Inference (eval / --benchmark) runs on the fused forward engine below; with gradients enabled the call goes through the
+training engine of swin_train.py (explicit forward / backward incl. stochastic depth, first correct version).  There is
+no CPU fallback.
 """
 from __future__ import annotations
 
@@ -343,6 +344,7 @@ class SwinTransformerV2(nn.Module):
                     nn.init.constant_(n.bias, 0)
                     nn.init.constant_(n.weight, 0)
         self._engine: Optional[SwinEngine] = None
+        self._train_engine = None
 
     def no_weight_decay(self):
         return {"absolute_pos_embed"}
@@ -361,13 +363,21 @@ class SwinTransformerV2(nn.Module):
     def forward(self, y, cbcr=None):
         """forward(y, cbcr) with reference-format tensors (swinv2.py:703-705), or forward(x) with the (B,4096,24) tensor
         FusedDCT(out_size=32) writes."""
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("rgbnm: SwinV2 training (window-attention backward, stochastic depth) is not built yet; "
-                                      "wrap inference in torch.no_grad() / model.eval()")
         if cbcr is not None:
             y = swin_embed_input_from_planes(y, cbcr)
         elif y.dim() != 3 or y.shape[2] != IN_FEAT:
             raise ValueError("rgbnm SwinV2: expected (y, cbcr) in the reference layout or a (B,4096,24) embed input")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training path (swin_train.py): explicit forward / backward behind one autograd.Function
+            from . import swin_train as ST
+            if y.device.type != "cuda":
+                raise _lib.RgbnmError("rgbnm: the SwinV2 training engine needs a CUDA device; there is no CPU fallback")
+            if self._train_engine is None or self._train_engine.device != y.device:
+                if next(self.parameters()).device != y.device:
+                    self.to(y.device)
+                self._train_engine = ST.SwinTrainEngine(self, y.device)
+            names = [n for n, _ in self.named_parameters()]
+            return ST.SwinFunction.apply(y, self._train_engine, names, *[p for _, p in self.named_parameters()])
         eng = self.prepare(y.device)
         if eng.weights_stale():
             eng.refresh_weights()

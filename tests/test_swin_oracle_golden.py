@@ -114,7 +114,7 @@ def test_swin_no_cpu_fallback():
         with torch.no_grad():
             m(yf, cf)
     m.train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises((RgbnmError, RuntimeError)):       # the training engine needs a CUDA device as well
         m(yf, cf)
 
 

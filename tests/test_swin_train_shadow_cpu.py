@@ -1,0 +1,139 @@
+"""CPU: the host-side orchestration of the SwinV2 training engine (rgb_no_more_b200/swin_train.py: what is saved, which
+gradient flows where, residual / post-norm / stochastic-depth bookkeeping, the parameter-only graph behind the attention
+tables) checked against the reference's own loss and gradients (tests/golden/swin_train.npz).  The CUDA kernels cannot run
+here, so every kernel entry point of the engine is replaced by a few lines of torch with the same contract; the kernels
+themselves are tested one by one on the GPU (tests/test_swin_bwd_gpu.py, tests/test_swin_gpu.py)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import swin_oracle as SO
+from rgb_no_more_b200 import gemm as G
+from rgb_no_more_b200 import swin as S
+from rgb_no_more_b200 import swin_train as ST
+from tests.helpers import load, seeded_swin_state_dict, golden_swin_inputs
+
+BF = torch.bfloat16
+
+
+def _gelu_grad(u):
+    u = u.float()
+    return 0.5 * (1 + torch.erf(u / 2 ** 0.5)) + u * torch.exp(-0.5 * u * u) / (2 * torch.pi) ** 0.5
+
+
+def fake_gemm(a, b, epilogue=G.EPI_STORE, bias=None, aux=None, out=None, out2=None, posemb=None, out_f32=None, splits=0, alpha=1.0,
+              trans_out=False, perm_heads=0, perm_head_dim=0, ln=None, ln_eps=1e-5):
+    if epilogue == G.EPI_WGRAD_ATOMIC:
+        r = a.float().t() @ b.float()                       # [M, N]
+        out_f32 += r.t() if trans_out else r
+        return out_f32
+    acc = a.float() @ b.float().t()
+    if bias is not None:
+        acc = acc + bias
+    if epilogue == G.EPI_GELU:
+        return acc.to(BF), F.gelu(acc).to(BF)
+    if epilogue == G.EPI_DGELU:
+        acc = acc * _gelu_grad(aux)
+    elif epilogue == G.EPI_RESIDUAL:
+        acc = acc + aux.float()
+    return acc.to(BF)
+
+
+class ShadowEngine(ST.SwinTrainEngine):
+    def __init__(self, model):
+        self.model, self.device, self.L = model, torch.device("cpu"), None
+        depths = [len(layer.blocks) for layer in model.layers]
+        self.dpr = [float(v) for v in torch.linspace(0, model.drop_path_rate, sum(depths))]
+
+    def _ln_fwd(self, x, norm, res, scale, rows_per_scale, y):
+        o = F.layer_norm(x.float(), (x.shape[1],), norm[0], norm[1], 1e-5)
+        if scale is not None:
+            o = o * scale.repeat_interleave(rows_per_scale).unsqueeze(1)
+        if res is not None:
+            o = o + res.float()
+        y.copy_(o.to(BF))
+        return y
+
+    def _ln_bwd(self, dy, x, gamma, scale, rows_per_scale, gname, bname):
+        with torch.enable_grad():               # autograd runs Function.backward with grad mode off
+            xr = x.float().requires_grad_(True)
+            g = gamma.clone().requires_grad_(True)
+            b = torch.zeros_like(gamma).requires_grad_(True)
+            o = F.layer_norm(xr, (x.shape[1],), g, b, 1e-5)
+            if scale is not None:
+                o = o * scale.repeat_interleave(rows_per_scale).unsqueeze(1)
+            o.backward(dy.float())
+        self.grads[gname] += g.grad
+        self.grads[bname] += b.grad
+        return xr.grad.to(BF)
+
+    @staticmethod
+    def _attn(qkv, bias, scale, B, H, Cd, heads, shift):
+        x = qkv.view(B, H, H, 3 * Cd)
+        if shift:
+            x = torch.roll(x, shifts=(-shift, -shift), dims=(1, 2))
+        xw = SO.window_partition(x, 8).view(-1, 64, 3 * Cd)
+        q, k, v = xw.reshape(-1, 64, 3, heads, 32).permute(2, 0, 3, 1, 4)
+        attn = F.normalize(q, dim=-1) @ F.normalize(k, dim=-1).transpose(-2, -1)
+        attn = attn * scale.view(1, heads, 1, 1) + bias.unsqueeze(0)
+        if shift:
+            mask = SO.shift_mask(H, H, 8, shift)
+            attn = (attn.view(-1, mask.shape[0], heads, 64, 64) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, 64, 64)
+        o = (attn.softmax(-1) @ v).transpose(1, 2).reshape(-1, 8, 8, Cd)
+        o = SO.window_reverse(o, 8, H, H)
+        if shift:
+            o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
+        return o.reshape(B * H * H, Cd)
+
+    def _attn_fwd(self, qkv, bias, scale, B, H, Cd, heads, window, shift):
+        return self._attn(qkv.float(), bias, scale, B, H, Cd, heads, shift).to(BF)
+
+    def _attn_bwd(self, qkv, datt, bias, scale, B, H, Cd, heads, window, shift):
+        with torch.enable_grad():
+            q = qkv.float().requires_grad_(True)
+            b, s = bias.clone().requires_grad_(True), scale.clone().requires_grad_(True)
+            self._attn(q, b, s, B, H, Cd, heads, shift).backward(datt.float())
+        return q.grad.to(BF), b.grad, s.grad
+
+    def _gather(self, x, B, H, Cd):
+        x = x.view(B, H, H, Cd)
+        return torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1).reshape(-1, 4 * Cd).contiguous()
+
+    def _scatter(self, dy, B, H, Cd):
+        dy = dy.view(B, H // 2, H // 2, 4, Cd)
+        out = torch.empty((B, H, H, Cd), dtype=dy.dtype)
+        out[:, 0::2, 0::2], out[:, 1::2, 0::2], out[:, 0::2, 1::2], out[:, 1::2, 1::2] = dy[..., 0, :], dy[..., 1, :], dy[..., 2, :], dy[..., 3, :]
+        return out.reshape(-1, Cd)
+
+
+@pytest.fixture
+def patched(monkeypatch):
+    monkeypatch.setattr(ST.G, "gemm", fake_gemm)
+    monkeypatch.setattr(ST.K, "colsum", lambda a, out, *r: out.add_(a.float().sum(0)))
+    monkeypatch.setattr(ST.K, "weight_prep", lambda w, wb, wt, *r: (wb.copy_(w.to(BF)), wt.copy_(w.t().to(BF))))
+
+
+def test_training_orchestration_matches_reference_gradients(patched):
+    g = load("swin_train.npz")
+    m = S.SwinTransformerV2(img_size=256, patch_size=4, embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=8,
+                            mlp_ratio=4, drop_path_rate=0.0, pretrained_window_sizes=[0, 0, 0, 0], device="cpu", pixel_space="dct")
+    m.load_state_dict(seeded_swin_state_dict(m))
+    m.train()
+    eng = ShadowEngine(m)
+    yf, cf = golden_swin_inputs(g["input_seed"])
+    x = S.swin_embed_input_from_planes(yf, cf)
+    names = [n for n, _ in m.named_parameters()]
+    logits = ST.SwinFunction.apply(x, eng, names, *[p for _, p in m.named_parameters()])
+    labels = torch.zeros((2, 1000))
+    labels[0, 3], labels[0, 7], labels[1, 999] = 0.7, 0.3, 1.0
+    loss = torch.nn.CrossEntropyLoss()(logits, labels)
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 2e-2 * float(g["loss"])
+    named = dict(m.named_parameters())
+    for k in [k[5:] for k in g.files if k.startswith("grad:")]:
+        got = named[k].grad.float()
+        ref = torch.from_numpy(g["grad:" + k])
+        cos = float(F.cosine_similarity(got.reshape(-1)[:4096], ref, dim=0))
+        assert cos > 0.99, (k, cos)
+        assert abs(float(got.norm()) - float(g["gradnorm:" + k])) < 5e-2 * float(g["gradnorm:" + k]), (k, float(got.norm()), float(g["gradnorm:" + k]))
