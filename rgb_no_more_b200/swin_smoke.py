@@ -48,3 +48,24 @@ def run() -> None:
         if not err <= 3e-2 * max(rng, 1.0):
             raise AssertionError(f"rgbnm smoke: SwinV2 logits differ from the oracle by {err} (range {rng})")
     print(f"rgbnm smoke: SwinV2 DCT forward ok (|dlogits| <= {worst:.3g} of the logit range)")
+    # one training step of the same model (training engine: saved-activation forward, backward kernels): loss and two
+    # gradients against autograd through the CPU oracle
+    import torch.nn.functional as F
+    m.train()
+    x = emb.to(torch.bfloat16)
+    labels = torch.tensor([3, 7], device=dev)
+    loss = F.cross_entropy(m(x), labels)
+    loss.backward()
+    torch.cuda.synchronize()
+    params = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "relative_coords_table" not in k and "attn_mask" not in k
+                  else v.clone()) for k, v in sd.items()}
+    ref_loss = F.cross_entropy(SO.forward_from_embed(params, x.float().cpu().reshape(B, 64, 64, 24), depths=depths, heads=heads), labels.cpu())
+    ref_loss.backward()
+    if not abs(float(loss) - float(ref_loss)) <= 2e-2 * max(float(ref_loss), 1.0):
+        raise AssertionError(f"rgbnm smoke: SwinV2 training loss {float(loss)} vs oracle {float(ref_loss)}")
+    named = dict(m.named_parameters())
+    for k in ("layers.0.blocks.1.attn.qkv.weight", "layers.1.blocks.0.mlp.fc1.weight", "layers.0.blocks.1.attn.cpb_mlp.2.weight"):
+        cos = float(F.cosine_similarity(named[k].grad.float().cpu().reshape(-1), params[k].grad.reshape(-1), dim=0))
+        if not cos > 0.98:
+            raise AssertionError(f"rgbnm smoke: SwinV2 gradient of {k} differs from the oracle (cos {cos})")
+    print(f"rgbnm smoke: SwinV2 DCT training step ok (loss {float(loss):.4f} vs oracle {float(ref_loss):.4f})")
