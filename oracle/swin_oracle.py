@@ -98,8 +98,9 @@ def window_attention(xw, sd, prefix, heads, ws, mask):
     return F.linear(x, sd[prefix + ".proj.weight"], sd[prefix + ".proj.bias"])
 
 
-def block(x, sd, prefix, H, W, heads, ws, shift):
-    # SwinTransformerBlock.forward, swinv2.py:270-309 (eval: drop_path = identity)
+def block(x, sd, prefix, H, W, heads, ws, shift, s1=None, s2=None):
+    # SwinTransformerBlock.forward, swinv2.py:270-309.  s1 / s2: per-image stochastic-depth scales (mask / keep_prob, timm
+    # DropPath with scale_by_keep) of the two branches, shape (B,); None = identity (eval, or drop_path 0)
     B, L, C = x.shape
     shortcut = x
     x = x.view(B, H, W, C)
@@ -112,10 +113,12 @@ def block(x, sd, prefix, H, W, heads, ws, shift):
     if shift > 0:
         x = torch.roll(x, shifts=(shift, shift), dims=(1, 2))
     x = x.view(B, H * W, C)
-    x = shortcut + _ln(x, sd, prefix + ".norm1")
+    a = _ln(x, sd, prefix + ".norm1")
+    x = shortcut + (a if s1 is None else a * s1.view(-1, 1, 1))
     m = F.linear(F.gelu(F.linear(x, sd[prefix + ".mlp.fc1.weight"], sd[prefix + ".mlp.fc1.bias"])),
                  sd[prefix + ".mlp.fc2.weight"], sd[prefix + ".mlp.fc2.bias"])
-    return x + _ln(m, sd, prefix + ".norm2")
+    m = _ln(m, sd, prefix + ".norm2")
+    return x + (m if s2 is None else m * s2.view(-1, 1, 1))
 
 
 def patch_merging(x, sd, prefix, H, W):
@@ -134,7 +137,8 @@ def tokens(sd, emb_in):
 
 
 def forward_from_embed(sd: Dict[str, torch.Tensor], emb_in: torch.Tensor, depths: Sequence[int] = (2, 2, 6, 2),
-                       heads: Sequence[int] = (3, 6, 12, 24), window: int = 8, collect: List = None) -> torch.Tensor:
+                       heads: Sequence[int] = (3, 6, 12, 24), window: int = 8, collect: List = None,
+                       drop_scales: Sequence = None) -> torch.Tensor:
     """SwinTransformerV2.forward (swinv2.py:681-705) from the embed input (B, R, R, 24) to the logits."""
     res = emb_in.shape[1]
     x = tokens(sd, emb_in)
@@ -143,7 +147,10 @@ def forward_from_embed(sd: Dict[str, torch.Tensor], emb_in: torch.Tensor, depths
         ws = min(window, H)                                            # swinv2.py:208-211
         for bi in range(depth):
             shift = 0 if (bi % 2 == 0 or H <= window) else window // 2
-            x = block(x, sd, f"layers.{li}.blocks.{bi}", H, W, heads[li], ws, shift)
+            s1 = s2 = None
+            if drop_scales is not None:                                # one (s1, s2) pair per block, in forward order
+                s1, s2 = drop_scales[sum(depths[:li]) + bi]
+            x = block(x, sd, f"layers.{li}.blocks.{bi}", H, W, heads[li], ws, shift, s1, s2)
             if collect is not None:
                 collect.append((f"l{li}b{bi}", x))
         if li < len(depths) - 1:

@@ -42,8 +42,23 @@ class SwinTrainEngine:
         self.model, self.device, self.L = model, device, _lib.load()
         depths = [len(layer.blocks) for layer in model.layers]
         self.dpr = [float(v) for v in torch.linspace(0, model.drop_path_rate, sum(depths))]      # swinv2.py:648
+        self._lins: Dict[int, tuple] = {}
 
     # ---------------------------------------------------------------------------------------------
+    def _lin(self, weight) -> "_Lin":
+        """bf16 working copies of a Linear weight, rebuilt only when the parameter has been written (optimiser step, load)."""
+        if not hasattr(self, "_lins"):
+            self._lins = {}
+        hit = self._lins.get(id(weight))
+        if hit is None or hit[0] != weight._version or hit[1].w.device != self.device:
+            hit = (weight._version, _Lin(weight, self.device))
+            self._lins[id(weight)] = hit
+        return hit[1]
+
+    def _draw(self, B: int, keep: float) -> torch.Tensor:
+        """Per-image stochastic-depth scale mask / keep (timm DropPath, scale_by_keep), fp32 [B] on the device."""
+        return torch.empty(B, device=self.device).bernoulli_(keep) / keep
+
     def _f32(self, t):
         return t.detach().to(self.device, torch.float32).contiguous()
 
@@ -106,7 +121,7 @@ class SwinTrainEngine:
         bf = lambda *s: torch.empty(s, dtype=torch.bfloat16, device=dev)
         sv: dict = {"B": B, "x_in": x_in, "stages": []}
         pe = m.patch_embed
-        sv["embed"] = _Lin(pe.projection[0].weight, dev)
+        sv["embed"] = self._lin(pe.projection[0].weight)
         T0 = x_in.shape[0]
         e = G.gemm(x_in, sv["embed"].w, G.EPI_STORE, bias=self._f32(pe.projection[0].bias), out=bf(T0, m.embed_dim))
         sv["e"] = e
@@ -132,9 +147,8 @@ class SwinTrainEngine:
                 blk_index += 1
                 s1 = s2 = None
                 if m.training and keep < 1.0:
-                    s1 = torch.empty(B, device=dev).bernoulli_(keep) / keep
-                    s2 = torch.empty(B, device=dev).bernoulli_(keep) / keep
-                lq, lp, l1, l2 = _Lin(a.qkv.weight, dev), _Lin(a.proj.weight, dev), _Lin(blk.mlp.fc1.weight, dev), _Lin(blk.mlp.fc2.weight, dev)
+                    s1, s2 = self._draw(B, keep), self._draw(B, keep)
+                lq, lp, l1, l2 = self._lin(a.qkv.weight), self._lin(a.proj.weight), self._lin(blk.mlp.fc1.weight), self._lin(blk.mlp.fc2.weight)
                 qkv_bias = torch.cat((a.q_bias, torch.zeros_like(a.v_bias), a.v_bias)).detach().float().contiguous()
                 qkv = G.gemm(x, lq.w, G.EPI_STORE, bias=qkv_bias, out=bf(T, 3 * Cd))
                 att = self._attn_fwd(qkv, bias_d, scale_d, B, H, Cd, heads, a.window_size[0], blk.shift_size)
@@ -145,14 +159,14 @@ class SwinTrainEngine:
                 mm = G.gemm(f, l2.w, G.EPI_STORE, bias=self._f32(blk.mlp.fc2.bias), out=bf(T, Cd))
                 g2 = self._f32(blk.norm2.weight)
                 x2 = self._ln_fwd(mm, (g2, self._f32(blk.norm2.bias)), x1, s2, H * H, bf(T, Cd))
-                st["blocks"].append(dict(pfx=pfx, heads=heads, window=a.window_size[0], shift=blk.shift_size, x=x, qkv=qkv, att=att, p=p, x1=x1,
+                st["blocks"].append(dict(pfx=pfx, attn=a, heads=heads, window=a.window_size[0], shift=blk.shift_size, x=x, qkv=qkv, att=att, p=p, x1=x1,
                                          u=u, f=f, m=mm, g1=g1, g2=g2, s1=s1, s2=s2, lq=lq, lp=lp, l1=l1, l2=l2, bias_t=bias_t, scale_t=scale_t,
                                          bias_d=bias_d, scale_d=scale_d))
                 x = x2
             if layer.downsample is not None:
                 ds = layer.downsample
                 gath = self._gather(x, B, H, Cd)
-                lr = _Lin(ds.reduction.weight, dev)
+                lr = self._lin(ds.reduction.weight)
                 red = G.gemm(gath, lr.w, G.EPI_STORE, out=bf(T // 4, 2 * Cd))
                 gd = self._f32(ds.norm.weight)
                 x = self._ln_fwd(red, (gd, self._f32(ds.norm.bias)), None, None, 1, bf(T // 4, 2 * Cd))
@@ -211,7 +225,7 @@ class SwinTrainEngine:
                 K.colsum(dqkv[:, 2 * Cd:], gr[pfx + ".attn.v_bias"])
                 dx = G.gemm(dqkv, b["lq"].wt, G.EPI_RESIDUAL, aux=dx1)
                 # parameter-only graph behind the attention tables
-                a = dict(m.named_modules())[pfx + ".attn"]
+                a = b["attn"]
                 tg = torch.autograd.grad([b["bias_t"], b["scale_t"]], [a.cpb_mlp[0].weight, a.cpb_mlp[0].bias, a.cpb_mlp[2].weight, a.logit_scale],
                                          [dbias, dscale])
                 for name, g_ in zip((".attn.cpb_mlp.0.weight", ".attn.cpb_mlp.0.bias", ".attn.cpb_mlp.2.weight", ".attn.logit_scale"), tg):

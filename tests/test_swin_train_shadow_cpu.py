@@ -137,3 +137,57 @@ def test_training_orchestration_matches_reference_gradients(patched):
         cos = float(F.cosine_similarity(got.reshape(-1)[:4096], ref, dim=0))
         assert cos > 0.99, (k, cos)
         assert abs(float(got.norm()) - float(g["gradnorm:" + k])) < 5e-2 * float(g["gradnorm:" + k]), (k, float(got.norm()), float(g["gradnorm:" + k]))
+
+
+def test_stochastic_depth_bookkeeping_matches_oracle(patched):
+    """Per-image, per-branch DropPath scales: the engine's forward / backward with a fixed set of masks against autograd
+    through the oracle with the same masks (two-stage model, drop_path 0.5 so that many branches are dropped)."""
+    torch.manual_seed(5)
+    depths, heads = (2, 2), (3, 6)
+    m = S.SwinTransformerV2(img_size=256, patch_size=4, embed_dim=96, depths=list(depths), num_heads=list(heads), window_size=8,
+                            drop_path_rate=0.5, pretrained_window_sizes=[0, 0], device="cpu", pixel_space="dct")
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.ndim == 1:
+                p.add_(0.2 * torch.randn_like(p))
+    m.train()
+    B = 3
+    eng = ShadowEngine(m)
+    drawn = []
+
+    def draw(Bn, keep):
+        s = torch.empty(Bn).bernoulli_(keep) / keep
+        drawn.append(s)
+        return s
+    eng._draw = draw
+    x = torch.randn(B, 4096, 24) * 0.5
+    names = [n for n, _ in m.named_parameters()]
+    logits = ST.SwinFunction.apply(x, eng, names, *[p for _, p in m.named_parameters()])
+    y = torch.tensor([1, 2, 3])
+    F.cross_entropy(logits, y).backward()
+    # block 0 has drop probability 0 (linspace(0, rate, n)[0]): no draw; the other three blocks draw two masks each
+    assert len(drawn) == 6 and any(float(s.min()) == 0.0 for s in drawn)
+    scales = [(None, None)] + [(drawn[2 * i], drawn[2 * i + 1]) for i in range(3)]
+    sd = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "relative_coords_table" not in k and "attn_mask" not in k
+              else v.detach().clone()) for k, v in m.state_dict().items()}
+    ref = SO.forward_from_embed(sd, x.to(BF).float().reshape(B, 64, 64, 24), depths=depths, heads=heads, drop_scales=scales)
+    F.cross_entropy(ref, y).backward()
+    assert float((logits.detach() - ref.detach()).abs().max()) < 3e-2 * float(ref.detach().abs().max())
+    named = dict(m.named_parameters())
+    for k in ("layers.0.blocks.1.attn.qkv.weight", "layers.1.blocks.1.mlp.fc2.weight", "layers.1.blocks.0.norm1.weight",
+              "patch_embed.projection.0.weight", "layers.0.downsample.reduction.weight"):
+        cos = float(F.cosine_similarity(named[k].grad.reshape(-1), sd[k].grad.reshape(-1), dim=0))
+        assert cos > 0.99, (k, cos)
+
+
+def test_weight_copies_are_cached_until_the_parameter_changes(patched):
+    m = S.SwinTransformerV2(img_size=256, patch_size=4, embed_dim=96, depths=[2], num_heads=[3], window_size=8,
+                            drop_path_rate=0.0, pretrained_window_sizes=[0], device="cpu", pixel_space="dct")
+    eng = ShadowEngine(m)
+    w = m.layers[0].blocks[0].attn.qkv.weight
+    a = eng._lin(w)
+    assert eng._lin(w) is a
+    with torch.no_grad():
+        w.add_(1.0)                                   # what an optimiser step does: bumps the parameter's version
+    b = eng._lin(w)
+    assert b is not a and torch.equal(b.w.float(), w.detach().to(BF).float())
