@@ -46,3 +46,26 @@ def test_gpu_entry_points_fail_loudly_without_a_device():
     m = V.ViT(patch_size=16, emb_size=192, depth=1, n_classes=10, drop_p=0.0, pixel_space="DCT", num_heads=3, head_size=64)
     with pytest.raises(Exception):
         m(torch.zeros(1, 196, 384))
+
+
+def test_product_modules_never_import_the_oracle():
+    """oracle/ is test infrastructure: only the smoke checkers (called by __graft_entry__.smoke()), tests/ and bench.py's CPU
+    legs may import it -- never a module on the product path."""
+    import ast
+    import glob
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    offenders = []
+    for path in glob.glob(os.path.join(root, "rgb_no_more_b200", "*.py")):
+        if path.endswith("smoke.py"):
+            continue
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            if any(n == "oracle" or n.startswith("oracle.") for n in names):
+                offenders.append(os.path.basename(path))
+    assert offenders == []
