@@ -16,7 +16,6 @@ no CPU fallback.
 """
 from __future__ import annotations
 
-import ctypes as C
 import math
 from typing import Dict, List, Optional
 

@@ -13,7 +13,7 @@ torch from the kernels' d(bias tile) / d(scale).
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional
+from typing import Dict
 
 import torch
 import torch.nn.functional as F

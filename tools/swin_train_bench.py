@@ -3,7 +3,7 @@ forward with saved activations -> CE -> backward -> torch AdamW), batch 64 per G
 utils/configs.py:137), drop_path 0.2, CUDA events.  Prints one JSON line."""
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch, torch.nn.functional as F
+import torch, torch.nn.functional as F
 from rgb_no_more_b200 import plan as P, synth, swin as S, transforms as TF
 
 ap = argparse.ArgumentParser()
