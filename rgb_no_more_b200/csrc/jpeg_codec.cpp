@@ -48,13 +48,17 @@ struct HuffTable {
     static constexpr int FAST = 9;
     int16_t fast_ac[1 << FAST];
 
-    void build() {
+    // false: the code-length counts do not describe a prefix code (more than 2^l codes of length <= l): the canonical
+    // code would run past its length and the lookahead fill below would write outside look[] (libjpeg rejects such
+    // tables in jpeg_make_d_derived_tbl, "bogus Huffman table definition")
+    bool build() {
         int code = 0, k = 0;
         for (int l = 1; l <= 16; ++l) {
             valptr[l] = k;
             mincode[l] = code;
             code += bits[l];
             k += bits[l];
+            if (code > (1 << l)) return false;
             maxcode[l] = bits[l] ? code - 1 : -1;
             code <<= 1;
         }
@@ -76,9 +80,10 @@ struct HuffTable {
             const int len = e >> 8, rs = e & 0xff, run = rs >> 4, magbits = rs & 15;
             if (magbits == 0 || len + magbits > FAST) continue;
             int k = ((i << len) & ((1 << FAST) - 1)) >> (FAST - magbits);   // the magnitude bits that follow the code
-            if (k < (1 << (magbits - 1))) k += (-1 << magbits) + 1;           // receive_extend
+            if (k < (1 << (magbits - 1))) k -= (1 << magbits) - 1;            // receive_extend
             if (k >= -128 && k <= 127) fast_ac[i] = int16_t((k * 256) + (run * 16) + (len + magbits));
         }
+        return true;
     }
 };
 
@@ -229,7 +234,7 @@ struct Decoder {
                 while (o < seglen) {
                     int pq = seg[o] >> 4, tq = seg[o] & 15;
                     ++o;
-                    if (tq > 3) return RGBNM_ERR_CORRUPT;
+                    if (tq > 3 || pq > 1 || o + (pq ? 128 : 64) > seglen) return RGBNM_ERR_CORRUPT;
                     for (int i = 0; i < 64; ++i) {
                         int v;
                         if (pq) {
@@ -247,8 +252,9 @@ struct Decoder {
                 while (o < seglen) {
                     int tc = seg[o] >> 4, th = seg[o] & 15;
                     ++o;
-                    if (th > 3 || tc > 1) return RGBNM_ERR_CORRUPT;
+                    if (th > 3 || tc > 1 || o + 16 > seglen) return RGBNM_ERR_CORRUPT;
                     HuffTable& t = tc ? ac[th] : dc[th];
+                    t.present = false;
                     int total = 0;
                     t.bits[0] = 0;
                     for (int i = 1; i <= 16; ++i) {
@@ -258,10 +264,11 @@ struct Decoder {
                     if (total > 256 || o + total > seglen) return RGBNM_ERR_CORRUPT;
                     std::memcpy(t.vals, seg + o, total);
                     o += total;
+                    if (!t.build()) return RGBNM_ERR_CORRUPT;
                     t.present = true;
-                    t.build();
                 }
             } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {  // SOF0/1/2
+                if (seglen < 6) return RGBNM_ERR_CORRUPT;
                 progressive = (m == 0xC2);
                 precision = seg[0];
                 height = rd16(seg + 1);
@@ -269,6 +276,8 @@ struct Decoder {
                 ncomp = seg[5];
                 if (ncomp != 1 && ncomp != 3) return RGBNM_ERR_UNSUPPORTED;
                 if (precision != 8) return RGBNM_ERR_UNSUPPORTED;
+                if (seglen < 6 + 3 * ncomp || width == 0 || height == 0) return RGBNM_ERR_CORRUPT;
+                hmax = vmax = 1;
                 for (int i = 0; i < ncomp; ++i) {
                     comp[i].id = seg[6 + 3 * i];
                     comp[i].h = seg[7 + 3 * i] >> 4;
@@ -279,7 +288,7 @@ struct Decoder {
                 }
                 for (int i = 0; i < ncomp; ++i) {
                     Component& c = comp[i];
-                    if (c.h < 1 || c.v < 1 || c.h > 4 || c.v > 4) return RGBNM_ERR_CORRUPT;
+                    if (c.h < 1 || c.v < 1 || c.h > 4 || c.v > 4 || c.tq > 3) return RGBNM_ERR_CORRUPT;
                     c.dsw = (width * c.h + hmax - 1) / hmax;
                     c.dsh = (height * c.v + vmax - 1) / vmax;
                     c.wb = (width * c.h + hmax * 8 - 1) / (hmax * 8);
@@ -289,12 +298,14 @@ struct Decoder {
             } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
                 return RGBNM_ERR_UNSUPPORTED;  // lossless / arithmetic / hierarchical
             } else if (m == 0xDD) {
+                if (seglen < 2) return RGBNM_ERR_CORRUPT;
                 restart_interval = rd16(seg);
             } else if (m == 0xDA) {  // SOS
-                if (!have_sof) return RGBNM_ERR_CORRUPT;
+                if (!have_sof || seglen < 1) return RGBNM_ERR_CORRUPT;
                 int ns = seg[0];
                 if (progressive) return RGBNM_ERR_PROGRESSIVE;
                 if (ns != ncomp) return RGBNM_ERR_UNSUPPORTED;  // non-interleaved baseline scans
+                if (seglen < 1 + 2 * ns + 3) return RGBNM_ERR_CORRUPT;
                 for (int i = 0; i < ns; ++i) {
                     int cid = seg[1 + 2 * i];
                     int k = -1;
@@ -303,6 +314,7 @@ struct Decoder {
                     if (k != i) return RGBNM_ERR_UNSUPPORTED;
                     comp[k].td = seg[2 + 2 * i] >> 4;
                     comp[k].ta = seg[2 + 2 * i] & 15;
+                    if (comp[k].td > 3 || comp[k].ta > 3) return RGBNM_ERR_CORRUPT;
                 }
                 *sos_pos = pos + len;
                 return RGBNM_OK;
@@ -317,6 +329,8 @@ struct Decoder {
     // coefficient is stored: x*q >= -1024 <=> x >= -floor(1024/q), x*q <= 1016 <=> x <= floor(1016/q))
     int decode_scan(size_t pos, int16_t* const planes[3], int* clamp_live = nullptr) {
         int16_t lim_lo[3][64], lim_hi[3][64];      // indexed by zig-zag position
+        for (int i = 0; i < ncomp; ++i)
+            if (comp[i].tq > 3 || comp[i].td > 3 || comp[i].ta > 3 || !qt_present[comp[i].tq]) return RGBNM_ERR_CORRUPT;
         for (int i = 0; i < ncomp; ++i)
             for (int k = 0; k < 64; ++k) {
                 const int qq = qt[comp[i].tq][kZigzag[k]] ? qt[comp[i].tq][kZigzag[k]] : 1;

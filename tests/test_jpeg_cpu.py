@@ -132,3 +132,42 @@ def test_errors_are_runtime_errors_like_the_pybind_module():
         dm.read_coefficients_from_bytes(b.getvalue())                # SOF2: outside the path, reported, not mis-decoded
     with pytest.raises(RuntimeError):
         dm.decode_batch([synth.synth_jpeg(0, 64)], 64, 64)           # wrong geometry for the batch layout
+
+
+def _scan_bytes(buf: bytes) -> bytes:
+    """Entropy-coded segment: everything after the SOS header up to the EOI marker."""
+    pos = 2
+    while True:
+        assert buf[pos] == 0xFF
+        m = buf[pos + 1]
+        ln = (buf[pos + 2] << 8) | buf[pos + 3]
+        pos += 2 + ln
+        if m == 0xDA:
+            break
+    end = buf.rindex(b"\xff\xd9")
+    return buf[pos:end]
+
+
+@pytest.mark.parametrize("quality,subsampling,size", [(75, 2, (512, 512)), (50, 2, (512, 512)), (100, 2, (512, 512)),
+                                                      (90, 0, (512, 512)), (75, 2, (200, 136)), (95, 0, (72, 40))])
+def test_pil_file_reencodes_to_identical_scan_bytes(quality, subsampling, size):
+    """Bit-exact pin of the Huffman decoder against libjpeg-turbo's ENCODER: PIL writes baseline
+    files with the Annex-K tables; decoding such a file and writing the coefficients back with the same tables must
+    reproduce its entropy-coded segment byte for byte.  A single wrong coefficient (+-1, wrong position, wrong
+    DC prediction) changes the re-encoded bits, which the <= 1 level pixel comparison above cannot see at q = 1."""
+    rng = np.random.default_rng(quality * 31 + subsampling)
+    low = rng.integers(0, 256, size=(24, 24, 3), dtype=np.uint8)
+    img = Image.fromarray(low).resize(size, Image.BICUBIC)
+    noise = rng.integers(-12, 13, size=(size[1], size[0], 3))
+    img = Image.fromarray(np.clip(np.asarray(img).astype(np.int16) + noise, 0, 255).astype(np.uint8))
+    b = io.BytesIO()
+    img.save(b, "JPEG", quality=quality, subsampling=subsampling)
+    buf = b.getvalue()
+    dims, quant, y, c = dm.read_coefficients_from_bytes(buf)
+    chroma = (2, 2) if subsampling == 2 else (1, 1)
+    again = dm.write_coefficients(size[0], size[1], y, c, quant, chroma=chroma)
+    a, b2 = _scan_bytes(buf), _scan_bytes(again)
+    assert len(a) == len(b2)
+    assert a == b2
+    # and an independent decoder (libjpeg-turbo through PIL) reads identical pixels from both files
+    assert np.array_equal(np.asarray(Image.open(io.BytesIO(again)).convert("RGB")), np.asarray(Image.open(io.BytesIO(buf)).convert("RGB")))
