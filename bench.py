@@ -166,7 +166,7 @@ def run_ours(args):
     stage = None
     if args.stage == "train":
         from rgb_no_more_b200 import train_step as TS
-        stage = TS.TrainStage(dev, arch=args.arch, batch=B, dtype=args.dtype, world=world, use_graph=not args.no_graph)
+        stage = TS.TrainStage(dev, arch=args.arch, batch=B, dtype=args.dtype, world=world, use_graph=not args.no_graph, rank=rank)
     # K0 writes the operand of the patch projection straight into the train stage's static input buffer
     out_buf = stage.x_static if (stage is not None and out_dtype == torch.bfloat16) else torch.empty((B, 196, 384), dtype=out_dtype, device=dev)
     labels_pool = [torch.randint(0, 1000, (B,), device=dev) for _ in range(N_POOL)]

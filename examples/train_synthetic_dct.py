@@ -59,7 +59,7 @@ def main():
     files, labels = make_dataset(args.files, args.classes, seed=1)
     tf = TF.get_transform("imagenet_dct", "train", ops_list=P.AUGLIST_VITS if args.arch != "vitti" else P.AUGLIST_VITTI,
                           num_ops=2, ops_magnitude=3, dtype=torch.bfloat16, device=dev)
-    stage = TS.TrainStage(dev, arch=args.arch, batch=args.batch, world=world, lr=args.lr, warmup_steps=10, total_steps=args.steps)
+    stage = TS.TrainStage(dev, arch=args.arch, batch=args.batch, world=world, lr=args.lr, warmup_steps=10, total_steps=args.steps, rank=rank)
     fd = FD.JpegFeeder(dev, args.batch)
     torch.manual_seed(11997733 + rank)                         # SEED + rank, like the reference's workers
 

@@ -22,28 +22,37 @@ ARCHS = {"vitti": dict(emb_size=192, depth=12, num_heads=3, wd=1e-4), "vits": di
 
 
 class TrainStage:
+    RING = 8
+
     def __init__(self, device, arch: str = "vits", batch: int = 256, dtype: str = "bf16", world: int = 1, lr: float = 3e-3,
                  warmup_steps: int = 10000, total_steps: int = 112590, mixup_alpha: float = 0.2, use_graph: bool = True,
-                 seed: int = 11997733, attention: str = "auto"):
+                 seed: int = 11997733, attention: str = "auto", rank: int = 0):
         if dtype != "bf16":
             raise NotImplementedError("rgbnm TrainStage: the tcgen05 path computes in bf16 (fp32 accumulation)")
         cfg = ARCHS[arch]
         self.dev = torch.device(device)
         self.B, self.world = batch, world
-        torch.manual_seed(seed)            # same seed on every rank: identical initial replicas, like DDP's broadcast
-        self.model = V.ViT(patch_size=16, emb_size=cfg["emb_size"], depth=cfg["depth"], n_classes=1000, drop_p=0.0,
-                           pixel_space="DCT", ver=1, use_subblock=True, device=self.dev, num_heads=cfg["num_heads"],
-                           head_size=64, attention=attention)
+        # same initial replica on every rank (DDP's broadcast, train.py:137) WITHOUT touching the global RNG streams:
+        # the augmentation plans are drawn from torch's global CPU generator, seeded SEED + rank by the caller (train.py:119)
+        with torch.random.fork_rng(devices=[self.dev] if self.dev.type == "cuda" else []):
+            torch.manual_seed(seed)
+            self.model = V.ViT(patch_size=16, emb_size=cfg["emb_size"], depth=cfg["depth"], n_classes=1000, drop_p=0.0,
+                               pixel_space="DCT", ver=1, use_subblock=True, device=self.dev, num_heads=cfg["num_heads"],
+                               head_size=64, attention=attention)
         self.eng = self.model.prepare(self.dev)
         self.base_lr, self.wd = lr, cfg["wd"]
         self.warmup_steps, self.total_steps = warmup_steps, total_steps
         self.m = torch.zeros_like(self.eng.flat)
         self.v = torch.zeros_like(self.eng.flat)
         self.gnorm = torch.zeros(1, dtype=torch.float32, device=self.dev)
-        self.hyper_host = torch.zeros(9, dtype=torch.float32).pin_memory()
-        self.hyper = torch.zeros(9, dtype=torch.float32, device=self.dev)
-        self.lam_host = torch.zeros(2, dtype=torch.float32).pin_memory()
-        self.lam = torch.zeros(2, dtype=torch.float32, device=self.dev)
+        # per-step scalars (9 optimiser hyper-parameters + 2 mixup weights) travel through a ring of pinned staging
+        # buffers, each guarded by an event recorded after its H2D copy: the host may run many steps ahead of the GPU
+        # (graph replays are asynchronous) and must not rewrite a buffer whose copy is still queued
+        self._scalars_dev = torch.zeros(11, dtype=torch.float32, device=self.dev)
+        self.hyper, self.lam = self._scalars_dev[:9], self._scalars_dev[9:]
+        pin = self.dev.type == "cuda"
+        self._ring = [torch.zeros(11, dtype=torch.float32).pin_memory() if pin else torch.zeros(11) for _ in range(self.RING)]
+        self._ring_ev = [None] * self.RING
         self.mixup_alpha = mixup_alpha
         self.step_no = 0
         self.use_graph = use_graph
@@ -54,11 +63,16 @@ class TrainStage:
         self.y_static = torch.zeros((batch,), dtype=torch.int64, device=self.dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
         self.launches_per_step = 0
-        self._rng = torch.Generator().manual_seed(seed + 17)
+        self._rng = torch.Generator().manual_seed(seed + 17 + rank)     # per-rank mixup stream (reference: SEED + rank)
+        self.lam_override = None                                           # tests: inject (lam, 1 - lam) instead of drawing
 
     # ---- pieces ---------------------------------------------------------------------------------------------
-    def _lr(self, it: int) -> float:
-        # linear warm-up (train.py:150-152) then per-iteration cosine annealing (pipeline_utils.py:538)
+    def _lr(self, step_no: int) -> float:
+        """Learning rate the reference uses for its (0-based) `step_no`-th optimiser step (train.py:149-152, 174-176):
+        `current_itr` is incremented BEFORE use, so it = step_no + 1; warm-up sets LR * (it + 1) / WARMUP while
+        it < WARMUP; from it = WARMUP on the per-iteration CosineAnnealingLR (T_max = maxiters - WARMUP,
+        pipeline_utils.py:538), stepped after the optimiser, has been stepped it - WARMUP times."""
+        it = step_no + 1
         if it < self.warmup_steps:
             return self.base_lr * (it + 1) / self.warmup_steps
         t = (it - self.warmup_steps) / max(1, self.total_steps - self.warmup_steps)
@@ -86,18 +100,25 @@ class TrainStage:
     def _set_hyper(self):
         t = self.step_no + 1
         lr = self._lr(self.step_no)
-        h = self.hyper_host
-        h[0], h[1], h[2], h[3] = lr, 0.9, 0.999, 1e-8
-        h[4], h[5] = 1.0 - 0.9 ** t, 1.0 - 0.999 ** t
-        h[6] = lr / self.base_lr * self.wd
-        # sumsq runs after the SUM allreduce, so the norm and the gradient both carry the factor `world`
-        h[7], h[8] = 1.0 / self.world, 1.0
-        self.hyper.copy_(h, non_blocking=True)
-        lam = torch._sample_dirichlet(torch.tensor([self.mixup_alpha, self.mixup_alpha]), generator=self._rng) \
-            if self.mixup_alpha > 0 else torch.tensor([1.0, 0.0])
-        lam, _ = lam.sort(descending=True)
-        self.lam_host.copy_(lam)
-        self.lam.copy_(self.lam_host, non_blocking=True)
+        if self.lam_override is not None:
+            lam = torch.tensor([float(self.lam_override), 1.0 - float(self.lam_override)])
+        elif self.mixup_alpha > 0:
+            lam = torch._sample_dirichlet(torch.tensor([self.mixup_alpha, self.mixup_alpha]), generator=self._rng)
+            lam, _ = lam.sort(descending=True)
+        else:
+            lam = torch.tensor([1.0, 0.0])
+        # sumsq runs after the SUM allreduce, so the norm and the gradient both carry the factor `world` (h[7])
+        vals = torch.tensor([lr, 0.9, 0.999, 1e-8, 1.0 - 0.9 ** t, 1.0 - 0.999 ** t, lr / self.base_lr * self.wd,
+                             1.0 / self.world, 1.0, float(lam[0]), float(lam[1])], dtype=torch.float32)
+        k = self.step_no % self.RING
+        if self._ring_ev[k] is not None:
+            self._ring_ev[k].synchronize()                 # the copy that last read this staging buffer has completed
+        self._ring[k].copy_(vals)
+        self._scalars_dev.copy_(self._ring[k], non_blocking=True)
+        if self.dev.type == "cuda":
+            if self._ring_ev[k] is None:
+                self._ring_ev[k] = torch.cuda.Event()
+            self._ring_ev[k].record()
 
     # ---- public ---------------------------------------------------------------------------------------------
     def step(self, x: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:

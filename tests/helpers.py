@@ -113,3 +113,27 @@ def golden_swin_inputs(seed, batch=2):
     yf = torch.rand((batch, 1, 32, 32, 8, 8), generator=g) * 2 - 1
     cf = torch.rand((batch, 2, 16, 16, 8, 8), generator=g) * 2 - 1
     return yf, cf
+
+
+def golden_vits_inputs(seed, batch=8):
+    """Inputs of tests/golden/vit_s.npz (tools/make_golden.py::golden_vits_inputs)."""
+    g = torch.Generator().manual_seed(int(seed))
+    decay = torch.rand((8, 8), generator=g).pow(2) * 0.9 + 0.1
+    yf = (torch.rand((batch, 1, 28, 28, 8, 8), generator=g) * 2 - 1) * decay
+    cf = (torch.rand((batch, 2, 14, 14, 8, 8), generator=g) * 2 - 1) * decay
+    return yf, cf
+
+
+VITS_GOLDEN_KEYS = ("patchembed.projection.0.weight", "patchembed.projection.0.bias", "encoder.0.0.fn.eb_mha.qkv.weight",
+                    "encoder.0.0.fn.eb_mha.qkv.bias", "encoder.3.0.fn.eb_mha.projection.weight", "encoder.6.1.fn.eb_ffb.0.weight",
+                    "encoder.6.1.fn.eb_ffb.0.bias", "encoder.11.1.fn.eb_ffb.3.weight", "encoder.11.1.fn.eb_ffb.3.bias",
+                    "encoder.5.0.fn.eb_lrnorm1.weight", "encoder.9.1.fn.eb_lrnorm2.bias", "classhead.ch_lrnorm.weight",
+                    "classhead.ch_linear1.weight", "classhead.ch_linear2.weight", "classhead.ch_linear2.bias")
+
+
+def vits_soft_labels():
+    labels = torch.zeros((8, 1000))
+    for b in range(8):
+        labels[b, (37 * b + 3) % 1000] = 0.75
+        labels[b, (91 * b + 500) % 1000] = 0.25
+    return labels

@@ -146,3 +146,45 @@ def test_equalize_quantised_dc_plane():
     flat = y2.clone()
     flat[0, :, :, 0, 0] = 37
     assert torch.equal(O.equalize(flat), flat)
+
+
+def test_vit_oracle_train_step_matches_reference_loop():
+    """oracle/vit_oracle.py (forward, loss, gradients AND the 3-step optimiser loop: clip -> AdamW -> decoupled decay under
+    the warm-up schedule) against the reference's own classes run by tools/make_golden.py::gen_vit_s (ViT-S, batch 8)."""
+    from oracle import vit_oracle as VO
+    from tests.helpers import seeded_state_dict, golden_vits_inputs, vits_soft_labels, VITS_GOLDEN_KEYS
+    from rgb_no_more_b200 import vit as V
+    torch.set_num_threads(8)
+    g = load("vit_s.npz")
+    shell = V.ViT(patch_size=16, emb_size=384, depth=12, n_classes=1000, drop_p=0.0, num_heads=6, head_size=64,
+                  pixel_space="DCT", ver=1, use_subblock=True)
+    sd = seeded_state_dict(shell)
+    yf, cf = golden_vits_inputs(g["input_seed"])
+    emb_in = O.embed_input(yf, cf)
+    with torch.no_grad():
+        logits = VO.forward_embedded(sd, emb_in)
+    assert np.abs(logits.numpy() - g["logits"]).max() < 2e-4 * max(1.0, np.abs(g["logits"]).max())
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss = torch.nn.CrossEntropyLoss()(VO.forward_embedded(params, emb_in), vits_soft_labels())
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 1e-4
+    for k in VITS_GOLDEN_KEYS:
+        got = params[k].grad.reshape(-1)[:4096].numpy()
+        assert np.abs(got - g["grad:" + k]).max() < 2e-4 * max(1e-3, np.abs(g["grad:" + k]).max()), k
+    # the optimiser loop: same lr trace as train.py:149-152 (it = step + 1 -> LR * (it + 1) / WARMUP)
+    onehot = torch.nn.functional.one_hot(torch.from_numpy(g["train_labels"]), 1000).float()
+    state, losses = {}, []
+    sd = {k: v.clone() for k, v in sd.items()}
+    for s_, l0 in enumerate(g["train_lams"]):
+        l0 = float(l0)
+        x = l0 * emb_in + (1 - l0) * emb_in.roll(1, 0)
+        soft = l0 * onehot + (1 - l0) * onehot.roll(1, 0)
+        losses.append(VO.train_step(sd, x, soft, state, lr=3e-3 * (s_ + 2) / 10, wd=3e-4))
+    assert np.abs(np.array(losses) - g["train_losses"]).max() < 2e-3, (losses, g["train_losses"])
+    init = seeded_state_dict(shell)
+    for k in VITS_GOLDEN_KEYS:
+        ref = g["param3:" + k]
+        d_ref = ref - init[k].reshape(-1)[:4096].numpy()
+        d_got = sd[k].reshape(-1)[:4096].numpy() - init[k].reshape(-1)[:4096].numpy()
+        cos = float((d_ref * d_got).sum() / (np.linalg.norm(d_ref) * np.linalg.norm(d_got) + 1e-30))
+        assert cos > 0.999, (k, cos)         # fp32 both sides; Adam's m / sqrt(v) amplifies last-bit gradient differences near 0

@@ -10,6 +10,7 @@ Vectors:
   pipeline.npz       full get_transform('imagenet_dct', train/test) runs under fixed seeds,
                      with the plans our sampler resolves under the same seeds
   embed_vit.npz      PatchEmbedding_DCT_Group input tensor + ViT-Ti logits  (models/plainvit.py)
+  vit_s.npz          ViT-S (benchmarked config) logits / loss / 15 gradients at batch 8 and 3 steps of the reference's optimiser loop
 """
 from __future__ import annotations
 
@@ -275,9 +276,93 @@ def gen_embed_vit():
     print("embed_vit done; loss", float(loss))
 
 
+def golden_vits_inputs(seed, batch=8):
+    """ToRange'd planes with a natural-ish spectrum (decaying with frequency) so activations are not white noise."""
+    g = torch.Generator().manual_seed(int(seed))
+    decay = torch.rand((8, 8), generator=g).pow(2) * 0.9 + 0.1
+    yf = (torch.rand((batch, 1, 28, 28, 8, 8), generator=g) * 2 - 1) * decay
+    cf = (torch.rand((batch, 2, 14, 14, 8, 8), generator=g) * 2 - 1) * decay
+    return yf, cf
+
+
+def gen_vit_s():
+    """ViT-S (E = 384, 6 heads -- the BENCHMARKED configuration, BASELINE config 3) from the reference's own classes:
+    (i) eval logits + training loss and gradients at batch 8 (plainvit.py:559-612),
+    (ii) three optimiser steps of the reference loop body (train.py:146-176: CE on mixup soft labels, clip_grad_norm_(1),
+         AdamW(wd = 0, eps = 1e-8), custom_optims.WeightDecay on '.weight' names without 'lrnorm', warm-up lr), fp32 CPU,
+         with the mixed inputs / soft labels fixed -> parameters after the 3 steps (slices + norms)."""
+    import utils.custom_optims as coptim
+    torch.set_num_threads(8)
+    yf, cf = golden_vits_inputs(5)
+    out = {"input_seed": np.int64(5), "batch": np.int64(8)}
+    model = pvit.ViT(patch_size=16, emb_size=384, depth=12, n_classes=1000, drop_p=0.0, num_heads=6, head_size=64,
+                     pixel_space="DCT", ver=1, use_subblock=True)
+    model.load_state_dict(seeded_state_dict(model))
+    model.eval()
+    with torch.no_grad():
+        out["logits"] = model(yf, cf).numpy()
+    model.train()
+    labels = torch.zeros((8, 1000))
+    for b in range(8):
+        labels[b, (37 * b + 3) % 1000] = 0.75
+        labels[b, (91 * b + 500) % 1000] = 0.25
+    loss = torch.nn.CrossEntropyLoss()(model(yf, cf), labels)
+    loss.backward()
+    out["loss"] = loss.detach().numpy()
+    keys = ("patchembed.projection.0.weight", "patchembed.projection.0.bias", "encoder.0.0.fn.eb_mha.qkv.weight",
+            "encoder.0.0.fn.eb_mha.qkv.bias", "encoder.3.0.fn.eb_mha.projection.weight", "encoder.6.1.fn.eb_ffb.0.weight",
+            "encoder.6.1.fn.eb_ffb.0.bias", "encoder.11.1.fn.eb_ffb.3.weight", "encoder.11.1.fn.eb_ffb.3.bias",
+            "encoder.5.0.fn.eb_lrnorm1.weight", "encoder.9.1.fn.eb_lrnorm2.bias", "classhead.ch_lrnorm.weight",
+            "classhead.ch_linear1.weight", "classhead.ch_linear2.weight", "classhead.ch_linear2.bias")
+    sdg = dict(model.named_parameters())
+    for k in keys:
+        gk = sdg[k].grad
+        out["gradnorm:" + k] = gk.norm().numpy()
+        out["grad:" + k] = gk.reshape(-1)[:4096].numpy()
+    out["grad_total_norm"] = torch.sqrt(sum((p.grad ** 2).sum() for p in model.parameters())).numpy()
+    # ---- (ii) the reference's optimiser loop body, 3 steps ----------------------------------------------------
+    model.load_state_dict(seeded_state_dict(model))
+    LR, WD, WARMUP = 3e-3, 3e-4, 10
+    optimizer = torch.optim.AdamW(model.parameters(), lr=LR, weight_decay=0, eps=1e-8)
+    weight_decayer = coptim.WeightDecay([p for n, p in model.named_parameters() if (".weight" in n) and ("lrnorm" not in n)],
+                                        lr=LR, weight_decay=WD)
+    lam = [1.0, 0.8, 0.6]                                # step 0 without mixup, then RandomMixup_DCT's convex combination
+    int_labels = torch.tensor([(37 * b + 3) % 1000 for b in range(8)])
+    onehot = torch.nn.functional.one_hot(int_labels, 1000).float()
+    out["train_labels"] = int_labels.numpy()
+    losses, current_itr = [], 0
+    for s_ in range(3):
+        l0 = lam[s_]
+        ym, cm = l0 * yf + (1 - l0) * yf.roll(1, 0), l0 * cf + (1 - l0) * cf.roll(1, 0)     # cls_transforms.py:176-179
+        soft = l0 * onehot + (1 - l0) * onehot.roll(1, 0)
+        optimizer.zero_grad()
+        weight_decayer.zero_grad()
+        current_itr += 1
+        if current_itr < WARMUP:
+            for grp in optimizer.param_groups:
+                grp["lr"] = LR * (current_itr + 1) / WARMUP
+            for gs, gd in zip(optimizer.param_groups, weight_decayer.param_groups):
+                gd["lr"] = gs["lr"]
+        ls = torch.nn.CrossEntropyLoss()(model(ym, cm), soft)
+        ls.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1)
+        optimizer.step()
+        weight_decayer.step()
+        losses.append(float(ls))
+    out["train_lams"] = np.array(lam)
+    out["train_losses"] = np.array(losses)
+    init = seeded_state_dict(model)
+    for k in keys:
+        pk = sdg[k].detach()
+        out["param3:" + k] = pk.reshape(-1)[:4096].numpy()
+        out["delta3norm:" + k] = (pk - init[k]).norm().numpy()
+    np.savez_compressed(os.path.join(OUT, "vit_s.npz"), **out)
+    print("vit_s done; loss", float(loss), "train losses", losses)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    todo = sys.argv[1:] or ["ops_small", "ops_extra", "resize", "pipeline", "embed_vit"]
+    todo = sys.argv[1:] or ["ops_small", "ops_extra", "resize", "pipeline", "embed_vit", "vit_s"]
     for name in todo:
         globals()["gen_" + name]()
     for f in sorted(os.listdir(OUT)):
