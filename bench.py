@@ -394,6 +394,8 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         line["host_decode"] = host_decode_rate()
         line["cpu_baseline"] = cpu_baseline(args)
+        if stage is not None:
+            line["torch_b200_baseline"] = torch_b200_baseline(args)
     print(json.dumps(line))
 
 
@@ -573,7 +575,7 @@ def cpu_baseline(args):
     """Our arm's `cpu_baseline`: the reference arm below, run once in a fresh process (this one already holds a CUDA
     context and a warm torch thread pool -- forking it is not safe) on a smaller sample."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1", "--arch", args.arch,
-           "--cpu-sample", str(args.cpu_sample)]
+           "--cpu-sample", str(args.cpu_sample if args.cpu_sample > 0 else 64), "--cpu-budget-s", "30"]
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         env.pop(k, None)
@@ -585,23 +587,72 @@ def cpu_baseline(args):
 
 
 def run_reference(args):
+    """Reference arm.  With oracle/_ref staged (oracle/make_ref.py, run by build() in the container that has /root/reference)
+    this is the REFERENCE ITSELF on the host cores: its DataLoader workers (decode -> dequantise -> DCT transforms), its
+    RandomMixup_DCT, its pvit.ViT, its optimiser objects (oracle/ref_arm.py lists what is its and what is ours); same arch,
+    same RandAugment setting and -- when `steps + warmup` such steps fit ~4 minutes on this host -- the same 256-image batch
+    as our arm.  Without oracle/_ref: the oracle port, as in round 1."""
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = args.cpu_sample
-    sec, t_data, t_model = cpu_train_steps(args, n, cores, args.steps, args.warmup)
+    from oracle import ref_arm as RA
+    if RA.available() and not args.port:
+        want = args.cpu_sample if args.cpu_sample > 0 else args.batch
+        n = RA.calibrate_images_per_step(args.arch, cores, want, args.steps + args.warmup, args.cpu_budget_s)
+        r = RA.cpu_train_arm(args.arch, n, args.steps, args.warmup, cores)
+        sec, kind = r["sec_per_step"], "reference"
+        sample = (f"{n} images per step ({'the full batch of our arm' if n == args.batch else f'bounded sample; our arm: {args.batch}'}) "
+                  f"of the same workload ({args.arch} DCT train step, RandAugment num_ops=2 magnitude=9): the reference's own "
+                  f"datasets.dataset_selector DataLoader with {cores} worker processes (JPEG files -> dct_manip.read_coefficients [this "
+                  f"repo's host decoder: the reference's needs jpeglib.h] -> dequantise -> get_transform('imagenet_dct','train')), "
+                  f"RandomMixup_DCT, models.plainvit.ViT + CrossEntropyLoss + clip + AdamW + WeightDecay in fp32 (reference default "
+                  f"AMP off) on {cores} torch threads; loader wait {r['sec_loader_wait'] * 1e3:.0f} ms + model step {r['sec_model'] * 1e3:.0f} ms")
+        workload = (f"reference CPU path (oracle/_ref: the reference's own Python) of the {args.arch} DCT train step from JPEG files, "
+                    f"{n} images/step, RandAugment num_ops=2 magnitude=9")
+        same = n == args.batch
+    else:
+        n = args.cpu_sample if args.cpu_sample > 0 else 32
+        sec, t_data, t_model = cpu_train_steps(args, n, cores, args.steps, args.warmup)
+        kind, sample, same = "port", _cpu_desc(args, n, cores, t_data, t_model), False
+        workload = (f"reference CPU path (oracle port) of the {args.arch} DCT train step, bounded sample of {n} "
+                    f"images/step (our arm: batch {args.batch}/GPU), RandAugment num_ops=2 magnitude=9")
     val = n / sec
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"reference CPU path (oracle port) of the {args.arch} DCT train step, bounded sample of {n} "
-                                   f"images/step (our arm: batch {args.batch}/GPU), RandAugment num_ops=2 magnitude=9",
-                       "cpu_model": _cpu_model()},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": _cpu_desc(args, n, cores, t_data, t_model)},
+            "config": {"workload": workload, "cpu_model": _cpu_model(), "same_config": same, "images_per_step": n},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def run_torch_b200(args):
+    """PyTorch-on-B200 baseline: the reference's own model classes under eager PyTorch."""
+    from oracle import ref_arm as RA
+    if not RA.available():
+        print(json.dumps({"impl": "torch_b200", "unavailable": "oracle/_ref not staged"}))
+        return
+    out = RA.torch_b200_arm(args.arch, args.batch, max(3, args.steps), max(3, args.warmup))
+    out["impl"] = "torch_b200"
+    print(json.dumps(out))
+
+
+def torch_b200_baseline(args):
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "torch_b200", "--steps", "5", "--warmup", "3", "--arch", args.arch,
+           "--batch", str(args.batch)]
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+        for line in reversed(out.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"error": out.stderr[-300:]}
+    except Exception as ex:  # noqa: BLE001 -- a side measurement must never cost the headline line
+        return {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
 
 def _cpu_model():
@@ -620,13 +671,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_b200"])
+    ap.add_argument("--port", action="store_true", help="reference arm: force the oracle port even if oracle/_ref is staged")
+    ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="reference arm: wall-clock budget of all CPU steps")
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--arch", default="vits")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--stage", default="auto", choices=["auto", "k0", "train"])
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly (for ncu launch lists)")
-    ap.add_argument("--cpu-sample", type=int, default=32, help="images per CPU step of the reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images per CPU step of the reference arm (0: the full batch if it fits the budget)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-swin", action="store_true", help="skip the SwinV2-T eval-forward side measurement")
     args = ap.parse_args()
@@ -635,6 +688,8 @@ def main():
         args.stage = "train" if os.path.exists(os.path.join(ROOT, "rgb_no_more_b200", "train_step.py")) else "k0"
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_b200":
+        run_torch_b200(args)
     else:
         run_ours(args)
 

@@ -1,0 +1,3 @@
+"""`import dct_manip` (datasets.py:10, utils/custom_transforms.py:7 of the reference) -> the B200 repository's host decoder.
+Same return contract as dct_manip.cpp:152-178 / :578-606; see INTEGRATION.md section 1."""
+from rgb_no_more_b200.dct_manip import decode_batch, read_coefficients, read_coefficients_from_bytes, write_coefficients  # noqa: F401

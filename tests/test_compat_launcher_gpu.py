@@ -1,0 +1,55 @@
+"""Boundary B4 on the GPU: the REFERENCE's train.py (CLI, config, DDP wrap, loop, evaluation, checkpoint, final save) driven by
+`python -m rgb_no_more_b200.compat.launch --backend b200` on synthetic 512x512 JPEG files: `--domain dct --model_arch vits`,
+one epoch of 3 optimiser steps + minival / train-val / test evaluation, B200 loaders + B200 model behind the reference's seams."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "train.py")), reason="oracle/_ref not staged (oracle/make_ref.py)")
+def test_reference_train_py_runs_on_the_b200_backend(tmp_path):
+    from rgb_no_more_b200 import synth
+    data = tmp_path / "data"
+    data.mkdir()
+    n_files, rows = 16, 120
+    for i in range(n_files):
+        (data / f"img_{i}.JPEG").write_bytes(synth.synth_jpeg(i))
+    for name in ("train", "val"):
+        with open(tmp_path / f"index_{name}.csv", "w") as f:
+            f.write("Filepath,Label\n")
+            for r in range(rows if name == "train" else 40):
+                f.write(f"img_{r % n_files}.JPEG,{r % 8}\n")
+    save = tmp_path / "out" / "model.pth"
+    save.parent.mkdir()
+    cmd = [sys.executable, "-m", "rgb_no_more_b200.compat.launch", "--ref", REF, "--backend", "b200", "--",
+           "--train", "--eval", "--domain", "dct", "--embed_type", "1", "--model_arch", "vits", "--batch", "40", "--epochs", "1",
+           "--warmup_steps", "2", "--num_gpus", "1", "--num_cpus", "4", "--no_extract", "--no_resize", "--temp_datapath", str(data),
+           "--indexpaths", f"{tmp_path / 'index_train.csv'},{tmp_path / 'index_val.csv'}", "--savepath", str(save), "--verbose", "1",
+           "--port", str(_free_port()), "--num_ops", "2", "--ops_magnitude", "9"]
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, env=env, cwd=str(tmp_path))
+    log = r.stdout + r.stderr
+    assert r.returncode == 0, log[-4000:]
+    assert "rgbnm B200 backend: ViT (vits)" in log, log[-3000:]                 # the opt-in took effect in the spawned rank
+    assert "Training complete" in log and "Test Acc" in log, log[-3000:]
+    sd = torch.load(save, map_location="cpu")
+    assert len(sd) == 152 and sd["encoder.0.0.fn.eb_mha.qkv.weight"].shape == (1152, 384)     # reference key set (plainvit.py)
+    assert all(torch.isfinite(v).all() for v in sd.values())
+    ckpts = [p for p in os.listdir(save.parent) if p != "model.pth" and p.endswith(".pth")]
+    assert ckpts, os.listdir(save.parent)                                       # per-epoch checkpoint written by the reference loop

@@ -81,9 +81,22 @@ def test_golden_pipeline_cases():
             # no resize: bit exact against the reference's own output
             assert np.array_equal(oy[0].numpy(), g[f"case{k}_y"]) and np.array_equal(oc[0].numpy(), g[f"case{k}_c"]), (k, names)
         else:
-            # direct comparison: everything except tie flips (and what a DC op makes of them) is identical
-            assert float((oy[0].numpy() != g[f"case{k}_y"]).mean()) < 0.12, (k, names)
-            assert float((oc[0].numpy() != g[f"case{k}_c"]).mean()) < 0.12, (k, names)
+            # x2 up / x2 down: the direct comparison with the reference's own output is split where the reference rounds:
+            # (a) K0's resized planes vs the reference's planes right after RandomResizedCrop_DCT: one LSB, only on float64 ties
+            pl = plans[k]
+            ry, rc = _run_planes(tf, y, c, q, [_resize_only(pl)])
+            xy, xc = O.resized_planes_exact(*_views(y, c, q, 0), pl)
+            assert_only_tie_mismatches(ry[0].numpy(), g[f"case{k}_ry"], xy.numpy(), (k, "Y"))
+            assert_only_tie_mismatches(rc[0].numpy(), g[f"case{k}_rc"], xc.numpy(), (k, "CbCr"))
+            # (b) flip + RandAugment ops: the REFERENCE's resized planes fed through K0 in identity geometry (28 x 28 block
+            #     "image", unit tables) must give the reference's final planes bit for bit -- so every mismatch of the
+            #     end-to-end output traces back to a tie of (a), not to a fraction of tolerated differences
+            y28 = torch.from_numpy(g[f"case{k}_ry"]).reshape(1, 28, 28, 64)
+            c28 = torch.from_numpy(g[f"case{k}_rc"]).reshape(1, 2, 14, 14, 64)
+            ident = P.Plan(crop_i=0, crop_j=0, crop_size=28, flip=pl.flip, train=pl.train, ops=pl.ops)
+            fy, fc = _run_planes(tf, y28, c28, torch.ones((1, 3, 64), dtype=torch.int16), [ident])
+            assert np.array_equal(fy[0].numpy(), g[f"case{k}_y"]), (k, names, lsb_report(fy[0].numpy(), g[f"case{k}_y"]))
+            assert np.array_equal(fc[0].numpy(), g[f"case{k}_c"]), (k, names, lsb_report(fc[0].numpy(), g[f"case{k}_c"]))
 
 
 def _random_batch(B, seed, dense):

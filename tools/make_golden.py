@@ -208,6 +208,12 @@ def gen_pipeline():
         pl = P.sample_train_plan(64, 64, list(ops), 2, mag, bank)
         k = len(cases)
         out[f"case{k}_y"], out[f"case{k}_c"] = ry.numpy(), rc.numpy()
+        # the reference's planes right after RandomResizedCrop_DCT (first transform = first RNG draws): the GPU test feeds
+        # them back through K0 in identity geometry, so flip + RandAugment are checked bit-exactly against the
+        # reference's own final output in the resize cases too
+        torch.manual_seed(seed)
+        iy, ic = ctrans.RandomResizedCrop_DCT(28, scale=(0.05, 1.0), ratio=(1, 1))((y, c))
+        out[f"case{k}_ry"], out[f"case{k}_rc"] = iy.numpy(), ic.numpy()
         cases.append((img, seed, mag))
         plans.append(pl)
         print(f"  case {k}: img {img} seed {seed} crop {pl.crop_i},{pl.crop_j},{pl.crop_size} flip {pl.flip} ops "
