@@ -10,7 +10,6 @@
 Everything else of the reference (CLI, config, optimiser construction, loop, evaluation, checkpoints, tensorboard) runs as is."""
 from __future__ import annotations
 
-import logging
 import os
 
 import torch
@@ -42,7 +41,8 @@ def get_model(cfg, report=True):
     model.prepare(torch.device("cuda", cfg.RANK) if isinstance(cfg.RANK, int) else cfg.RANK)   # flat buffers BEFORE DDP wraps it
     if cfg.RANK == 0 and report:
         n = sum(p.numel() for p in model.parameters())
-        logging.info(f"rgbnm B200 backend: {type(model).__name__} ({cfg.MODEL.ARCH}), {n:,} parameters, dataset {cfg.TRAIN.DATASET}")
+        # print, not logging: the reference configures logging in the parent only (train.py:236), spawned ranks log nothing below WARNING
+        print(f"rgbnm B200 backend: {type(model).__name__} ({cfg.MODEL.ARCH}), {n:,} parameters, dataset {cfg.TRAIN.DATASET}", flush=True)
     return model
 
 

@@ -86,13 +86,16 @@ def test_golden_pipeline_cases():
             pl = plans[k]
             ry, rc = _run_planes(tf, y, c, q, [_resize_only(pl)])
             xy, xc = O.resized_planes_exact(*_views(y, c, q, 0), pl)
-            assert_only_tie_mismatches(ry[0].numpy(), g[f"case{k}_ry"], xy.numpy(), (k, "Y"))
-            assert_only_tie_mismatches(rc[0].numpy(), g[f"case{k}_rc"], xc.numpy(), (k, "CbCr"))
+            # (eval cases hold no ops: their final planes ARE the resized planes)
+            g_ry = g[f"case{k}_ry"] if f"case{k}_ry" in g.files else g[f"case{k}_y"]
+            g_rc = g[f"case{k}_rc"] if f"case{k}_rc" in g.files else g[f"case{k}_c"]
+            assert_only_tie_mismatches(ry[0].numpy(), g_ry, xy.numpy(), (k, "Y"))
+            assert_only_tie_mismatches(rc[0].numpy(), g_rc, xc.numpy(), (k, "CbCr"))
             # (b) flip + RandAugment ops: the REFERENCE's resized planes fed through K0 in identity geometry (28 x 28 block
             #     "image", unit tables) must give the reference's final planes bit for bit -- so every mismatch of the
             #     end-to-end output traces back to a tie of (a), not to a fraction of tolerated differences
-            y28 = torch.from_numpy(g[f"case{k}_ry"]).reshape(1, 28, 28, 64)
-            c28 = torch.from_numpy(g[f"case{k}_rc"]).reshape(1, 2, 14, 14, 64)
+            y28 = torch.from_numpy(g_ry).reshape(1, 28, 28, 64)
+            c28 = torch.from_numpy(g_rc).reshape(1, 2, 14, 14, 64)
             ident = P.Plan(crop_i=0, crop_j=0, crop_size=28, flip=pl.flip, train=pl.train, ops=pl.ops)
             fy, fc = _run_planes(tf, y28, c28, torch.ones((1, 3, 64), dtype=torch.int16), [ident])
             assert np.array_equal(fy[0].numpy(), g[f"case{k}_y"]), (k, names, lsb_report(fy[0].numpy(), g[f"case{k}_y"]))
