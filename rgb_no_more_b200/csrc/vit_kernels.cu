@@ -331,9 +331,14 @@ __global__ void unperm_rows_add_kernel(const float* __restrict__ src, float* __r
 // ------------------------------------------------------------------------------------------
 // sum of squares (gradient norm) and the fused optimiser step
 // ------------------------------------------------------------------------------------------
+// Deterministic: per-block partial sums go to a scratch array, the block that finishes last adds them up in index order.  The
+// result feeds the clip factor of the optimiser step, which every data-parallel replica must evaluate to the SAME bits from the
+// same all-reduced gradient -- an atomicAdd per block (arrival order) let replicas drift apart by an ulp per step
+// (tests/test_ddp_gpu.py).
 __global__ void __launch_bounds__(256)
-sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out, float* __restrict__ partial, unsigned* __restrict__ counter) {
     __shared__ float red[8];
+    __shared__ bool last;
     float s = 0.0f;
     const size_t n4 = n / 4;
     const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -348,7 +353,24 @@ sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
     if (threadIdx.x == 0) {
         float t = 0.0f;
         for (int k = 0; k < 8; ++k) t += red[k];
-        atomicAdd(out, t);
+        partial[blockIdx.x] = t;
+        __threadfence();
+        last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // fixed-shape tree over the partials: thread t sums partial[t], partial[t + 256], ... in order, then the block reduces
+    float t = 0.0f;
+    for (unsigned k = threadIdx.x; k < gridDim.x; k += 256) t += __ldcg(partial + k);
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.0f;
+        for (int k = 0; k < 8; ++k) tot += red[k];
+        *out += tot;
+        *counter = 0;              // ready for the next launch on this stream
     }
 }
 
@@ -513,7 +535,20 @@ int rgbnm_sumsq_f32(const float* g, long long n, float* out, void* stream) {
     if (n == 0) return RGBNM_OK;
     long long blocks = (n / 4 + 255) / 256;
     const int grid = int(blocks < 1 ? 1 : (blocks > vitk::sms() * 8 ? vitk::sms() * 8 : blocks));
-    vitk::sumsq_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, size_t(n), out);
+    // per-device scratch (partials + arrival counter), allocated on first use -- i.e. during the warm-up steps that precede any
+    // CUDA-graph capture; launches that share it must be stream-ordered (one optimiser step at a time per device)
+    static float* scratch[64] = {nullptr};
+    int dev = 0;
+    RGBNM_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return RGBNM_ERR_ARG;
+    if (scratch[dev] == nullptr) {
+        const size_t bytes = (size_t(vitk::sms()) * 8 + 1) * sizeof(float);
+        RGBNM_CUDA_CHECK(cudaMalloc(&scratch[dev], bytes));
+        RGBNM_CUDA_CHECK(cudaMemset(scratch[dev], 0, bytes));
+    }
+    float* partial = scratch[dev] + 1;
+    unsigned* counter = reinterpret_cast<unsigned*>(scratch[dev]);
+    vitk::sumsq_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, size_t(n), out, partial, counter);
     RGBNM_CUDA_CHECK(cudaGetLastError());
     return RGBNM_OK;
 }

@@ -37,5 +37,11 @@ def allreduce_flat(flat_grad: torch.Tensor, world: int) -> float:
     """SUM all-reduce of the flat gradient buffer in place; returns the factor the optimiser must apply (1 / world)."""
     if world > 1:
         import torch.distributed as dist
-        dist.all_reduce(flat_grad)
+        if flat_grad.is_cuda and dist.get_backend() != "nccl":
+            # gloo (CPU tests, single-GPU multi-rank tests): stage through the host; the product path is NCCL over NVLink
+            host = flat_grad.cpu()
+            dist.all_reduce(host)
+            flat_grad.copy_(host)
+        else:
+            dist.all_reduce(flat_grad)
     return 1.0 / world

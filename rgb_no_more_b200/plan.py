@@ -440,3 +440,132 @@ def pack_plans(plans: Sequence[Plan], clamp_in: Optional[Sequence[bool]] = None,
         for k, op in enumerate(pl.ops):
             _PLAN_OP.pack_into(buf, base + _PLAN_HEAD.size + k * _PLAN_OP.size, op.code, *[int(v) for v in op.p], 0, float(op.f))
     return np.frombuffer(buf, dtype=PLAN_DTYPE).copy()
+
+
+# --------------------------------------------------------------------------
+# Batched sampler: the same DISTRIBUTION as `sample_train_plan`, a whole batch per call
+# --------------------------------------------------------------------------
+_CHROMAS = ("Grayscale", "Color", "AutoSaturation", "ChromaDrop")
+_STATS_CODES = (OP_BRIGHTNESS, OP_AUTOCONTRAST, OP_AUTOSATURATION, OP_EQUALIZE, OP_SOLARIZE)
+
+
+class BatchedSampler:
+    """Draws `n` training plans at once and returns them PACKED (`struct rgbnm_plan[n]`, the array `FusedDCT.run` takes).
+
+    `sample_train_plan` replays the reference's torch-global-RNG call sequence image by image (the RNG contract of SURVEY.md
+    8a: seed-for-seed identical plans, ~60 us of Python per image -- as much host time per batch as the GPU step takes).  This
+    sampler draws from the same distributions -- RandomResizedCrop_DCT (custom_transforms.py:580-629), RandomFlip_DCT (:934),
+    RandAugment_dct incl. the chroma-op exclusion rules and the op-internal draws (:944-1021, 1109-1124) -- but takes all
+    uniforms of a batch from one `torch.Generator` call and resolves them with numpy, ~0.3 ms per 256 images.  The STREAM
+    differs from the reference's (same seed -> different but identically distributed plans); parity tests use the per-image
+    sampler, throughput paths (bench from-JPEG arm, compat loader) this one."""
+
+    def __init__(self, height: int, width: int, ops_list: Optional[Sequence[str]], num_ops: int, magnitude_bin: int,
+                 bank: FilterBank, size: int = 28, num_bins: int = 11, scale=(0.05, 1.0)):
+        if ops_list is None:
+            raise NotImplementedError("rgbnm: the batched sampler needs an explicit DCT ops_list")
+        if len(ops_list) > 0 and num_ops > MAX_OPS:
+            raise ValueError(f"rgbnm: num_ops={num_ops} exceeds plan capacity {MAX_OPS}")
+        self.h, self.w, self.size, self.scale = height, width, size, scale
+        self.num_ops = num_ops if len(ops_list) > 0 else 0
+        self.train = len(ops_list) > 0
+        choices = _even_choices(size)
+        vmax = int(round(math.sqrt(height * width))) + 2
+        # crop side for every possible rounded sqrt(target area): the scalar rule, tabulated
+        self.side_of = np.array([max(2, _choose_closest(v, choices, width)) for v in range(vmax + 1)], dtype=np.int64)
+        if self.side_of.max() > min(height, width):
+            raise NotImplementedError("rgbnm: batched sampler expects crops that always fit (square inputs)")
+        allowed = SUPPORTED_CROPS[size]
+        lo = int(round(math.sqrt(height * width * scale[0])))
+        if any(int(s) not in allowed for s in self.side_of[lo:]):
+            raise ValueError(f"rgbnm: a {height}x{width}-block input can draw crop sides outside {allowed}")
+        # the three op lists RandAugment_dct can be in (full -> minus Grayscale after a chroma op / minus all chroma ops after Grayscale)
+        full = list(ops_list)
+        for name in full:
+            if name in UNSUPPORTED_OPS:
+                raise NotImplementedError(f"rgbnm: DCT op '{name}' is outside the B200 hot path (SURVEY.md 8a row a21)")
+            if name not in OP_NAMES:
+                raise ValueError(f"The provided operator {name} is not recognized.")
+        self.lists = [full, [o for o in full if o != "Grayscale"], [o for o in full if o not in _CHROMAS]]
+        meta = _augmentation_space(num_bins, (size, size))
+        self.names = full
+        idx = {n: i for i, n in enumerate(full)}
+        self.list_idx = [np.array([idx[o] for o in lst], dtype=np.int64) for lst in self.lists]
+        # per (op, sign) template of the resolved op; Cutout / ChromaDrop parameters are filled from their own draws
+        k = len(full)
+        self.t_code = np.zeros(k, dtype=np.int16)
+        self.t_signed = np.zeros(k, dtype=bool)
+        self.t_p = np.zeros((k, 2, 8), dtype=np.int16)
+        self.t_f = np.zeros((k, 2), dtype=np.float32)
+        self.cut_size = np.zeros(k, dtype=np.int64)
+        state = torch.random.get_rng_state()
+        for i, name in enumerate(full):
+            mags, signed = meta[name]
+            mag = mags[magnitude_bin] if isinstance(mags, list) else mags
+            self.t_signed[i] = signed
+            for s, m in enumerate((mag, -1.0 * mag)):
+                op = resolve_op(name, m, size, bank)          # Cutout / ChromaDrop draw here: state restored below
+                self.t_code[i] = op.code
+                self.t_p[i, s] = op.p
+                self.t_f[i, s] = op.f
+            if OP_NAMES[name] == OP_CUTOUT:
+                sz = round(mag)
+                self.cut_size[i] = int(sz - (sz % 2))
+        torch.random.set_rng_state(state)
+        self.is_chroma = np.array([n in _CHROMAS for n in full])
+        self.is_gray = np.array([n == "Grayscale" for n in full])
+        self.needs = np.isin(self.t_code, np.array(_STATS_CODES, dtype=np.int16))
+
+    def sample(self, n: int, clamp_in=None, generator: Optional[torch.Generator] = None) -> np.ndarray:
+        """-> packed PLAN_DTYPE array of n plans.  `generator`: a CPU torch.Generator (default: the global one)."""
+        K = self.num_ops
+        u = torch.rand((n, 4 + 5 * max(K, 1)), dtype=torch.float64, generator=generator).numpy()
+        out = np.zeros(n, dtype=PLAN_DTYPE)
+        area = self.h * self.w
+        target = area * (self.scale[0] + (self.scale[1] - self.scale[0]) * u[:, 0])
+        side = self.side_of[np.rint(np.sqrt(target)).astype(np.int64)]
+        out["crop_size"] = side
+        out["crop_i"] = np.floor(u[:, 1] * (self.h - side + 1)).astype(np.int64) // 2 * 2
+        out["crop_j"] = np.floor(u[:, 2] * (self.w - side + 1)).astype(np.int64) // 2 * 2
+        out["flip"] = u[:, 3] <= 0.5
+        out["train"] = int(self.train)
+        out["n_ops"] = K
+        out["clamp_in"] = 1 if clamp_in is None else np.asarray(clamp_in).astype(np.int16)
+        state = np.zeros(n, dtype=np.int64)                     # index into self.lists
+        needs = np.zeros(n, dtype=bool)
+        G = self.size
+        for k in range(K):
+            c = u[:, 4 + 5 * k: 9 + 5 * k]
+            lens = np.array([len(x) for x in self.list_idx])[state]
+            pick = np.minimum((c[:, 0] * lens).astype(np.int64), lens - 1)
+            op = np.empty(n, dtype=np.int64)
+            for s in range(3):
+                m = state == s
+                if m.any():
+                    op[m] = self.list_idx[s][pick[m]]
+            sign = (self.t_signed[op] & (c[:, 1] >= 0.5)).astype(np.int64)       # torch.randint(2): 1 -> negative magnitude
+            code = self.t_code[op]
+            p = self.t_p[op, sign].copy()
+            f = self.t_f[op, sign]
+            cut = code == OP_CUTOUT
+            if cut.any():
+                # dct_ops.py:796-807 via cutout_rect: centre = randint(0, G) // 2 * 2 per axis, rows mirrored about the image
+                ch = np.floor(c[cut, 2] * G).astype(np.int64) // 2 * 2
+                cw = np.floor(c[cut, 3] * G).astype(np.int64) // 2 * 2
+                sz = self.cut_size[op[cut]]
+                for col0, (cen_h, cen_w, sze, H) in ((0, (ch, cw, sz, G)), (4, (ch // 2, cw // 2, sz // 2, G // 2))):
+                    p[cut, col0 + 0] = np.maximum(0, H - cen_h - sze)
+                    p[cut, col0 + 1] = H - np.maximum(0, cen_h - sze)
+                    p[cut, col0 + 2] = np.maximum(0, cen_w - sze)
+                    p[cut, col0 + 3] = H - np.maximum(0, H - cen_w - sze)
+            drop = code == OP_CHROMADROP
+            if drop.any():
+                p[drop, 0] = np.where(c[drop, 4] > 0.5, 0, 1)
+            out["ops"]["code"][:, k] = code
+            out["ops"]["p"][:, k] = p
+            out["ops"]["f"][:, k] = f
+            needs |= self.needs[op]
+            gray, chroma = self.is_gray[op], self.is_chroma[op]
+            state = np.where(gray, 2, np.where(chroma & (state == 0), 1, state))
+        out["needs_stats"] = needs
+        return out

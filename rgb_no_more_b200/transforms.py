@@ -58,6 +58,7 @@ class FusedDCT:
         self._lut = torch.from_numpy(P.posterize_lut()).to(self.device)
         self._tables = _lib.K0Tables()
         self._eq_lut = None
+        self._stats = None
         self._sync_tables()
 
     # -- tables ---------------------------------------------------------------------------
@@ -79,9 +80,11 @@ class FusedDCT:
     # -- launch ---------------------------------------------------------------------------
     def run(self, y_q: torch.Tensor, c_q: torch.Tensor, quant: torch.Tensor, plans, clamp_in=None,
             out_mode: Optional[int] = None, out: Optional[torch.Tensor] = None,
-            plans_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+            plans_dev: Optional[torch.Tensor] = None, needs_stats: Optional[bool] = None) -> torch.Tensor:
         """y_q int16 [B,hb,wb,64] (or [B,1,hb,wb,8,8]), c_q int16 [B,2,hb/2,wb/2,64], quant int16 [B,3,64],
-        all on `device`.  `plans`: list[Plan] or packed numpy array (or pass `plans_dev`)."""
+        all on `device`.  `plans`: list[Plan] or packed numpy array (or pass `plans_dev`).
+        `needs_stats=False` (known on the host: no plan of the batch holds a statistics op, e.g. the eval transform) skips the
+        DC-statistics pre-pass launch; None = decide from `plans` when they are given as a list, else launch it."""
         B = y_q.shape[0]
         if y_q.dim() == 6:
             hb, wb = y_q.shape[2], y_q.shape[3]
@@ -92,6 +95,9 @@ class FusedDCT:
                 raise ValueError("rgbnm: coefficient tensors must be contiguous int16 on the transform's device")
         if c_q.numel() != B * 2 * (hb // 2) * (wb // 2) * 64 or quant.numel() != B * 192:
             raise ValueError("rgbnm: coefficient batch shapes are inconsistent (4:2:0 layout expected)")
+        if needs_stats is None:
+            needs_stats = (self.kind == "train") if (plans_dev is not None or isinstance(plans, np.ndarray)) \
+                else any(pl.needs_stats for pl in plans)
         if plans_dev is None:
             if not isinstance(plans, np.ndarray):
                 for pl in plans:
@@ -110,14 +116,19 @@ class FusedDCT:
             else:
                 out = torch.empty((B, self.tokens, self.feat), dtype=torch.bfloat16 if out_mode == OUT_BF16 else torch.float32,
                                   device=self.device)
-        stats = torch.zeros((B, P.MAX_OPS, 2), dtype=torch.float32, device=self.device)
+        # scratch of the statistics pre-pass: persistent (no allocation / memset per call).  Every slot the fused kernel reads
+        # (ops of plans with needs_stats) is rewritten by the pre-pass of the same call.
+        if self._stats is None or self._stats.shape[0] < B:
+            self._stats = torch.zeros((B, P.MAX_OPS, 2), dtype=torch.float32, device=self.device)
+        stats = self._stats
         if self._eq_lut is None or self._eq_lut.shape[0] < B:      # scratch of the Equalize op (per image and op slot)
             self._eq_lut = torch.empty((B, P.MAX_OPS, 2048), dtype=torch.int16, device=self.device)
         self._tables.equalize_lut = self._eq_lut.data_ptr()
         st = _lib.stream_ptr()
         L = self._lib
-        _lib.check(L.rgbnm_k0_dcstats_ex(y_q.data_ptr(), c_q.data_ptr(), quant.data_ptr(), plans_dev.data_ptr(),
-                                         C.byref(self._tables), stats.data_ptr(), B, hb, wb, self.layout, st), "rgbnm_k0_dcstats")
+        if needs_stats:
+            _lib.check(L.rgbnm_k0_dcstats_ex(y_q.data_ptr(), c_q.data_ptr(), quant.data_ptr(), plans_dev.data_ptr(),
+                                             C.byref(self._tables), stats.data_ptr(), B, hb, wb, self.layout, st), "rgbnm_k0_dcstats")
         _lib.check(L.rgbnm_k0_fused_ex(y_q.data_ptr(), c_q.data_ptr(), quant.data_ptr(), plans_dev.data_ptr(),
                                        C.byref(self._tables), stats.data_ptr(), out.data_ptr(), out_mode, self.layout, B, hb, wb, st),
                    "rgbnm_k0_fused")

@@ -52,5 +52,5 @@ def test_reference_train_py_runs_on_the_b200_backend(tmp_path):
     sd = torch.load(save, map_location="cpu")
     assert len(sd) == 152 and sd["encoder.0.0.fn.eb_mha.qkv.weight"].shape == (1152, 384)     # reference key set (plainvit.py)
     assert all(torch.isfinite(v).all() for v in sd.values())
-    ckpts = [p for p in os.listdir(save.parent) if p != "model.pth" and p.endswith(".pth")]
-    assert ckpts, os.listdir(save.parent)                                       # per-epoch checkpoint written by the reference loop
+    ckdir = save.parent / "checkpoints"                                         # per-epoch checkpoint written by the reference loop
+    assert ckdir.is_dir() and os.listdir(ckdir), os.listdir(save.parent)
