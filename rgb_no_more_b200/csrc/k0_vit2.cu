@@ -37,8 +37,8 @@ namespace k0v2 {
 using namespace k0;
 
 typedef unsigned long long p2;            // packed pair: token 0 in the low word, token 1 in the high word
-constexpr int WARPS = 4;                  // warps per CTA (independent: no block-level barrier)
-constexpr int CTAS_PER_SM = 5;            // 20 resident warps / SM: shared memory 5 x (4 x 11,344 + 1 KB) <= 228 KB
+constexpr int WARPS = 5;                  // warps per CTA (independent: no block-level barrier)
+constexpr int CTAS_PER_SM = 4;            // 20 resident warps / SM: shared memory 4 x (5 x 11,440 + 1 KB) <= 228 KB
 constexpr int PITCH = 144;                // tile row pitch in bytes (16 pairs + 2 pad)
 constexpr int TILE_B = 32 * PITCH;        // bytes per tile (32 rows: the x2-down row pass produces 16 rows per block row)
 constexpr int QROW_B = 80;                // fp32 table row: [q0..q7 | cq0..cq7 | 16 B pad] -> the 8 rows of a table sit on distinct bank groups
@@ -50,10 +50,11 @@ struct __align__(16) WarpSmem {
     unsigned char T[2 * TILE_B];      // tile of pair p at T + p * TILE_B: rows of 16 p2 (+ pad), row-major
     unsigned char qt[24 * QROW_B];    // per (component, coefficient row): q[8] and cq[8] = -(2^23 + 2^15) * q (dequantisation bias)
     rgbnm_plan plan;
-    int info[24];                     // per block of the quad: source block index, child flags, zeroing op (pack_info)
+    int info[2][24];                  // per block of the quad: source block index, child flags, zeroing op (pack_info); two slots:
+                                      // the next quad's blocks are traced (and its first loads issued) before this quad ends
 };
 static_assert(sizeof(WarpSmem) % 16 == 0, "warp slices must stay 16-byte aligned");
-static_assert(CTAS_PER_SM * (WARPS * sizeof(WarpSmem) + 1024) <= 228 * 1024, "five CTAs per SM must fit");
+static_assert(CTAS_PER_SM * (WARPS * sizeof(WarpSmem) + 1024) <= 228 * 1024, "the resident CTAs of an SM must fit");
 
 // ---- packed fp32x2 primitives: both halves IEEE round-to-nearest, like the scalar operators they replace ------------------
 __device__ __forceinline__ p2 pk(float lo, float hi) { p2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
@@ -176,9 +177,10 @@ __device__ __forceinline__ int4 ldg128(const unsigned char* base, uint32_t off) 
 // per-lane constants of the passes (bits of the lane id -> shared-window addresses), set up once per warp
 struct LaneK {
     uint32_t T;          // tile 0
-    uint32_t rst;        // row-pass store, luma (all modes) / chroma x2-down: T + (bit3 * 8 + i8) * PITCH + bit4 * 64
-    uint32_t rst_c;      // row-pass store, chroma identity / x2-up, and chroma read-out: T + bit4 * TILE_B + i8 * PITCH + bit3 * 64
-    uint32_t ccol;       // column-pass / P2b column: T + bit4 * TILE_B + (lane & 15) * 8
+    // tile columns are stored interleaved: column c (0..7) of half h (block column / chroma component) sits in slot 2c + h
+    uint32_t rst;        // row-pass store, luma (all modes) / chroma x2-down: T + (bit3 * 8 + i8) * PITCH + bit4 * 8, columns at + 16 k
+    uint32_t rst_c;      // row-pass store, chroma identity / x2-up: T + bit4 * TILE_B + i8 * PITCH + bit3 * 8 (also the chroma read-out base)
+    uint32_t ccol;       // column-pass / P2b column: T + bit4 * TILE_B + slot(lane & 15) * 8
     uint32_t prow;       // P3 row: T + bit4 * TILE_B + (lane & 15) * PITCH
     uint32_t qrow;       // table row of the lane's coefficient row: qt + i8 * QROW_B
     uint32_t info;       // info[0]
@@ -198,16 +200,18 @@ __device__ __forceinline__ void load_q(uint32_t qrow, float (&q)[8], float (&cq)
 struct RowLoads {
     int4 l0, r0, l1, r1;
 };
-__device__ __forceinline__ RowLoads r_down2_load(const LaneK& K, int lane, const unsigned char* __restrict__ plane, int wbytes, int b0,
+__device__ __forceinline__ RowLoads r_down2_load(uint32_t info, int lane, const unsigned char* __restrict__ plane, int wbytes, int b0,
                                                  int tok_stride) {
     const uint32_t lc = ((lane >> 3) & 1) * wbytes + (lane & 7) * 16;
-    const uint32_t ia = K.info + 4 * (b0 + (lane >> 4));
+    const uint32_t ia = info + 4 * (b0 + (lane >> 4));
     const uint32_t o0 = (uint32_t(lds32(ia)) & 0xffffu) * 128u + lc, o1 = (uint32_t(lds32(ia + 4 * tok_stride)) & 0xffffu) * 128u + lc;
+    const int4* p0 = reinterpret_cast<const int4*>(plane + o0);        // right-hand block of the pair = + 128 bytes: immediate offset
+    const int4* p1 = reinterpret_cast<const int4*>(plane + o1);
     RowLoads L;
-    L.l0 = ldg128(plane, o0);
-    L.r0 = ldg128(plane, o0 + 128);
-    L.l1 = ldg128(plane, o1);
-    L.r1 = ldg128(plane, o1 + 128);
+    L.l0 = __ldg(p0);
+    L.r0 = __ldg(p0 + 8);
+    L.l1 = __ldg(p1);
+    L.r1 = __ldg(p1 + 8);
     return L;
 }
 __device__ __forceinline__ void r_down2_compute(const RowLoads& L, uint32_t qrow, uint32_t dst, bool clamp) {
@@ -217,21 +221,26 @@ __device__ __forceinline__ void r_down2_compute(const RowLoads& L, uint32_t qrow
     dequant8_p(L.l0, L.l1, q, cq, clamp, xl);
     dequant8_p(L.r0, L.r1, q, cq, clamp, xr);
     down2_1d_p<1, 1>(xl, xr, o);
+    // 8-byte stores into every other slot (tile columns are interleaved: slot 2k + half): a lane never writes both halves of a
+    // 16-byte chunk, so ptxas cannot fuse stores into STS.128 -- which needs four consecutive registers and costs two moves per
+    // pair -- and the wavefront count is the same (rows r and r + 8 of a half-warp share banks: 2 x 8 wavefronts either way)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) sts128(dst + 16 * k, o[2 * k], o[2 * k + 1]);
+    for (int k = 0; k < 8; ++k) sts64(dst + 16 * k, o[k]);
 }
 
 // identity / x2-up: one lane item = row i8 of one block pair (tokens 0 / 1)
-__device__ __forceinline__ void r_small_load(const LaneK& K, int lane, const unsigned char* __restrict__ plane, int b0, int tok_stride,
-                                             int4& a0, int4& a1, int& inf0, int& inf1) {
-    inf0 = lds32(K.info + 4 * b0);
-    inf1 = lds32(K.info + 4 * (b0 + tok_stride));
+__device__ __forceinline__ void r_small_load(uint32_t info, int lane, const unsigned char* __restrict__ plane, int b0, int tok_stride,
+                                             int4& a0, int4& a1) {
+    const int inf0 = lds32(info + 4 * b0), inf1 = lds32(info + 4 * (b0 + tok_stride));
     const uint32_t lc = (lane & 7) * 16;
     a0 = ldg128(plane, (uint32_t(inf0) & 0xffffu) * 128u + lc);
     a1 = ldg128(plane, (uint32_t(inf1) & 0xffffu) * 128u + lc);
 }
 template <int MODE>
-__device__ __forceinline__ void r_small_compute(const int4& a0, const int4& a1, int inf0, int inf1, uint32_t qrow, uint32_t dst, bool clamp) {
+__device__ __forceinline__ void r_small_compute(const int4& a0, const int4& a1, uint32_t info, int b0, int tok_stride, uint32_t qrow,
+                                                uint32_t dst, bool clamp) {
+    int inf0 = 0, inf1 = 0;
+    if (MODE == MODE_UP2) { inf0 = lds32(info + 4 * b0); inf1 = lds32(info + 4 * (b0 + tok_stride)); }
     float q[8], cq[8];
     load_q(qrow, q, cq);
     p2 x[8];
@@ -240,10 +249,10 @@ __device__ __forceinline__ void r_small_compute(const int4& a0, const int4& a1, 
         p2 o[8];
         up2_1d_p<1>(x, (inf0 >> 17) & 1, (inf1 >> 17) & 1, o);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) sts128(dst + 16 * k, o[2 * k], o[2 * k + 1]);
+        for (int k = 0; k < 8; ++k) sts64(dst + 16 * k, o[k]);
     } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) sts128(dst + 16 * k, x[2 * k], x[2 * k + 1]);
+        for (int k = 0; k < 8; ++k) sts64(dst + 16 * k, x[k]);
     }
 }
 
@@ -368,15 +377,11 @@ __device__ __forceinline__ unsigned bf2(float a, float b) {
     return *reinterpret_cast<unsigned*>(&t);
 }
 
-// ---- one quad -------------------------------------------------------------------------------------------------------------------
-template <int OUT_MODE>
-__device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int lane, int img, int tr, int tp, int mode,
-                                             const unsigned char* __restrict__ y_img, const unsigned char* __restrict__ c_img,
-                                             const rgbnm_k0_tables& tb, const float* __restrict__ stats, void* __restrict__ out_, int wb,
-                                             int hc, int wc) {
+// ---- block bookkeeping of one quad: lanes 0..23 trace one block each into info slot `slot`
+//      (block id = p*12 + [luma: tok*4 + bi*2 + bj | chroma: 8 + tok*2 + comp-1]) ------------------------------------------------
+__device__ __forceinline__ void trace_quad(WarpSmem& ws, int lane, int tr, int tp, int mode, int wb, int wc, int slot,
+                                           const unsigned char* __restrict__ y_img, const unsigned char* __restrict__ c_img, size_t hcwc128) {
     const rgbnm_plan& pl = ws.plan;
-    const bool clamp = pl.clamp_in != 0;
-    // ---- block bookkeeping: lanes 0..23 trace one block each (block id = p*12 + [luma: tok*4 + bi*2 + bj | chroma: 8 + tok*2 + comp-1])
     if (lane < 24) {
         const int p = lane >= 12, bb = lane - 12 * p;
         int comp, r, c;
@@ -396,36 +401,67 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
         if (mode == MODE_DOWN2) { sr = ci + 2 * t.r; sc = cj + 2 * t.c; }
         else if (mode == MODE_IDENT) { sr = ci + t.r; sc = cj + t.c; }
         else { sr = ci + (t.r >> 1); sc = cj + (t.c >> 1); chr = t.r & 1; chc = t.c & 1; }
-        ws.info[lane] = pack_info(sr * (comp == 0 ? wb : wc) + sc, chr, chc, t.zero);
+        const int W = comp == 0 ? wb : wc;
+        ws.info[slot][lane] = pack_info(sr * W + sc, chr, chc, t.zero);
+        // pull the block's source rows into L2 now (they are loaded a quad later): one line per source block
+        const unsigned char* src = (comp == 0 ? y_img : c_img + size_t(comp - 1) * hcwc128) + size_t(sr * W + sc) * 128;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+        if (mode == MODE_DOWN2) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 128));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + size_t(W) * 128));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + size_t(W) * 128 + 128));
+        }
     }
-    __syncwarp();
+}
 
+// first luma loads of a quad (x2-down: round (pair 0, block row 0); else the single round of both pairs: A.l0 / A.l1 = pair 0
+// tokens 0 / 1, A.r0 / A.r1 = pair 1).  16 registers: what can be carried through the chroma column pass without spilling.
+__device__ __forceinline__ void luma_first_loads(uint32_t info, int lane, const unsigned char* __restrict__ y_img, int wb, int mode,
+                                                 RowLoads& A) {
+    if (mode == MODE_DOWN2) {
+        A = r_down2_load(info, lane, y_img, wb * 128, 0, 4);
+    } else {
+        const int b3 = (lane >> 3) & 1, b4 = lane >> 4;          // lane = (row i8, block row b3, block column b4)
+        r_small_load(info, lane, y_img, b3 * 2 + b4, 4, A.l0, A.l1);
+        r_small_load(info, lane, y_img, 12 + b3 * 2 + b4, 4, A.r0, A.r1);
+    }
+}
+
+// ---- one quad -------------------------------------------------------------------------------------------------------------------
+// MODE_T >= 0 / NOCLAMP_T: compile-time resize case / "dequantisation clamp proven idle" (the x2-down, no-clamp instance is the
+// hot one in both the eval geometry and the training mix); MODE_T = -1: everything decided at run time.
+// On entry info slot `slot` is traced and A holds the quad's first luma loads; if `has_next`, the next quad (ntr, ntp) of the
+// same image is traced into the other slot and its first loads are issued into A before the chroma column pass, so that they
+// are in flight during the tail of this quad.
+template <int OUT_MODE, int MODE_T, bool NOCLAMP_T>
+__device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int lane, int img, int tr, int tp, int mode_rt,
+                                             const unsigned char* __restrict__ y_img, const unsigned char* __restrict__ c_img,
+                                             const rgbnm_k0_tables& tb, const float* __restrict__ stats, void* __restrict__ out_, int wb,
+                                             int hc, int wc, RowLoads& A, int slot, bool has_next, int ntr, int ntp) {
+    const rgbnm_plan& pl = ws.plan;
+    const int mode = MODE_T >= 0 ? MODE_T : mode_rt;
+    const bool clamp = NOCLAMP_T ? false : (pl.clamp_in != 0);
+    const uint32_t info = K.info + slot * 96;
     const int b3 = (lane >> 3) & 1, b4 = lane >> 4;
+    // the next quad is traced first: its source lines travel to L2 while this quad computes (its slot is read after the chroma row pass)
+    if (has_next) trace_quad(ws, lane, ntr, ntp, mode, wb, wc, slot ^ 1, y_img, c_img, size_t(hc) * wc * 128);
     // ---- R, luma ----------------------------------------------------------------------------------------------------------------
     if (mode == MODE_DOWN2) {
         // rounds (pair, block row) = (0,0) (0,1) (1,0) (1,1); the loads of round r+2 are issued as round r is consumed
         const int wbytes = wb * 128;
-        RowLoads A = r_down2_load(K, lane, y_img, wbytes, 0, 4);
-        RowLoads B = r_down2_load(K, lane, y_img, wbytes, 2, 4);
+        RowLoads B = r_down2_load(info, lane, y_img, wbytes, 2, 4);
         r_down2_compute(A, K.qrow, K.rst, clamp);
-        A = r_down2_load(K, lane, y_img, wbytes, 12, 4);
+        A = r_down2_load(info, lane, y_img, wbytes, 12, 4);
         r_down2_compute(B, K.qrow, K.rst + 16 * PITCH, clamp);
-        B = r_down2_load(K, lane, y_img, wbytes, 14, 4);
+        B = r_down2_load(info, lane, y_img, wbytes, 14, 4);
         r_down2_compute(A, K.qrow, K.rst + TILE_B, clamp);
         r_down2_compute(B, K.qrow, K.rst + TILE_B + 16 * PITCH, clamp);
+    } else if (mode == MODE_UP2) {
+        r_small_compute<MODE_UP2>(A.l0, A.l1, info, b3 * 2 + b4, 4, K.qrow, K.rst, clamp);
+        r_small_compute<MODE_UP2>(A.r0, A.r1, info, 12 + b3 * 2 + b4, 4, K.qrow, K.rst + TILE_B, clamp);
     } else {
-        // lane = (row i8, block row b3, block column b4) of pair 0, then of pair 1
-        int4 a0, a1, c0, c1;
-        int ia0, ia1, ic0, ic1;
-        r_small_load(K, lane, y_img, b3 * 2 + b4, 4, a0, a1, ia0, ia1);
-        r_small_load(K, lane, y_img, 12 + b3 * 2 + b4, 4, c0, c1, ic0, ic1);
-        if (mode == MODE_UP2) {
-            r_small_compute<MODE_UP2>(a0, a1, ia0, ia1, K.qrow, K.rst, clamp);
-            r_small_compute<MODE_UP2>(c0, c1, ic0, ic1, K.qrow, K.rst + TILE_B, clamp);
-        } else {
-            r_small_compute<MODE_IDENT>(a0, a1, ia0, ia1, K.qrow, K.rst, clamp);
-            r_small_compute<MODE_IDENT>(c0, c1, ic0, ic1, K.qrow, K.rst + TILE_B, clamp);
-        }
+        r_small_compute<MODE_IDENT>(A.l0, A.l1, info, b3 * 2 + b4, 4, K.qrow, K.rst, clamp);
+        r_small_compute<MODE_IDENT>(A.r0, A.r1, info, 12 + b3 * 2 + b4, 4, K.qrow, K.rst + TILE_B, clamp);
     }
     __syncwarp();
 
@@ -453,8 +489,8 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
                     p2 xl[8], xr[8], o[16];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        lds128(K.prow + 16 * j, xl[2 * j], xl[2 * j + 1]);
-                        lds128(K.prow + 64 + 16 * j, xr[2 * j], xr[2 * j + 1]);
+                        lds128(K.prow + 32 * j, xl[2 * j], xr[2 * j]);              // slots (2c, 2c + 1) = columns (c, c + 8)
+                        lds128(K.prow + 32 * j + 16, xl[2 * j + 1], xr[2 * j + 1]);
                     }
                     a16_1d_p(xl, xr, o);
                     const size_t off = (size_t(img) * TOKENS + (2 * tr + p) * 14 + 2 * tp) * FEAT + c16 * 16;
@@ -484,26 +520,27 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
             if (mode == MODE_DOWN2) {
                 // lane bit 4 = component (the block-column `half` of r_down2_*); chroma block ids 8 + tok*2 + (comp-1), token stride 2
                 const unsigned char* plane = c_img + size_t(b4) * hc * wc * 128;
-                const RowLoads A = r_down2_load(K, lane, plane, wc * 128, 8, 2);
-                const RowLoads B = r_down2_load(K, lane, plane, wc * 128, 20, 2);
+                const RowLoads CA = r_down2_load(info, lane, plane, wc * 128, 8, 2);
+                const RowLoads CB = r_down2_load(info, lane, plane, wc * 128, 20, 2);
                 const uint32_t qr = K.qrow + (1 + b4) * 8 * QROW_B;
-                r_down2_compute(A, qr, K.rst, clamp);
-                r_down2_compute(B, qr, K.rst + TILE_B, clamp);
+                r_down2_compute(CA, qr, K.rst, clamp);
+                r_down2_compute(CB, qr, K.rst + TILE_B, clamp);
             } else {
                 // lane = (row i8, component b3, pair b4)
                 const unsigned char* plane = c_img + size_t(b3) * hc * wc * 128;
                 int4 a0, a1;
-                int ia0, ia1;
-                r_small_load(K, lane, plane, b4 * 12 + 8 + b3, 2, a0, a1, ia0, ia1);
+                r_small_load(info, lane, plane, b4 * 12 + 8 + b3, 2, a0, a1);
                 const uint32_t qr = K.qrow + (1 + b3) * 8 * QROW_B;
-                if (mode == MODE_UP2) r_small_compute<MODE_UP2>(a0, a1, ia0, ia1, qr, K.rst_c, clamp);
-                else r_small_compute<MODE_IDENT>(a0, a1, ia0, ia1, qr, K.rst_c, clamp);
+                if (mode == MODE_UP2) r_small_compute<MODE_UP2>(a0, a1, info, b4 * 12 + 8 + b3, 2, qr, K.rst_c, clamp);
+                else r_small_compute<MODE_IDENT>(a0, a1, info, b4 * 12 + 8 + b3, 2, qr, K.rst_c, clamp);
             }
             __syncwarp();
+            // the next quad's first luma loads: in flight during the chroma column pass and read-out of this one
+            if (has_next) luma_first_loads(K.info + (slot ^ 1) * 96, lane, y_img, wb, mode, A);
         }
         // ---- the column pass proper ----------------------------------------------------------------------------------------
         const int b0 = p * 12 + (k < 2 ? k * 2 + half : 8 + half);
-        const int inf0 = lds32(K.info + 4 * b0), inf1 = lds32(K.info + 4 * (b0 + (k < 2 ? 4 : 2)));
+        const int inf0 = lds32(info + 4 * b0), inf1 = lds32(info + 4 * (b0 + (k < 2 ? 4 : 2)));
         const int z0 = ((inf0 >> 18) & 7) - 1, z1 = ((inf1 >> 18) & 7) - 1;
         const int comp = k < 2 ? 0 : 1 + half;
         p2 v[8];
@@ -548,37 +585,35 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
                 }
             }
         } else {
-            // S tile rows (k*8 ..) of pair p, columns half*8 ..: element (i, c), or (c, i) for a transposed block
-            const uint32_t S = K.ccol - c * 8 + (k < 2 ? k * 8 : 0) * PITCH;
-            if (!Tf) {
+            // S tile rows (k*8 ..) of pair p, slots 2 * column + half: element (i, c), or (c, i) for a transposed block -- one
+            // store sequence with a run-time stride (two branches made ptxas copy every pair into a fixed register pair)
+            const uint32_t S = K.ccol - c * 16 + (k < 2 ? k * 8 : 0) * PITCH + c * (Tf ? PITCH : 16);
+            const uint32_t stride = Tf ? 16 : PITCH;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) sts64(S + i * PITCH + c * 8, to_range2(v[i]));
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) sts64(S + c * PITCH + i * 8, to_range2(v[i]));
-            }
+            for (int i = 0; i < 8; ++i) sts64(S + i * stride, to_range2(v[i]));
         }
     }
     __syncwarp();
     if (OUT_MODE == RGBNM_K0_OUT_INT16_PLANES) return;
 
-    // ---- chroma out: lane = (pair p = b4, component b3, block row i8) ----------------------------------------------------------
+    // ---- chroma out: lane = (pair p = b4, block row i8, column group b3): 16-byte loads give (Cb, Cr) of 4 columns -----------------
     {
-        p2 a, b, c4, d, e, f, g, h;
-        lds128(K.rst_c, a, b);
-        lds128(K.rst_c + 16, c4, d);
-        lds128(K.rst_c + 32, e, f);
-        lds128(K.rst_c + 48, g, h);
-        const size_t off = (size_t(img) * TOKENS + (2 * tr + p) * 14 + 2 * tp) * FEAT + 256 + b3 * 64 + (lane & 7) * 8;
+        p2 cb[4], cr[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) lds128(K.rst_c - b3 * 8 + b3 * 64 + 16 * m, cb[m], cr[m]);     // row i8, slots 8 b3 + 2m, + 1
+        const size_t off = (size_t(img) * TOKENS + (2 * tr + p) * 14 + 2 * tp) * FEAT + 256 + (lane & 7) * 8 + b3 * 4;
         if (OUT_MODE == RGBNM_K0_OUT_F32) {
-            float4* d0 = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_) + off);
-            float4* d1 = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_) + off + FEAT);
-            d0[0] = make_float4(lo_of(a), lo_of(b), lo_of(c4), lo_of(d)); d0[1] = make_float4(lo_of(e), lo_of(f), lo_of(g), lo_of(h));
-            d1[0] = make_float4(hi_of(a), hi_of(b), hi_of(c4), hi_of(d)); d1[1] = make_float4(hi_of(e), hi_of(f), hi_of(g), hi_of(h));
+            float* o = reinterpret_cast<float*>(out_) + off;
+            *reinterpret_cast<float4*>(o) = make_float4(lo_of(cb[0]), lo_of(cb[1]), lo_of(cb[2]), lo_of(cb[3]));
+            *reinterpret_cast<float4*>(o + 64) = make_float4(lo_of(cr[0]), lo_of(cr[1]), lo_of(cr[2]), lo_of(cr[3]));
+            *reinterpret_cast<float4*>(o + FEAT) = make_float4(hi_of(cb[0]), hi_of(cb[1]), hi_of(cb[2]), hi_of(cb[3]));
+            *reinterpret_cast<float4*>(o + FEAT + 64) = make_float4(hi_of(cr[0]), hi_of(cr[1]), hi_of(cr[2]), hi_of(cr[3]));
         } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_);
-            *reinterpret_cast<uint4*>(o + off) = make_uint4(bf2(lo_of(a), lo_of(b)), bf2(lo_of(c4), lo_of(d)), bf2(lo_of(e), lo_of(f)), bf2(lo_of(g), lo_of(h)));
-            *reinterpret_cast<uint4*>(o + off + FEAT) = make_uint4(bf2(hi_of(a), hi_of(b)), bf2(hi_of(c4), hi_of(d)), bf2(hi_of(e), hi_of(f)), bf2(hi_of(g), hi_of(h)));
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_) + off;
+            *reinterpret_cast<uint2*>(o) = make_uint2(bf2(lo_of(cb[0]), lo_of(cb[1])), bf2(lo_of(cb[2]), lo_of(cb[3])));
+            *reinterpret_cast<uint2*>(o + 64) = make_uint2(bf2(lo_of(cr[0]), lo_of(cr[1])), bf2(lo_of(cr[2]), lo_of(cr[3])));
+            *reinterpret_cast<uint2*>(o + FEAT) = make_uint2(bf2(hi_of(cb[0]), hi_of(cb[1])), bf2(hi_of(cb[2]), hi_of(cb[3])));
+            *reinterpret_cast<uint2*>(o + FEAT + 64) = make_uint2(bf2(hi_of(cr[0]), hi_of(cr[1])), bf2(hi_of(cr[2]), hi_of(cr[3])));
         }
     }
     __syncwarp();
@@ -597,9 +632,9 @@ k0_vit2_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, 
         const uint32_t base = uint32_t(__cvta_generic_to_shared(smem_raw)) + warp * uint32_t(sizeof(WarpSmem));
         const int i8 = lane & 7, b3 = (lane >> 3) & 1, b4 = lane >> 4;
         K.T = base;
-        K.rst = base + (b3 * 8 + i8) * PITCH + b4 * 64;
-        K.rst_c = base + b4 * TILE_B + i8 * PITCH + b3 * 64;
-        K.ccol = base + b4 * TILE_B + (lane & 15) * 8;
+        K.rst = base + (b3 * 8 + i8) * PITCH + b4 * 8;
+        K.rst_c = base + b4 * TILE_B + i8 * PITCH + b3 * 8;
+        K.ccol = base + b4 * TILE_B + (2 * (lane & 7) + b3) * 8;          // slot of tile column lane & 15
         K.prow = base + b4 * TILE_B + (lane & 15) * PITCH;
         K.qrow = base + uint32_t(offsetof(WarpSmem, qt)) + i8 * QROW_B;
         K.info = base + uint32_t(offsetof(WarpSmem, info));
@@ -608,7 +643,10 @@ k0_vit2_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, 
     const long long gw = (long long)blockIdx.x * WARPS + warp, tw = (long long)gridDim.x * WARPS;
     const int q_begin = int(gw * nq / tw), q_end = int((gw + 1) * nq / tw);
     const int hc = hb >> 1, wc = wb >> 1;
-    int cur = -1, mode = MODE_BAD;
+    int cur = -1, mode = MODE_BAD, slot = 0;
+    bool pre = false;                   // info slot `slot` traced and A loaded by the previous quad
+    RowLoads A;
+    A.l0 = A.r0 = A.l1 = A.r1 = make_int4(0, 0, 0, 0);
     for (int q = q_begin; q < q_end; ++q) {
         const int img = q / QUADS_PER_IMAGE, rem = q - img * QUADS_PER_IMAGE;
         if (img != cur) {
@@ -624,12 +662,28 @@ k0_vit2_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, 
             __syncwarp();
             cur = img;
             mode = mode_of(ws.plan.crop_size, GRID_Y);
+            pre = false;
         }
         if (mode == MODE_BAD) continue;
         const int tr = rem / 7, tp = rem - tr * 7;
-        process_quad<OUT_MODE>(ws, K, lane, img, tr, tp, mode, reinterpret_cast<const unsigned char*>(y + size_t(img) * hb * wb * 64),
-                               reinterpret_cast<const unsigned char*>(cbcr + size_t(img) * 2 * hc * wc * 64), tb,
-                               stats_all + size_t(img) * RGBNM_MAX_OPS * 2, out_, wb, hc, wc);
+        const unsigned char* y_img = reinterpret_cast<const unsigned char*>(y + size_t(img) * hb * wb * 64);
+        const unsigned char* c_img = reinterpret_cast<const unsigned char*>(cbcr + size_t(img) * 2 * hc * wc * 64);
+        if (!pre) {
+            trace_quad(ws, lane, tr, tp, mode, wb, wc, slot, y_img, c_img, size_t(hc) * wc * 128);
+            __syncwarp();
+            luma_first_loads(K.info + slot * 96, lane, y_img, wb, mode, A);
+        }
+        const bool has_next = (q + 1 < q_end) && (rem + 1 < QUADS_PER_IMAGE);
+        const int nrem = rem + 1, ntr = nrem / 7, ntp = nrem - ntr * 7;
+        const float* stats = stats_all + size_t(img) * RGBNM_MAX_OPS * 2;
+        if (OUT_MODE != RGBNM_K0_OUT_INT16_PLANES && mode == MODE_DOWN2 && ws.plan.clamp_in == 0)
+            process_quad<OUT_MODE, MODE_DOWN2, true>(ws, K, lane, img, tr, tp, mode, y_img, c_img, tb, stats, out_, wb, hc, wc, A, slot,
+                                                     has_next, ntr, ntp);
+        else
+            process_quad<OUT_MODE, -1, false>(ws, K, lane, img, tr, tp, mode, y_img, c_img, tb, stats, out_, wb, hc, wc, A, slot,
+                                              has_next, ntr, ntp);
+        pre = has_next;
+        if (has_next) slot ^= 1;
     }
 }
 

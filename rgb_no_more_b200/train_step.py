@@ -45,6 +45,9 @@ class TrainStage:
         self.m = torch.zeros_like(self.eng.flat)
         self.v = torch.zeros_like(self.eng.flat)
         self.gnorm = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        if self.dev.type == "cuda":
+            K.sumsq(self.eng.flat_grad, self.gnorm)        # first call allocates the reduction scratch: must not happen under graph capture
+            self.gnorm.zero_()
         # per-step scalars (9 optimiser hyper-parameters + 2 mixup weights) travel through a ring of pinned staging
         # buffers, each guarded by an event recorded after its H2D copy: the host may run many steps ahead of the GPU
         # (graph replays are asynchronous) and must not rewrite a buffer whose copy is still queued
