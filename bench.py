@@ -30,9 +30,22 @@ import torch  # noqa: E402
 METRIC = "images/sec (512x512 JPEG, ViT-S DCT) at 1/2/4/8 B200; DCT-aug+embed HBM GB/s"
 UNIT = "images/s"
 N_POOL = 4          # distinct input batches cycled through (4 x 201 MB >> 126 MB L2)
-K0_NCU_TRAFFIC_BYTES = 98580992
-K0_NCU_TRAFFIC_SOURCE = "profiles/r01_step_v2_k0ncu_launches.txt (85.2 MB read + 13.3 MB written; replays partly hit L2)"
+K0_NCU_FILES = {"train": "profiles/r02_k0_v2_train_ncu.txt", "eval": "profiles/r02_k0_v2_eval_ncu.txt"}
 VIT_TRAIN_GFLOP_PER_IMAGE = {"vits": 27.28, "vitti": 7.40}      # dense GEMM + attention MACs x 2, fwd + bwd
+
+
+def k0_ncu_traffic(kind: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE K0 launch (batch 256) from the committed `ncu --set full` summary of the
+    current kernel (tools/ncu_summary.py writes the `traffic(dram read+write) = N bytes` line) -- read from the file, not a constant."""
+    path = os.path.join(ROOT, K0_NCU_FILES[kind])
+    try:
+        with open(path) as f:
+            for ln in f:
+                if ln.strip().startswith("traffic(dram read+write)"):
+                    return int(float(ln.split("=")[1].split()[0])), K0_NCU_FILES[kind]
+    except OSError:
+        pass
+    return None, K0_NCU_FILES[kind] + " (missing)"
 
 
 def peaks():
@@ -255,25 +268,36 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed_loop(step_e2e, args.steps, args.warmup)
 
-    # ---- from JPEG bytes: host Huffman decode (all cores) -> pinned ring -> copy stream -> K0 -> step ------------------
+    # ---- from JPEG bytes: host Huffman decode -> pinned ring -> copy stream -> K0 -> step, at ANY world size -------------------
+    # Every rank decodes its own batches with cpu_count // world host threads (the reference gives each rank num_cpus // world_size
+    # DataLoader workers, pipeline_utils.py:125) and draws fresh augmentation plans for every batch INSIDE the timed region
+    # (plan.BatchedSampler: same distributions as the per-image sampler, one vectorised draw per batch).
     e2e_jpeg = None
-    if world == 1 and not args.no_cpu and stage is not None:
+    if not args.no_cpu and stage is not None:
         from rgb_no_more_b200 import feeder as FD, synth
-        jpegs = synth.synth_jpeg_set(B)
-        fd = FD.JpegFeeder(dev, B, 64, 64, slots=3)
-        fd.submit(jpegs)
-        y0, c0, q0, fl0, s0 = fd.get()
-        fd.release(s0)
-        jplans = torch.from_numpy(P.pack_plans(plan_pool[0], fl0).view(np.uint8).reshape(B, -1).copy()).to(dev)
+        n_threads = max(1, (os.cpu_count() or 1) // world)
+        jpegs = synth.synth_jpeg_set(min(B, 64))
+        jpegs = (jpegs * (B // len(jpegs) + 1))[:B]
+        fd = FD.JpegFeeder(dev, B, 64, 64, slots=3, nthreads=n_threads)
+        sampler_b = P.BatchedSampler(64, 64, P.AUGLIST_VITS, 2, 9, tf.bank)
+        plan_host = [torch.empty((B, P.PLAN_DTYPE.itemsize), dtype=torch.uint8).pin_memory() for _ in range(3)]
+        plan_dev = [torch.empty((B, P.PLAN_DTYPE.itemsize), dtype=torch.uint8, device=dev) for _ in range(3)]
+        gen = torch.Generator().manual_seed(11997733 + rank)
 
         def step_jpeg(i):
             while len(fd.pending) < 2:
                 fd.submit(jpegs)                      # decode of the next batches overlaps this step
-            yj, cj, qj, _, slot = fd.get()
-            x = tf.run(yj, cj, qj, None, plans_dev=jplans, out=out_buf)
+            yj, cj, qj, flags, slot = fd.get()
+            k = i % 3
+            packed = sampler_b.sample(B, clamp_in=flags, generator=gen)
+            plan_host[k].copy_(torch.from_numpy(packed.view(np.uint8).reshape(B, -1)))
+            plan_dev[k].copy_(plan_host[k], non_blocking=True)
+            x = tf.run(yj, cj, qj, None, plans_dev=plan_dev[k], out=out_buf)
             fd.release(slot)
             res = stage.step(x, labels_pool[i % N_POOL])
             result_host.copy_(res.reshape(-1)[:1].float(), non_blocking=True)
+            if i % 3 == 2:
+                torch.cuda.current_stream().synchronize()      # the pinned plan buffers are reused every 3 steps
 
         n_j = max(args.steps // 2, 5)
         ms_jpeg = timed_loop(step_jpeg, n_j, 3)
@@ -282,10 +306,12 @@ def run_ours(args):
             fd.release(slot)
         torch.cuda.synchronize()
         fd.close()
-        e2e_jpeg = {"value": B / (ms_jpeg / n_j * 1e-3), "unit": UNIT, "jpeg_bytes_per_step": int(sum(len(j) for j in jpegs)),
-                    "h2d_bytes_per_step": int(fd.h2d_bytes), "host_cores": os.cpu_count() or 1,
-                    "what": "same step fed from JPEG byte strings: rgbnm_jpeg_decode_batch on the host cores into a pinned ring, "
-                            "copy stream, K0, train step; decode of the next batches overlaps the GPU"}
+        e2e_jpeg = {"value": B * world / (ms_jpeg / n_j * 1e-3), "unit": UNIT, "jpeg_bytes_per_step": int(sum(len(j) for j in jpegs)),
+                    "h2d_bytes_per_step": int(fd.h2d_bytes) + B * P.PLAN_DTYPE.itemsize, "host_cores": os.cpu_count() or 1,
+                    "decode_threads_per_rank": n_threads, "n_gpus": world,
+                    "what": "whole job fed from JPEG byte strings: every rank runs rgbnm_jpeg_decode_batch on cpu_count // world host "
+                            "threads into a pinned ring, copy stream, fresh plans per batch (BatchedSampler, inside the timed region), "
+                            "K0, train step; decode of the next batches overlaps the GPU"}
 
     # K0 kernel(s) alone: average over the timed region (events on the launching stream)
     k0_avg_ms = float(np.mean([a.elapsed_time(b) for a, b in k0_ms[-args.steps:]]))
@@ -370,10 +396,12 @@ def run_ours(args):
                      "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s",
                      "frac": alg / (k0_avg_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                      # dram__bytes_read.sum + dram__bytes_write.sum of one train-mix launch (ncu --set full, batch 256)
-                     "traffic": K0_NCU_TRAFFIC_BYTES if B == 256 else None, "traffic_source": K0_NCU_TRAFFIC_SOURCE,
+                     "traffic": k0_ncu_traffic("train")[0] if B == 256 else None, "traffic_source": k0_ncu_traffic("train")[1],
                      "algorithmic_bytes_per_launch": alg, "kernel_ms": k0_avg_ms},
         "roofline_eval_geometry": {"bound": "hbm", "achieved": alg_eval / (ms_eval * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                                    "unit": "GB/s", "frac": alg_eval / (ms_eval * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                   "traffic": k0_ncu_traffic("eval")[0] if B == 256 else None,
+                                   "traffic_source": k0_ncu_traffic("eval")[1],
                                    "algorithmic_bytes_per_launch": alg_eval, "kernel_ms": ms_eval,
                                    "images_per_s": B / (ms_eval * 1e-3)},
     }

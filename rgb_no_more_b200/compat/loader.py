@@ -132,8 +132,9 @@ class B200Loader:
             while queued:
                 b = queued.pop(0)
                 y, c, q, flags, slot = fd.get()
-                plans = self.tf.sample_plans(self.batch_size, self.hb, self.wb)
-                x = self.tf.run(y, c, q, plans, clamp_in=flags)
+                # one vectorised plan draw per batch (global torch CPU generator, seeded SEED + rank by dataset_selector)
+                plans = self.tf.sample_plans_packed(self.batch_size, self.hb, self.wb, clamp_in=flags)
+                x = self.tf.run(y, c, q, plans, needs_stats=bool(plans["needs_stats"].any()))
                 fd.release(slot)
                 if nxt < len(batches):
                     submit(batches[nxt])

@@ -37,30 +37,17 @@ namespace k0v2 {
 using namespace k0;
 
 typedef unsigned long long p2;            // packed pair: token 0 in the low word, token 1 in the high word
-// tuning knobs (A/B builds: tools/build_k0_variants.sh)
+// 16 resident warps / SM (4 CTAs x 4 warps, <= 128 registers: 106 used, no spills).  Measured on B200 (profiles/r02_k0_experiments.md):
+// 12, 16 and 20 warps / SM all land within 3 % of each other in the eval geometry; 20 warps need a 96-register cap that spills
+// the quad loop's control variables.
 #ifndef K0V2_WARPS
-#define K0V2_WARPS 5
+#define K0V2_WARPS 4
 #endif
 #ifndef K0V2_CTAS
 #define K0V2_CTAS 4
 #endif
-#ifndef K0V2_PF_L2
-#define K0V2_PF_L2 1            // trace_quad issues prefetch.global.L2 for the source lines of the NEXT quad
-#endif
-#ifndef K0V2_HOLD_CHROMA
-#define K0V2_HOLD_CHROMA 0      // issue the first chroma row-pass loads before the luma column passes (16 registers held)
-#endif
-#ifndef K0V2_ABLATE
-#define K0V2_ABLATE 0           // timing experiments only (results are wrong): 1 = loads only, 2 = row passes only, 3 = no column-pass math,
-#endif                          // 4 = no sub-block conversion (P2b / P3 math), 5 = no global stores
-#ifndef K0V2_Q_REGS
-#define K0V2_Q_REGS 0           // keep the lane's luma table row (q, cq: 16 registers) in registers across quads
-#endif
-#ifndef K0V2_PF_B
-#define K0V2_PF_B 0             // carry the second luma round of the next quad as well (32 instead of 16 registers)
-#endif
 constexpr int WARPS = K0V2_WARPS;         // warps per CTA (independent: no block-level barrier)
-constexpr int CTAS_PER_SM = K0V2_CTAS;    // resident warps / SM = WARPS x CTAS_PER_SM: shared memory CTAS x (WARPS x 11,440 + 1 KB) <= 228 KB
+constexpr int CTAS_PER_SM = K0V2_CTAS;    // shared memory: CTAS x (WARPS x 11,440 + 1 KB) <= 228 KB
 constexpr int PITCH = 144;                // tile row pitch in bytes (16 pairs + 2 pad)
 constexpr int TILE_B = 32 * PITCH;        // bytes per tile (32 rows: the x2-down row pass produces 16 rows per block row)
 constexpr int QROW_B = 80;                // fp32 table row: [q0..q7 | cq0..cq7 | 16 B pad] -> the 8 rows of a table sit on distinct bank groups
@@ -200,7 +187,7 @@ __device__ __forceinline__ int4 ldg128(const unsigned char* base, uint32_t off) 
 struct LaneK {
     uint32_t T;          // tile 0
     // tile columns are stored interleaved: column c (0..7) of half h (block column / chroma component) sits in slot 2c + h
-    uint32_t rst;        // row-pass store, luma (all modes) / chroma x2-down: T + (bit4 * 8 + i8) * PITCH + bit3 * 8, columns at + 16 k
+    uint32_t rst;        // row-pass store, luma (all modes) / chroma x2-down: T + (bit3 * 8 + i8) * PITCH + bit4 * 8, columns at + 16 k
     uint32_t rst_c;      // row-pass store, chroma identity / x2-up: T + bit4 * TILE_B + i8 * PITCH + bit3 * 8 (also the chroma read-out base)
     uint32_t ccol;       // column-pass / P2b column: T + bit4 * TILE_B + slot(lane & 15) * 8
     uint32_t prow;       // P3 row: T + bit4 * TILE_B + (lane & 15) * PITCH
@@ -216,8 +203,7 @@ __device__ __forceinline__ void load_q(uint32_t qrow, float (&q)[8], float (&cq)
 }
 
 // ---- R: row pass --------------------------------------------------------------------------------------------------------
-// One x2-down round = 32 lane items: row i8 of the upper / lower (lane bit 4) source block pair of block column `half` (lane bit 3):
-// the 16 lanes of a store phase are 8 consecutive tile rows x the two adjacent slots of one column pair -> all 32 banks.
+// One x2-down round = 32 lane items: row i8 of the upper / lower (lane bit 3) source block pair of block column `half` (lane bit 4).
 //   plane / wbytes: component plane and the byte size of one of its block rows; b0: block id of token 0 for half 0 (token 1 at
 //   + tok_stride).
 struct RowLoads {
@@ -225,8 +211,8 @@ struct RowLoads {
 };
 __device__ __forceinline__ RowLoads r_down2_load(uint32_t info, int lane, const unsigned char* __restrict__ plane, int wbytes, int b0,
                                                  int tok_stride) {
-    const uint32_t lc = (lane >> 4) * wbytes + (lane & 7) * 16;
-    const uint32_t ia = info + 4 * (b0 + ((lane >> 3) & 1));
+    const uint32_t lc = ((lane >> 3) & 1) * wbytes + (lane & 7) * 16;
+    const uint32_t ia = info + 4 * (b0 + (lane >> 4));
     const uint32_t o0 = (uint32_t(lds32(ia)) & 0xffffu) * 128u + lc, o1 = (uint32_t(lds32(ia + 4 * tok_stride)) & 0xffffu) * 128u + lc;
     const int4* p0 = reinterpret_cast<const int4*>(plane + o0);        // right-hand block of the pair = + 128 bytes: immediate offset
     const int4* p1 = reinterpret_cast<const int4*>(plane + o1);
@@ -237,12 +223,9 @@ __device__ __forceinline__ RowLoads r_down2_load(uint32_t info, int lane, const 
     L.r1 = __ldg(p1 + 8);
     return L;
 }
-__device__ __forceinline__ void r_down2_compute(const RowLoads& L, const float (&q)[8], const float (&cq)[8], uint32_t dst, bool clamp) {
-    if (K0V2_ABLATE == 1) {
-        const int x = L.l0.x ^ L.l0.y ^ L.l0.z ^ L.l0.w ^ L.r0.x ^ L.r0.y ^ L.r0.z ^ L.r0.w ^ L.l1.x ^ L.l1.y ^ L.l1.z ^ L.l1.w ^ L.r1.x ^ L.r1.y ^ L.r1.z ^ L.r1.w;
-        sts64(dst, p2(unsigned(x)));
-        return;
-    }
+__device__ __forceinline__ void r_down2_compute(const RowLoads& L, uint32_t qrow, uint32_t dst, bool clamp) {
+    float q[8], cq[8];
+    load_q(qrow, q, cq);
     p2 xl[8], xr[8], o[8];
     dequant8_p(L.l0, L.l1, q, cq, clamp, xl);
     dequant8_p(L.r0, L.r1, q, cq, clamp, xr);
@@ -263,10 +246,12 @@ __device__ __forceinline__ void r_small_load(uint32_t info, int lane, const unsi
     a1 = ldg128(plane, (uint32_t(inf1) & 0xffffu) * 128u + lc);
 }
 template <int MODE>
-__device__ __forceinline__ void r_small_compute(const int4& a0, const int4& a1, uint32_t info, int b0, int tok_stride,
-                                                const float (&q)[8], const float (&cq)[8], uint32_t dst, bool clamp) {
+__device__ __forceinline__ void r_small_compute(const int4& a0, const int4& a1, uint32_t info, int b0, int tok_stride, uint32_t qrow,
+                                                uint32_t dst, bool clamp) {
     int inf0 = 0, inf1 = 0;
     if (MODE == MODE_UP2) { inf0 = lds32(info + 4 * b0); inf1 = lds32(info + 4 * (b0 + tok_stride)); }
+    float q[8], cq[8];
+    load_q(qrow, q, cq);
     p2 x[8];
     dequant8_p(a0, a1, q, cq, clamp, x);
     if (MODE == MODE_UP2) {
@@ -429,8 +414,8 @@ __device__ __forceinline__ void trace_quad(WarpSmem& ws, int lane, int tr, int t
         ws.info[slot][lane] = pack_info(sr * W + sc, chr, chc, t.zero);
         // pull the block's source rows into L2 now (they are loaded a quad later): one line per source block
         const unsigned char* src = (comp == 0 ? y_img : c_img + size_t(comp - 1) * hcwc128) + size_t(sr * W + sc) * 128;
-        if (K0V2_PF_L2) asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
-        if (K0V2_PF_L2 && mode == MODE_DOWN2) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+        if (mode == MODE_DOWN2) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 128));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(src + size_t(W) * 128));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(src + size_t(W) * 128 + 128));
@@ -441,14 +426,13 @@ __device__ __forceinline__ void trace_quad(WarpSmem& ws, int lane, int tr, int t
 // first luma loads of a quad (x2-down: round (pair 0, block row 0); else the single round of both pairs: A.l0 / A.l1 = pair 0
 // tokens 0 / 1, A.r0 / A.r1 = pair 1).  16 registers: what can be carried through the chroma column pass without spilling.
 __device__ __forceinline__ void luma_first_loads(uint32_t info, int lane, const unsigned char* __restrict__ y_img, int wb, int mode,
-                                                 RowLoads& A, RowLoads& B) {
+                                                 RowLoads& A) {
     if (mode == MODE_DOWN2) {
         A = r_down2_load(info, lane, y_img, wb * 128, 0, 4);
-        if (K0V2_PF_B) B = r_down2_load(info, lane, y_img, wb * 128, 2, 4);
     } else {
-        const int b3 = (lane >> 3) & 1, b4 = lane >> 4;          // lane = (row i8, block column b3, block row b4)
-        r_small_load(info, lane, y_img, b4 * 2 + b3, 4, A.l0, A.l1);
-        r_small_load(info, lane, y_img, 12 + b4 * 2 + b3, 4, A.r0, A.r1);
+        const int b3 = (lane >> 3) & 1, b4 = lane >> 4;          // lane = (row i8, block row b3, block column b4)
+        r_small_load(info, lane, y_img, b3 * 2 + b4, 4, A.l0, A.l1);
+        r_small_load(info, lane, y_img, 12 + b3 * 2 + b4, 4, A.r0, A.r1);
     }
 }
 
@@ -462,19 +446,11 @@ template <int OUT_MODE, int MODE_T, bool NOCLAMP_T>
 __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int lane, int img, int tr, int tp, int mode_rt,
                                              const unsigned char* __restrict__ y_img, const unsigned char* __restrict__ c_img,
                                              const rgbnm_k0_tables& tb, const float* __restrict__ stats, void* __restrict__ out_, int wb,
-                                             int hc, int wc, RowLoads& A, RowLoads& B, int slot, bool has_next, int ntr, int ntp,
-                                             const float (&ql_)[8], const float (&cql_)[8]) {
+                                             int hc, int wc, RowLoads& A, int slot, bool has_next, int ntr, int ntp) {
     const rgbnm_plan& pl = ws.plan;
     const int mode = MODE_T >= 0 ? MODE_T : mode_rt;
     const bool clamp = NOCLAMP_T ? false : (pl.clamp_in != 0);
     const uint32_t info = K.info + slot * 96;
-    float ql[8], cql[8];
-    if (K0V2_Q_REGS) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { ql[i] = ql_[i]; cql[i] = cql_[i]; }
-    } else {
-        load_q(K.qrow, ql, cql);
-    }
     const int b3 = (lane >> 3) & 1, b4 = lane >> 4;
     // the next quad is traced first: its source lines travel to L2 while this quad computes (its slot is read after the chroma row pass)
     if (has_next) trace_quad(ws, lane, ntr, ntp, mode, wb, wc, slot ^ 1, y_img, c_img, size_t(hc) * wc * 128);
@@ -482,43 +458,33 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
     if (mode == MODE_DOWN2) {
         // rounds (pair, block row) = (0,0) (0,1) (1,0) (1,1); the loads of round r+2 are issued as round r is consumed
         const int wbytes = wb * 128;
-        if (!K0V2_PF_B) B = r_down2_load(info, lane, y_img, wbytes, 2, 4);
-        r_down2_compute(A, ql, cql, K.rst, clamp);
+        RowLoads B = r_down2_load(info, lane, y_img, wbytes, 2, 4);
+        r_down2_compute(A, K.qrow, K.rst, clamp);
         A = r_down2_load(info, lane, y_img, wbytes, 12, 4);
-        r_down2_compute(B, ql, cql, K.rst + 16 * PITCH, clamp);
+        r_down2_compute(B, K.qrow, K.rst + 16 * PITCH, clamp);
         B = r_down2_load(info, lane, y_img, wbytes, 14, 4);
-        r_down2_compute(A, ql, cql, K.rst + TILE_B, clamp);
-        r_down2_compute(B, ql, cql, K.rst + TILE_B + 16 * PITCH, clamp);
+        r_down2_compute(A, K.qrow, K.rst + TILE_B, clamp);
+        r_down2_compute(B, K.qrow, K.rst + TILE_B + 16 * PITCH, clamp);
     } else if (mode == MODE_UP2) {
-        r_small_compute<MODE_UP2>(A.l0, A.l1, info, b4 * 2 + b3, 4, ql, cql, K.rst, clamp);
-        r_small_compute<MODE_UP2>(A.r0, A.r1, info, 12 + b4 * 2 + b3, 4, ql, cql, K.rst + TILE_B, clamp);
+        r_small_compute<MODE_UP2>(A.l0, A.l1, info, b3 * 2 + b4, 4, K.qrow, K.rst, clamp);
+        r_small_compute<MODE_UP2>(A.r0, A.r1, info, 12 + b3 * 2 + b4, 4, K.qrow, K.rst + TILE_B, clamp);
     } else {
-        r_small_compute<MODE_IDENT>(A.l0, A.l1, info, b4 * 2 + b3, 4, ql, cql, K.rst, clamp);
-        r_small_compute<MODE_IDENT>(A.r0, A.r1, info, 12 + b4 * 2 + b3, 4, ql, cql, K.rst + TILE_B, clamp);
+        r_small_compute<MODE_IDENT>(A.l0, A.l1, info, b3 * 2 + b4, 4, K.qrow, K.rst, clamp);
+        r_small_compute<MODE_IDENT>(A.r0, A.r1, info, 12 + b3 * 2 + b4, 4, K.qrow, K.rst + TILE_B, clamp);
     }
-    // first chroma row-pass loads (x2-down): optionally issued here, a luma column pass + sub-block conversion ahead of their use
-    RowLoads CA;
-    CA.l0 = CA.r0 = CA.l1 = CA.r1 = make_int4(0, 0, 0, 0);
-    if (K0V2_HOLD_CHROMA && mode == MODE_DOWN2)
-        CA = r_down2_load(info, lane, c_img + size_t(b3) * hc * wc * 128, wc * 128, 8, 2);
     __syncwarp();
 
     // ---- C: three rounds (k = 0, 1: luma block rows; k = 2: chroma, whose row pass runs once the luma tokens are stored) ----------
     // lane = (pair p = b4, tile column c16)
     const int p = b4, c16 = lane & 15, half = c16 >> 3, c = c16 & 7;
     bool Tf = false;
-    p2 vtop[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) vtop[i] = 0;
 #pragma unroll 1
     for (int k = 0; k < 3; ++k) {
-        if ((K0V2_ABLATE == 1 || K0V2_ABLATE == 2) && k < 2) continue;
         if (k == 2) {
-            __syncwarp();                                                  // S / A16 . S complete
-            if (OUT_MODE != RGBNM_K0_OUT_INT16_PLANES && K0V2_ABLATE != 1 && K0V2_ABLATE != 2) {
-                // ---- P2b through shared memory, only for transposed blocks (odd number of rot90): the column pass wrote S across
-                //      columns; otherwise a lane's two column-pass results ARE its column of S and P2b ran in registers (below) ----
-                if (Tf) {
+            __syncwarp();                                                  // S complete (transposed blocks are written across columns)
+            if (OUT_MODE != RGBNM_K0_OUT_INT16_PLANES) {
+                // ---- P2b: column half of the sub-block conversion, in place: S -> A16 . S ------------------------------------
+                {
                     p2 xl[8], xr[8], t[16];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { xl[i] = lds64(K.ccol + i * PITCH); xr[i] = lds64(K.ccol + (8 + i) * PITCH); }
@@ -535,14 +501,8 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
                         lds128(K.prow + 32 * j, xl[2 * j], xr[2 * j]);              // slots (2c, 2c + 1) = columns (c, c + 8)
                         lds128(K.prow + 32 * j + 16, xl[2 * j + 1], xr[2 * j + 1]);
                     }
-                    if (K0V2_ABLATE == 4) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { o[i] = xl[i]; o[8 + i] = xr[i]; }
-                    } else {
-                        a16_1d_p(xl, xr, o);
-                    }
+                    a16_1d_p(xl, xr, o);
                     const size_t off = (size_t(img) * TOKENS + (2 * tr + p) * 14 + 2 * tp) * FEAT + c16 * 16;
-                    if (K0V2_ABLATE != 5)
                     if (OUT_MODE == RGBNM_K0_OUT_F32) {
                         float4* d0 = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_) + off);
                         float4* d1 = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_) + off + FEAT);
@@ -567,28 +527,25 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
             }
             // ---- R, chroma: tile of pair p, rows = source rows, 16 columns = [Cb 8 | Cr 8] ----------------------------------------
             if (mode == MODE_DOWN2) {
-                // lane bit 3 = component (the block-column `half` of r_down2_*); chroma block ids 8 + tok*2 + (comp-1), token stride 2
-                const unsigned char* plane = c_img + size_t(b3) * hc * wc * 128;
-                if (!K0V2_HOLD_CHROMA) CA = r_down2_load(info, lane, plane, wc * 128, 8, 2);
+                // lane bit 4 = component (the block-column `half` of r_down2_*); chroma block ids 8 + tok*2 + (comp-1), token stride 2
+                const unsigned char* plane = c_img + size_t(b4) * hc * wc * 128;
+                const RowLoads CA = r_down2_load(info, lane, plane, wc * 128, 8, 2);
                 const RowLoads CB = r_down2_load(info, lane, plane, wc * 128, 20, 2);
-                float qc[8], cqc[8];
-                load_q(K.qrow + (1 + b3) * 8 * QROW_B, qc, cqc);
-                r_down2_compute(CA, qc, cqc, K.rst, clamp);
-                r_down2_compute(CB, qc, cqc, K.rst + TILE_B, clamp);
+                const uint32_t qr = K.qrow + (1 + b4) * 8 * QROW_B;
+                r_down2_compute(CA, qr, K.rst, clamp);
+                r_down2_compute(CB, qr, K.rst + TILE_B, clamp);
             } else {
                 // lane = (row i8, component b3, pair b4)
                 const unsigned char* plane = c_img + size_t(b3) * hc * wc * 128;
                 int4 a0, a1;
                 r_small_load(info, lane, plane, b4 * 12 + 8 + b3, 2, a0, a1);
-                float qc[8], cqc[8];
-                load_q(K.qrow + (1 + b3) * 8 * QROW_B, qc, cqc);
-                if (mode == MODE_UP2) r_small_compute<MODE_UP2>(a0, a1, info, b4 * 12 + 8 + b3, 2, qc, cqc, K.rst_c, clamp);
-                else r_small_compute<MODE_IDENT>(a0, a1, info, b4 * 12 + 8 + b3, 2, qc, cqc, K.rst_c, clamp);
+                const uint32_t qr = K.qrow + (1 + b3) * 8 * QROW_B;
+                if (mode == MODE_UP2) r_small_compute<MODE_UP2>(a0, a1, info, b4 * 12 + 8 + b3, 2, qr, K.rst_c, clamp);
+                else r_small_compute<MODE_IDENT>(a0, a1, info, b4 * 12 + 8 + b3, 2, qr, K.rst_c, clamp);
             }
             __syncwarp();
             // the next quad's first luma loads: in flight during the chroma column pass and read-out of this one
-            if (has_next) luma_first_loads(K.info + (slot ^ 1) * 96, lane, y_img, wb, mode, A, B);
-            if (K0V2_ABLATE == 1 || K0V2_ABLATE == 2) continue;
+            if (has_next) luma_first_loads(K.info + (slot ^ 1) * 96, lane, y_img, wb, mode, A);
         }
         // ---- the column pass proper ----------------------------------------------------------------------------------------
         const int b0 = p * 12 + (k < 2 ? k * 2 + half : 8 + half);
@@ -601,14 +558,9 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
             p2 xl[8], xr[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) { xl[i] = lds64(colp + i * PITCH); xr[i] = lds64(colp + (8 + i) * PITCH); }
-            if (K0V2_ABLATE == 3) {
+            down2_1d_p<1, 2>(xl, xr, v);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = xl[i] ^ xr[i];
-            } else {
-                down2_1d_p<1, 2>(xl, xr, v);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = rint2(v[i]);             // torch.round -> int16 (dct_ops.py:577-578)
-            }
+            for (int i = 0; i < 8; ++i) v[i] = rint2(v[i]);                 // torch.round -> int16 (dct_ops.py:577-578)
         } else {
             const uint32_t colp = K.ccol + (k < 2 ? k * 8 : 0) * PITCH;
             if (mode == MODE_UP2) {
@@ -626,7 +578,7 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
         __syncwarp();                                                      // this round's tile reads are done: S may overwrite
         const int fr = k < 2 ? 2 * (2 * tr + p) + k : 2 * tr + p;
         const int fc0 = k < 2 ? 2 * (2 * tp) + half : 2 * tp;
-        if (K0V2_ABLATE != 3 && (pl.train | pl.flip | pl.n_ops)) Tf = run_ops_p(v, pl, comp, c, z0, z1, tb, stats, img, fr, fc0, k < 2 ? 2 : 1);
+        if (pl.train | pl.flip | pl.n_ops) Tf = run_ops_p(v, pl, comp, c, z0, z1, tb, stats, img, fr, fc0, k < 2 ? 2 : 1);
 
         if (OUT_MODE == RGBNM_K0_OUT_INT16_PLANES) {
             int16_t* o16 = reinterpret_cast<int16_t*>(out_) + size_t(img) * PLANE_ELEMS;
@@ -644,37 +596,14 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
         } else {
             // S tile rows (k*8 ..) of pair p, slots 2 * column + half: element (i, c), or (c, i) for a transposed block -- one
             // store sequence with a run-time stride (two branches made ptxas copy every pair into a fixed register pair)
-            if (K0V2_ABLATE != 3) {
+            const uint32_t S = K.ccol - c * 16 + (k < 2 ? k * 8 : 0) * PITCH + c * (Tf ? PITCH : 16);
+            const uint32_t stride = Tf ? 16 : PITCH;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = to_range2(v[i]);
-            }
-            if (k < 2 && !Tf) {
-                // luma, upright blocks: rows 0..7 (k = 0) and 8..15 (k = 1) of this lane's column of S stay in registers; the column
-                // half of the sub-block conversion A16 . S follows at once and only its result goes to the tile
-                if (k == 0) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) vtop[i] = v[i];
-                } else {
-                    p2 t[16];
-                    if (K0V2_ABLATE == 4) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { t[i] = vtop[i]; t[8 + i] = v[i]; }
-                    } else {
-                        a16_1d_p(vtop, v, t);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) sts64(K.ccol + i * PITCH, t[i]);
-                }
-            } else {
-                const uint32_t S = K.ccol - c * 16 + (k < 2 ? k * 8 : 0) * PITCH + c * (Tf ? PITCH : 16);
-                const uint32_t stride = Tf ? 16 : PITCH;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) sts64(S + i * stride, v[i]);
-            }
+            for (int i = 0; i < 8; ++i) sts64(S + i * stride, to_range2(v[i]));
         }
     }
     __syncwarp();
-    if (OUT_MODE == RGBNM_K0_OUT_INT16_PLANES || K0V2_ABLATE == 1 || K0V2_ABLATE == 2 || K0V2_ABLATE == 5) return;
+    if (OUT_MODE == RGBNM_K0_OUT_INT16_PLANES) return;
 
     // ---- chroma out: lane = (pair p = b4, block row i8, column group b3): 16-byte loads give (Cb, Cr) of 4 columns -----------------
     {
@@ -712,7 +641,7 @@ k0_vit2_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, 
         const uint32_t base = uint32_t(__cvta_generic_to_shared(smem_raw)) + warp * uint32_t(sizeof(WarpSmem));
         const int i8 = lane & 7, b3 = (lane >> 3) & 1, b4 = lane >> 4;
         K.T = base;
-        K.rst = base + (b4 * 8 + i8) * PITCH + b3 * 8;
+        K.rst = base + (b3 * 8 + i8) * PITCH + b4 * 8;
         K.rst_c = base + b4 * TILE_B + i8 * PITCH + b3 * 8;
         K.ccol = base + b4 * TILE_B + (2 * (lane & 7) + b3) * 8;          // slot of tile column lane & 15
         K.prow = base + b4 * TILE_B + (lane & 15) * PITCH;
@@ -725,9 +654,8 @@ k0_vit2_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, 
     const int hc = hb >> 1, wc = wb >> 1;
     int cur = -1, mode = MODE_BAD, slot = 0;
     bool pre = false;                   // info slot `slot` traced and A loaded by the previous quad
-    RowLoads A, B;
-    A.l0 = A.r0 = A.l1 = A.r1 = B.l0 = B.r0 = B.l1 = B.r1 = make_int4(0, 0, 0, 0);
-    float ql[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cql[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // luma table row of the lane's coefficient row: per image
+    RowLoads A;
+    A.l0 = A.r0 = A.l1 = A.r1 = make_int4(0, 0, 0, 0);
     for (int q = q_begin; q < q_end; ++q) {
         const int img = q / QUADS_PER_IMAGE, rem = q - img * QUADS_PER_IMAGE;
         if (img != cur) {
@@ -744,7 +672,6 @@ k0_vit2_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, 
             cur = img;
             mode = mode_of(ws.plan.crop_size, GRID_Y);
             pre = false;
-            if (K0V2_Q_REGS) load_q(K.qrow, ql, cql);
         }
         if (mode == MODE_BAD) continue;
         const int tr = rem / 7, tp = rem - tr * 7;
@@ -753,17 +680,17 @@ k0_vit2_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, 
         if (!pre) {
             trace_quad(ws, lane, tr, tp, mode, wb, wc, slot, y_img, c_img, size_t(hc) * wc * 128);
             __syncwarp();
-            luma_first_loads(K.info + slot * 96, lane, y_img, wb, mode, A, B);
+            luma_first_loads(K.info + slot * 96, lane, y_img, wb, mode, A);
         }
         const bool has_next = (q + 1 < q_end) && (rem + 1 < QUADS_PER_IMAGE);
         const int nrem = rem + 1, ntr = nrem / 7, ntp = nrem - ntr * 7;
         const float* stats = stats_all + size_t(img) * RGBNM_MAX_OPS * 2;
         if (OUT_MODE != RGBNM_K0_OUT_INT16_PLANES && mode == MODE_DOWN2 && ws.plan.clamp_in == 0)
-            process_quad<OUT_MODE, MODE_DOWN2, true>(ws, K, lane, img, tr, tp, mode, y_img, c_img, tb, stats, out_, wb, hc, wc, A, B, slot,
-                                                     has_next, ntr, ntp, ql, cql);
+            process_quad<OUT_MODE, MODE_DOWN2, true>(ws, K, lane, img, tr, tp, mode, y_img, c_img, tb, stats, out_, wb, hc, wc, A, slot,
+                                                     has_next, ntr, ntp);
         else
-            process_quad<OUT_MODE, -1, false>(ws, K, lane, img, tr, tp, mode, y_img, c_img, tb, stats, out_, wb, hc, wc, A, B, slot,
-                                              has_next, ntr, ntp, ql, cql);
+            process_quad<OUT_MODE, -1, false>(ws, K, lane, img, tr, tp, mode, y_img, c_img, tb, stats, out_, wb, hc, wc, A, slot,
+                                              has_next, ntr, ntp);
         pre = has_next;
         if (has_next) slot ^= 1;
     }

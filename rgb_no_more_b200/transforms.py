@@ -77,6 +77,17 @@ class FusedDCT:
                     for _ in range(n)]
         return [P.eval_plan(hb, wb) if self.out_size == 28 else P.eval_plan_swin(hb, wb, self.out_size)] * n
 
+    def sample_plans_packed(self, n: int, hb: int = 64, wb: int = 64, clamp_in=None, generator=None) -> np.ndarray:
+        """n plans, packed (`struct rgbnm_plan[n]`), drawn by plan.BatchedSampler: the same distributions as `sample_plans`, one
+        vectorised draw per batch instead of the reference's per-image RNG call sequence (~0.3 ms instead of ~15 ms per 256)."""
+        if self.kind != "train":
+            return P.pack_plans(self.sample_plans(n, hb, wb), clamp_in, out_size=self.out_size)
+        key = (hb, wb)
+        if getattr(self, "_batched", None) is None or self._batched[0] != key:
+            self._batched = (key, P.BatchedSampler(hb, wb, self.ops_list if self.ops_list is not None else P.AUGLIST_VITS,
+                                                   self.num_ops, self.ops_magnitude, self.bank, size=self.out_size))
+        return self._batched[1].sample(n, clamp_in=clamp_in, generator=generator)
+
     # -- launch ---------------------------------------------------------------------------
     def run(self, y_q: torch.Tensor, c_q: torch.Tensor, quant: torch.Tensor, plans, clamp_in=None,
             out_mode: Optional[int] = None, out: Optional[torch.Tensor] = None,
