@@ -1,5 +1,5 @@
 // Dense bf16 GEMMs of the DCT ViT, CTA-pair edition (sm_100a): tcgen05.mma.cta_group::2 over a
-// 2-CTA cluster.  The single-CTA kernel in gemm_tc.cu re-reads 128 x K of A and 192 x K of B from
+// 2-CTA cluster.  The round-1 single-CTA kernel (tools/legacy/gemm_tc_v1.cu, no longer built) re-read 128 x K of A and 192 x K of B from
 // L2 for every 128 x 192 tile (76.8 FLOP per L2 byte) and is capped by the L2 -> SM fabric at
 // ~0.95 PFLOP/s on this part (measured: 46.6 us for the 44.4 GFLOP qkv projection).  Here two SMs
 // share one 256 x BN accumulator tile: each CTA loads its own 128 rows of A and only HALF of the B
@@ -627,12 +627,8 @@ static int launch(const rgbnm_gemm_args& a, cudaStream_t st) {
 
 }  // namespace gemm2
 
-int rgbnm_gemm_bf16_v1(const rgbnm_gemm_args* args, void* stream);
-
 extern "C" int rgbnm_gemm_bf16(const rgbnm_gemm_args* args, void* stream) {
     using namespace gemm2;
-    static const bool use_v1 = (getenv("RGBNM_GEMM_V1") != nullptr);     // single-CTA kernel of gemm_tc.cu, kept for A/B runs
-    if (use_v1) return rgbnm_gemm_bf16_v1(args, stream);
     if (!args || !args->A || !args->B || args->M <= 0 || args->N <= 0 || args->K <= 0) return RGBNM_ERR_ARG;
     const rgbnm_gemm_args& a = *args;
     if ((a.lda % 8) || (a.ldb % 8)) return RGBNM_ERR_ARG;                      // TMA: 16-byte aligned row pitch

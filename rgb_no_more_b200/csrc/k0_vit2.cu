@@ -652,6 +652,9 @@ k0_vit2_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, 
     const long long gw = (long long)blockIdx.x * WARPS + warp, tw = (long long)gridDim.x * WARPS;
     const int q_begin = int(gw * nq / tw), q_end = int((gw + 1) * nq / tw);
     const int hc = hb >> 1, wc = wb >> 1;
+#ifdef K0V2_STAGGER_NS
+    __nanosleep(unsigned(gw & 3) * K0V2_STAGGER_NS);        // experiment: de-phase the warps of a scheduler
+#endif
     int cur = -1, mode = MODE_BAD, slot = 0;
     bool pre = false;                   // info slot `slot` traced and A loaded by the previous quad
     RowLoads A;

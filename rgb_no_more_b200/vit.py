@@ -34,7 +34,6 @@ from . import gemm as G
 from . import lib as _lib
 from . import ops as K
 
-_V1 = bool(os.environ.get("RGBNM_GEMM_V1"))      # single-CTA GEMM kernel (A/B measurements only)
 TOKENS = 196          # 14 x 14 patches of 16 x 16 pixels (224 px input)
 IN_FEAT = 384         # 256 luma + 64 Cb + 64 Cr coefficients per patch
 
@@ -141,9 +140,6 @@ class ViTEngine:
             lin.wt = torch.empty((lin.k, lin.n), **bf)
             if lin.qkv_heads:
                 lin.bias_k = torch.empty(lin.n, dtype=torch.float32, device=device)
-        self.qkv_gw = torch.zeros((3 * self.HD, self.E), dtype=torch.float32, device=device)
-        self.qkv_gb = torch.zeros(3 * self.HD, dtype=torch.float32, device=device)
-        self.qkv_tmp = torch.zeros(3 * self.HD, dtype=torch.float32, device=device)
         self.posemb = sincos_posemb(14, 14, self.E, device)
         self._versions = None
         self._wprep = None
@@ -269,7 +265,7 @@ class ViTEngine:
     # -- backward -----------------------------------------------------------------------------------
     def _wgrad_gemm(self, dy: torch.Tensor, x: torch.Tensor, gw: torch.Tensor, splits: int) -> None:
         # gw [out, in] += dy^T x.  The CTA-pair kernel tiles 256 (M) x 128 (N): put the longer side on M.
-        if x.shape[1] > dy.shape[1] and not _V1:
+        if x.shape[1] > dy.shape[1]:
             self._gemm(x, dy, G.EPI_WGRAD_ATOMIC, out_f32=gw, splits=splits, trans_out=True)
         else:
             self._gemm(dy, x, G.EPI_WGRAD_ATOMIC, out_f32=gw, splits=splits)
@@ -277,23 +273,13 @@ class ViTEngine:
     def _wgrad(self, dy: torch.Tensor, x: torch.Tensor, lin: _Lin, splits: int, bias_done: bool = False) -> None:
         """dW += dy^T x, db += colsum(dy) into the flat gradient buffer (reference parameter order).  bias_done: the
         LayerNorm backward that produced dy already accumulated its column sums into the bias gradient."""
-        if lin.qkv_heads and not _V1:
+        if lin.qkv_heads:
             # the kernel-side qkv layout is q|k|v head-major: the epilogue / column-sum kernels add each row at its
             # reference position ("(h d qkv)", plainvit.py:447), so the flat buffer keeps the reference layout
             self._gemm(dy, x, G.EPI_WGRAD_ATOMIC, out_f32=self.grad_of(lin.weight), splits=splits,
                        perm_heads=self.H, perm_head_dim=self.D)
             K.colsum(dy, self.grad_of(lin.bias), self.H, self.D)
             self.launches += 1
-        elif lin.qkv_heads:
-            gw, gb, tmp = self.qkv_gw, self.qkv_gb, self.qkv_tmp
-            gw.zero_()
-            gb.zero_()
-            self._wgrad_gemm(dy, x, gw, splits)
-            K.colsum(dy, gb)
-            K.qkv_unperm_rows_add(gw, self.grad_of(lin.weight), self.H, self.D)
-            K.qkv_perm_vec(gb, tmp, self.H, self.D, inverse=True)
-            self.grad_of(lin.bias).add_(tmp)
-            self.launches += 3
         else:
             self._wgrad_gemm(dy, x, self.grad_of(lin.weight), splits)
             if not bias_done:
@@ -307,7 +293,7 @@ class ViTEngine:
         M, E = B * TOKENS, self.E
         if zero_grad:
             self.flat_grad.zero_()
-        splits = max(1, min(16, (M // 64) // 8)) if _V1 else 0       # 0: chosen by the library (whole waves of CTA pairs)
+        splits = 0                                                   # chosen by the library (whole waves of CTA pairs)
         # ---- head (torch ops on B x E) ----
         z, pooled = bufs["z"], bufs["pooled"]
         w2, w1 = self.head2[0].data, self.head1[0].data

@@ -7,10 +7,10 @@ import torch
 
 def run() -> None:
     from oracle import dct_oracle as O          # checker only
-    from . import dct_manip as dm
-    from . import plan as P
-    from . import synth
-    from . import transforms as TF
+    from rgb_no_more_b200 import dct_manip as dm
+    from rgb_no_more_b200 import plan as P
+    from rgb_no_more_b200 import synth
+    from rgb_no_more_b200 import transforms as TF
 
     if not torch.cuda.is_available():
         raise RuntimeError("rgbnm smoke: no CUDA device; the B200 path has no CPU fallback")
@@ -52,10 +52,7 @@ def run() -> None:
         if err > 2e-5:
             raise AssertionError(f"rgbnm smoke: K0 embed input differs from the oracle by {err}")
     print(f"rgbnm smoke: K0 ok on {torch.cuda.get_device_name(0)} (ops bit-exact; {ties} tie-rounding LSB flips in resize)")
-    try:
-        from . import vit_smoke
-    except ImportError:
-        return
+    from . import swin as swin_smoke
+    from . import vit as vit_smoke
     vit_smoke.run()
-    from . import swin_smoke
     swin_smoke.run()

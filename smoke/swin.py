@@ -9,11 +9,11 @@ import torch
 def run() -> None:
     from oracle import dct_oracle as O           # checker only
     from oracle import swin_oracle as SO         # checker only
-    from . import dct_manip as dm
-    from . import plan as P
-    from . import swin as S
-    from . import synth
-    from . import transforms as TF
+    from rgb_no_more_b200 import dct_manip as dm
+    from rgb_no_more_b200 import plan as P
+    from rgb_no_more_b200 import swin as S
+    from rgb_no_more_b200 import synth
+    from rgb_no_more_b200 import transforms as TF
 
     dev = torch.device("cuda", 0)
     torch.manual_seed(11997733)

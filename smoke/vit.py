@@ -9,8 +9,8 @@ import torch.nn.functional as F
 
 def run() -> None:
     from oracle import vit_oracle as VO          # checker only
-    from . import train_step as TS
-    from . import vit as V
+    from rgb_no_more_b200 import train_step as TS
+    from rgb_no_more_b200 import vit as V
 
     dev = torch.device("cuda", 0)
     torch.manual_seed(11997733)

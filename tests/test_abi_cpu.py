@@ -49,16 +49,14 @@ def test_gpu_entry_points_fail_loudly_without_a_device():
 
 
 def test_product_modules_never_import_the_oracle():
-    """oracle/ is test infrastructure: only the smoke checkers (called by __graft_entry__.smoke()), tests/ and bench.py's CPU
+    """oracle/ is test infrastructure: only smoke/ (the checkers __graft_entry__.smoke() runs), tests/ and bench.py's CPU
     legs may import it -- never a module on the product path."""
     import ast
     import glob
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     offenders = []
-    for path in glob.glob(os.path.join(root, "rgb_no_more_b200", "*.py")):
-        if path.endswith("smoke.py"):
-            continue
+    for path in glob.glob(os.path.join(root, "rgb_no_more_b200", "**", "*.py"), recursive=True):
         tree = ast.parse(open(path).read())
         for node in ast.walk(tree):
             names = []

@@ -189,18 +189,17 @@ def test_colsum_weightprep_adamw():
 
 
 # ---- the model against the reference's own outputs -----------------------------------------------------------
-def _golden_model(attention="auto"):
+def _golden_model():
     m = V.ViT(patch_size=16, emb_size=192, depth=12, n_classes=1000, drop_p=0.0, num_heads=3, head_size=64,
-              pixel_space="DCT", ver=1, use_subblock=True, attention=attention)
+              pixel_space="DCT", ver=1, use_subblock=True)
     m.load_state_dict(seeded_state_dict(m))
     return m.to(DEV)
 
 
-@pytest.mark.parametrize("attention", ["auto", "torch"])
-def test_vitti_logits_match_reference(attention):
+def test_vitti_logits_match_reference():
     g = load("embed_vit.npz")
     yf, cf = golden_vit_inputs(g["input_seed"])
-    m = _golden_model(attention).eval()
+    m = _golden_model().eval()
     with torch.no_grad():
         logits = m(yf.to(DEV), cf.to(DEV)).cpu()
     ref = torch.from_numpy(g["logits_vitti"])

@@ -1,3 +1,5 @@
+// LEGACY, NOT BUILT: the round-1 single-CTA (cta_group::1) tcgen05 GEMM, superseded by rgb_no_more_b200/csrc/gemm2_tc.cu (CTA pairs).
+// Kept for reference only (DESIGN.md section 4 explains why pairs won); its tensor-map helpers now live in csrc/tmap.cu.
 // Dense bf16 GEMMs of the DCT ViT on the 5th-gen tensor cores (sm_100a): tcgen05.mma fed by
 // TMA, fp32 accumulators in TMEM, fused epilogues.  One persistent, warp-specialised kernel
 // template covers every dense contraction of models/plainvit.py forward and backward:
