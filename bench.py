@@ -371,6 +371,22 @@ def run_ours(args):
         except Exception as ex:  # noqa: BLE001 -- a side measurement must never cost the headline line
             swin_fwd = {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
+    # SwinV2-T DCT TRAINING (BASELINE config 5: window 8, bf16, data parallel), at every world size: K0 in the Swin layout with the
+    # RandAugment mix -> SwinTransformerV2 forward / backward (rgb_no_more_b200.swin_train) -> DDP all-reduce -> AdamW
+    swin_train = None
+    if args.stage == "train" and out_dtype == torch.bfloat16 and not args.no_swin:
+        try:
+            swin_train = swin_train_step(args, dev, dev_pool, timed_loop, rank, world, local)
+        except Exception as ex:  # noqa: BLE001
+            swin_train = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+    # BASELINE configs 1 and 2 (ViT-Ti) as side measurements on one GPU
+    vitti = None
+    if world == 1 and args.stage == "train" and args.arch == "vits" and out_dtype == torch.bfloat16 and not args.no_cpu:
+        try:
+            vitti = vitti_configs(args, dev, dev_pool, dev_plans, tf, tf_eval, labels_pool, timed_loop)
+        except Exception as ex:  # noqa: BLE001
+            vitti = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -412,6 +428,10 @@ def run_ours(args):
                                 "resident in HBM, CUDA-graph replay"}
     if swin_fwd is not None:
         line["swin_eval_forward"] = swin_fwd
+    if swin_train is not None:
+        line["swin_train"] = swin_train
+    if vitti is not None:
+        line["vitti_configs"] = vitti
     if stage is not None and args.arch in VIT_TRAIN_GFLOP_PER_IMAGE:
         # the ViT part of the step against the measured cuBLAS bf16 rate (sustained figure: timed inside a long step)
         tf_s = VIT_TRAIN_GFLOP_PER_IMAGE[args.arch] * B / ((ms_step - k0_avg_ms) * 1e-3) / 1e3
@@ -425,6 +445,97 @@ def run_ours(args):
         if stage is not None:
             line["torch_b200_baseline"] = torch_b200_baseline(args)
     print(json.dumps(line))
+
+
+def swin_train_step(args, dev, dev_pool, timed_loop, rank, world, local):
+    """BASELINE config 5 (SwinV2-T DCT, window 8, bf16, DDP): batch 64 per GPU (reference: 512 over 8 GPUs, configs.py:137),
+    drop_path 0.2, fresh plans per step from the batched sampler, the reference's own loop shape: DistributedDataParallel around
+    `swin.SwinTransformerV2` (gradients through one autograd.Function), torch AdamW.  Whole-job images/s, max over ranks."""
+    import torch.nn.functional as F
+    from rgb_no_more_b200 import plan as P, swin as S, transforms as TF
+    B = 64
+    with torch.random.fork_rng(devices=[dev]):
+        torch.manual_seed(11997733)
+        model = S.SwinTransformerV2(img_size=256, patch_size=4, embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24],
+                                    window_size=8, mlp_ratio=4, drop_path_rate=0.2, pretrained_window_sizes=[0, 0, 0, 0],
+                                    device="cpu", pixel_space="dct")
+        with torch.no_grad():       # the reference zero-initialises the block post-norms (identity blocks): randomise them
+            for p_ in model.parameters():
+                if p_.ndim == 1:
+                    p_.add_(0.1 * torch.randn_like(p_))
+    model.train().to(dev)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], output_device=local)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    tf = TF.FusedDCT(dev, "train", P.AUGLIST_VITS, 2, 9, torch.bfloat16, out_size=32)
+    labels = torch.randint(0, 1000, (B,), device=dev)
+    gen = torch.Generator().manual_seed(7 + rank)
+    losses = []
+
+    def step(i):
+        y, c, q = (t[:B] for t in dev_pool[i % len(dev_pool)])
+        plans = tf.sample_plans_packed(B, 64, 64, clamp_in=[False] * B, generator=gen)
+        x = tf.run(y, c, q, plans, needs_stats=bool(plans["needs_stats"].any()))
+        opt.zero_grad(set_to_none=True)
+        loss = F.cross_entropy(net(x), labels)
+        loss.backward()
+        opt.step()
+        losses.append(loss.detach())
+    n = max(args.steps // 4, 5)
+    ms = timed_loop(step, n, 3) / n
+    return {"value": B * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch_per_gpu": B, "n_gpus": world,
+            "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
+            "what": "SwinV2-T DCT (window 8) train step: K0 in the Swin layout (RandAugment mix, fresh plans per step) -> forward with "
+                    "saved activations -> CE -> backward -> " + ("DDP all-reduce (NCCL) -> " if world > 1 else "") + "torch AdamW; eager "
+                    "launches; tcgen05 GEMMs, mma.sync window attention forward, CUDA-core attention / LayerNorm backward"}
+
+
+def vitti_configs(args, dev, dev_pool, dev_plans, tf, tf_eval, labels_pool, timed_loop):
+    """BASELINE configs 1 and 2 on this arm.  (1) ViT-Ti --domain=DCT, batch 8, 64 synthetic 512x512 JPEGs, eval-only forward: from
+    JPEG bytes (host Huffman decode, 1 thread as the reference's single process) -> K0 eval geometry -> ViT-Ti forward, logits
+    to the host.  (2) ViT-Ti DCT, batch 256, train step with coefficients resident (K0 + tcgen05 ViT-Ti; the reference's config
+    names torch attention, this arm has only its own attention kernels)."""
+    from rgb_no_more_b200 import dct_manip as dm, plan as P, synth, train_step as TS, vit as V
+    out = {}
+    jpegs = synth.synth_jpeg_set(64)
+    with torch.random.fork_rng(devices=[dev]):
+        torch.manual_seed(11997733)
+        m = V.ViT(patch_size=16, emb_size=192, depth=12, n_classes=1000, drop_p=0.0, pixel_space="DCT", ver=1, use_subblock=True,
+                  device=dev, num_heads=3, head_size=64).eval()
+    host = torch.empty((8, 1000), dtype=torch.float32).pin_memory()
+    eplans = tf_eval.sample_plans(8)
+
+    def eval_pass(_i):
+        for b in range(0, 64, 8):
+            y, c, q, fl = dm.decode_batch(jpegs[b:b + 8], 64, 64, nthreads=1)
+            x = tf_eval.run(y.to(dev, non_blocking=True), c.to(dev, non_blocking=True), q.to(dev, non_blocking=True), eplans,
+                            clamp_in=fl.tolist())
+            with torch.no_grad():
+                host.copy_(m(x), non_blocking=True)
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    eval_pass(0)
+    reps = 3
+    t0 = time.perf_counter()
+    for i in range(reps):
+        eval_pass(i)
+    out["config1_eval_b8_from_jpeg"] = {"value": 64 * reps / (time.perf_counter() - t0), "unit": UNIT,
+                                        "what": "ViT-Ti DCT eval forward, batch 8, 64 JPEGs: 1 host decode thread -> H2D -> K0 (eval "
+                                                "geometry) -> ViT-Ti forward -> logits D2H, wall clock incl. decode"}
+    st = TS.TrainStage(dev, arch="vitti", batch=args.batch, world=1)
+    xb = torch.empty((args.batch, 196, 384), dtype=torch.bfloat16, device=dev)
+
+    def step(i):
+        k = i % N_POOL
+        x = tf.run(*dev_pool[k], None, plans_dev=dev_plans[k], out=st.x_static)
+        st.step(x, labels_pool[k])
+    n = max(args.steps // 2, 5)
+    ms = timed_loop(step, n, 3) / n
+    out["config2_train_b256"] = {"value": args.batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                                 "what": "ViT-Ti DCT train step (K0 -> fwd/bwd/AdamW), batch 256, coefficients resident"}
+    del st, xb
+    return out
 
 
 def swin_eval_forward(args, dev, dev_pool, clamp_flags, timed_loop, host_pool=None):

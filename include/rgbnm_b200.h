@@ -152,6 +152,10 @@ int rgbnm_k0_launch_count(void);
  *     models/swinv2.py:505-576, models/plainvit.py:50-88.  INT16_PLANES: [n][(32*32 + 2*16*16)*64]. */
 #define RGBNM_K0_LAYOUT_VIT16 0
 #define RGBNM_K0_LAYOUT_SWIN4 1
+/*   RGBNM_K0_LAYOUT_VIT16_NOSUB: `--no_subblock` (PatchEmbedding_DCT_Group with use_subblock = False, plainvit.py:173-216): the VIT16
+ *     geometry without the A16 products, out [n][196][384] = per 16 x 16 patch [Y 256 | Cb 64 | Cr 64] where the luma part is the
+ *     tile of the four un-converted 8 x 8 blocks, row-major ('b c (h pdh) (w pdw) p1 p2 -> b c h w (pdh p1) (pdw p2)') */
+#define RGBNM_K0_LAYOUT_VIT16_NOSUB 2
 int rgbnm_k0_dcstats_ex(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans,
                         const rgbnm_k0_tables* tables, float* stats, int n, int hb, int wb, int layout, void* stream);
 int rgbnm_k0_fused_ex(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans,

@@ -403,12 +403,18 @@ def transform_int16(y_q, c_q, quant, plan, filters, out_size: int = 28):
     return y, c
 
 
-def embed_input(yf: torch.Tensor, cf: torch.Tensor) -> torch.Tensor:
+def embed_input(yf: torch.Tensor, cf: torch.Tensor, subblock: bool = True) -> torch.Tensor:
     """PatchEmbedding_DCT_Group.forward up to (not including) the Linear
     (models/plainvit.py:200-216) for patch 16: rearrange 2x2 luma blocks into a
     16x16 tile, A16 . X . A16^T, collapse to [Y 256 | Cb 64 | Cr 64].
-    yf (B,1,28,28,8,8), cf (B,2,14,14,8,8) fp32 -> (B,14,14,384)."""
+    yf (B,1,28,28,8,8), cf (B,2,14,14,8,8) fp32 -> (B,14,14,384).
+    subblock = False (`--no_subblock`: patch2subblock returns no matrix, plainvit.py:33-38; apply_subblock is the identity, :59-60):
+    the rearrange 'b c (h pdh) (w pdw) p1 p2 -> b c h w (pdh p1) (pdw p2)' (:83) alone, i.e. the un-converted 16 x 16 tile."""
     b, _, H, W, _, _ = yf.shape
+    if not subblock:
+        y = yf.reshape(b, 1, H // 2, 2, W // 2, 2, 8, 8).permute(0, 1, 2, 4, 3, 6, 5, 7).reshape(b, H // 2, W // 2, 256)
+        c = cf.permute(0, 2, 3, 1, 4, 5).reshape(b, H // 2, W // 2, 128)
+        return torch.cat([y, c], dim=3)
     A = conversion_matrix(2)
     y = yf.reshape(b, 1, H // 2, 2, W // 2, 2, 8, 8).permute(0, 1, 2, 4, 3, 6, 5, 7)
     y = y.reshape(b, 1, H // 2, W // 2, 16, 16)

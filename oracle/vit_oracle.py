@@ -33,10 +33,30 @@ def sincos(h: int, w: int, e: int) -> torch.Tensor:
 
 
 def tokens(sd: Dict[str, torch.Tensor], emb_in: torch.Tensor) -> torch.Tensor:
-    """PatchEmbedding_DCT_Group.projection (plainvit.py:194-198): Linear + sincos + 'b h w e -> b (h w) e'.
-    emb_in: (B, 14, 14, 384) as produced by dct_oracle.embed_input."""
-    x = F.linear(emb_in, sd["patchembed.projection.0.weight"], sd["patchembed.projection.0.bias"])
-    b, h, w, e = x.shape
+    """The patch embedding from the K0 operand on (everything after rearrange / sub-block conversion / collapse), chosen by the
+    state_dict's key set.  emb_in: (B, 14, 14, 384) as produced by dct_oracle.embed_input(..., subblock=...).
+      embed_type 1  PatchEmbedding_DCT_Group.projection (plainvit.py:194-198): Linear + sincos + 'b h w e -> b (h w) e'
+      embed_type 2, sub-block  PatchEmbedding_DCT_Separate_subblock (:312-350): Linear(256) on Y | Linear(128) on CbCr -> GELU ->
+                    linearMix + residual -> sincos
+      embed_type 2, no sub-block  PatchEmbedding_DCT_Separate (:245-283): one Linear(64) per 8 x 8 block (4 luma, Cb, Cr) -> GELU ->
+                    LinearMix -> sincos.  Its rearrange puts the blocks side by side ('(c pdh pdw) (p1 p2)'); emb_in holds the
+                    un-converted 16 x 16 luma tile row-major, so block (pdh, pdw) is gathered from it here."""
+    b, h, w, _ = emb_in.shape
+    if "patchembed.projection.0.weight" in sd:
+        x = F.linear(emb_in, sd["patchembed.projection.0.weight"], sd["patchembed.projection.0.bias"])
+    elif "patchembed.projection_Y.1.weight" in sd:
+        y = F.linear(emb_in[..., :256], sd["patchembed.projection_Y.1.weight"], sd["patchembed.projection_Y.1.bias"])
+        c = F.linear(emb_in[..., 256:], sd["patchembed.projection_C.1.weight"], sd["patchembed.projection_C.1.bias"])
+        t = F.gelu(torch.cat([y, c], dim=3))
+        x = F.linear(t, sd["patchembed.linearMix.weight"], sd["patchembed.linearMix.bias"]) + t
+    else:
+        tile = emb_in[..., :256].reshape(b, h, w, 2, 8, 2, 8)                                    # (pdh p1) (pdw p2)
+        blocks = tile.permute(0, 1, 2, 3, 5, 4, 6).reshape(b, h, w, 4, 64)                       # (pdh pdw) (p1 p2)
+        outs = [F.linear(blocks[..., g, :], sd[f"patchembed.LinearY.{g}.weight"], sd[f"patchembed.LinearY.{g}.bias"]) for g in range(4)]
+        outs += [F.linear(emb_in[..., 256 + 64 * ci:320 + 64 * ci], sd[f"patchembed.LinearC.{ci}.weight"],
+                          sd[f"patchembed.LinearC.{ci}.bias"]) for ci in range(2)]
+        x = F.linear(F.gelu(torch.cat(outs, dim=3)), sd["patchembed.LinearMix.weight"], sd["patchembed.LinearMix.bias"])
+    e = x.shape[-1]
     return (x + sincos(h, w, e)).reshape(b, h * w, e)
 
 
@@ -70,13 +90,14 @@ def head(sd, x: torch.Tensor, emb: int) -> torch.Tensor:
     return F.linear(x, sd["classhead.ch_linear2.weight"], sd["classhead.ch_linear2.bias"])
 
 
-def forward(sd: Dict[str, torch.Tensor], yf: torch.Tensor, cf: torch.Tensor, depth: int = 12, upto_block=None) -> torch.Tensor:
+def forward(sd: Dict[str, torch.Tensor], yf: torch.Tensor, cf: torch.Tensor, depth: int = 12, upto_block=None,
+            subblock: bool = True) -> torch.Tensor:
     """ViT.forward(y, cbcr) (plainvit.py:601-612) on ToRange'd planes (B,1,28,28,8,8) + (B,2,14,14,8,8)."""
-    return forward_embedded(sd, O.embed_input(yf, cf), depth, upto_block)
+    return forward_embedded(sd, O.embed_input(yf, cf, subblock), depth, upto_block)
 
 
 def forward_embedded(sd, emb_in: torch.Tensor, depth: int = 12, upto_block=None) -> torch.Tensor:
-    emb = sd["patchembed.projection.0.weight"].shape[0]
+    emb = sd["classhead.ch_lrnorm.weight"].shape[0]
     heads = emb // 64
     x = tokens(sd, emb_in.reshape(emb_in.shape[0], 14, 14, 384))
     for l in range(depth):

@@ -260,6 +260,7 @@ extern "C" int rgbnm_k0_dcstats_ex(const int16_t* y, const int16_t* cbcr, const 
     using namespace k0;
     if (!y || !cbcr || !quant || !plans || !tables || !stats || n < 0) return RGBNM_ERR_ARG;
     if (hb < 2 || wb < 2 || hb > 255 || wb > 255 || (hb & 1) || (wb & 1)) return RGBNM_ERR_ARG;
+    if (layout == RGBNM_K0_LAYOUT_VIT16_NOSUB) layout = RGBNM_K0_LAYOUT_VIT16;      // same planes, only the embedding tail differs
     if (layout != RGBNM_K0_LAYOUT_VIT16 && layout != RGBNM_K0_LAYOUT_SWIN4) return RGBNM_ERR_ARG;
     if (n == 0) return RGBNM_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -598,7 +598,7 @@ static int launch_k0(const int16_t* y, const int16_t* cbcr, const int16_t* quant
 
 // second-generation ViT-layout kernel (k0_vit2.cu): packed fp32x2 arithmetic, quads of tokens
 int rgbnm_k0_vit2_launch(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans, const rgbnm_k0_tables* tables,
-                         const float* stats, void* out, int out_mode, int n, int hb, int wb, cudaStream_t st);
+                         const float* stats, void* out, int out_mode, int nosub, int n, int hb, int wb, cudaStream_t st);
 
 extern "C" int rgbnm_k0_fused_ex(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans,
                                  const rgbnm_k0_tables* tables, const float* stats, void* out, int out_mode, int layout,
@@ -607,9 +607,10 @@ extern "C" int rgbnm_k0_fused_ex(const int16_t* y, const int16_t* cbcr, const in
     if (hb < 2 || wb < 2 || hb > 255 || wb > 255 || (hb & 1) || (wb & 1)) return RGBNM_ERR_ARG;
     if (n == 0) return RGBNM_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (layout == RGBNM_K0_LAYOUT_VIT16_NOSUB) return rgbnm_k0_vit2_launch(y, cbcr, quant, plans, tables, stats, out, out_mode, 1, n, hb, wb, st);
     if (layout == RGBNM_K0_LAYOUT_VIT16) {
         static const bool v1 = getenv("RGBNM_K0_V1") != nullptr;      // first-generation kernel, A/B measurements only
-        if (!v1) return rgbnm_k0_vit2_launch(y, cbcr, quant, plans, tables, stats, out, out_mode, n, hb, wb, st);
+        if (!v1) return rgbnm_k0_vit2_launch(y, cbcr, quant, plans, tables, stats, out, out_mode, 0, n, hb, wb, st);
     }
 #define RGBNM_K0_CASE(OM, LY) \
     if (out_mode == OM && layout == LY) return launch_k0<OM, LY>(y, cbcr, quant, plans, tables, stats, out, n, hb, wb, st)

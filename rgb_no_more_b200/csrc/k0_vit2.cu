@@ -442,7 +442,9 @@ __device__ __forceinline__ void luma_first_loads(uint32_t info, int lane, const 
 // On entry info slot `slot` is traced and A holds the quad's first luma loads; if `has_next`, the next quad (ntr, ntp) of the
 // same image is traced into the other slot and its first loads are issued into A before the chroma column pass, so that they
 // are in flight during the tail of this quad.
-template <int OUT_MODE, int MODE_T, bool NOCLAMP_T>
+// NOSUB: RGBNM_K0_LAYOUT_VIT16_NOSUB (`--no_subblock`, plainvit.py:173-216 with use_subblock = False): no A16 products; the luma part of
+// the token is the 16 x 16 tile of the four un-converted blocks, row-major ('b c (h pdh) (w pdw) p1 p2 -> b c h w (pdh p1) (pdw p2)').
+template <int OUT_MODE, int MODE_T, bool NOCLAMP_T, bool NOSUB>
 __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int lane, int img, int tr, int tp, int mode_rt,
                                              const unsigned char* __restrict__ y_img, const unsigned char* __restrict__ c_img,
                                              const rgbnm_k0_tables& tb, const float* __restrict__ stats, void* __restrict__ out_, int wb,
@@ -484,7 +486,7 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
             __syncwarp();                                                  // S complete (transposed blocks are written across columns)
             if (OUT_MODE != RGBNM_K0_OUT_INT16_PLANES) {
                 // ---- P2b: column half of the sub-block conversion, in place: S -> A16 . S ------------------------------------
-                {
+                if (!NOSUB) {
                     p2 xl[8], xr[8], t[16];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { xl[i] = lds64(K.ccol + i * PITCH); xr[i] = lds64(K.ccol + (8 + i) * PITCH); }
@@ -501,24 +503,32 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
                         lds128(K.prow + 32 * j, xl[2 * j], xr[2 * j]);              // slots (2c, 2c + 1) = columns (c, c + 8)
                         lds128(K.prow + 32 * j + 16, xl[2 * j + 1], xr[2 * j + 1]);
                     }
-                    a16_1d_p(xl, xr, o);
+                    if (NOSUB) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { o[j] = xl[j]; o[8 + j] = xr[j]; }      // tile row as it stands
+                    } else {
+                        a16_1d_p(xl, xr, o);
+                    }
                     const size_t off = (size_t(img) * TOKENS + (2 * tr + p) * 14 + 2 * tp) * FEAT + c16 * 16;
+                    constexpr int HALF2 = 8;                       // element offset of the second 8 outputs of the row
                     if (OUT_MODE == RGBNM_K0_OUT_F32) {
-                        float4* d0 = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_) + off);
-                        float4* d1 = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_) + off + FEAT);
+                        float* f0 = reinterpret_cast<float*>(out_) + off;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            d0[j] = make_float4(lo_of(o[4 * j]), lo_of(o[4 * j + 1]), lo_of(o[4 * j + 2]), lo_of(o[4 * j + 3]));
-                            d1[j] = make_float4(hi_of(o[4 * j]), hi_of(o[4 * j + 1]), hi_of(o[4 * j + 2]), hi_of(o[4 * j + 3]));
+                            float4* d0 = reinterpret_cast<float4*>(f0 + (j >> 1) * HALF2 + (j & 1) * 4);
+                            float4* d1 = reinterpret_cast<float4*>(f0 + FEAT + (j >> 1) * HALF2 + (j & 1) * 4);
+                            *d0 = make_float4(lo_of(o[4 * j]), lo_of(o[4 * j + 1]), lo_of(o[4 * j + 2]), lo_of(o[4 * j + 3]));
+                            *d1 = make_float4(hi_of(o[4 * j]), hi_of(o[4 * j + 1]), hi_of(o[4 * j + 2]), hi_of(o[4 * j + 3]));
                         }
                     } else {
-                        uint4* d0 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_) + off);
-                        uint4* d1 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_) + off + FEAT);
+                        __nv_bfloat16* b0 = reinterpret_cast<__nv_bfloat16*>(out_) + off;
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
-                            d0[j] = make_uint4(bf2(lo_of(o[8 * j]), lo_of(o[8 * j + 1])), bf2(lo_of(o[8 * j + 2]), lo_of(o[8 * j + 3])),
+                            uint4* d0 = reinterpret_cast<uint4*>(b0 + j * HALF2);
+                            uint4* d1 = reinterpret_cast<uint4*>(b0 + FEAT + j * HALF2);
+                            *d0 = make_uint4(bf2(lo_of(o[8 * j]), lo_of(o[8 * j + 1])), bf2(lo_of(o[8 * j + 2]), lo_of(o[8 * j + 3])),
                                                bf2(lo_of(o[8 * j + 4]), lo_of(o[8 * j + 5])), bf2(lo_of(o[8 * j + 6]), lo_of(o[8 * j + 7])));
-                            d1[j] = make_uint4(bf2(hi_of(o[8 * j]), hi_of(o[8 * j + 1])), bf2(hi_of(o[8 * j + 2]), hi_of(o[8 * j + 3])),
+                            *d1 = make_uint4(bf2(hi_of(o[8 * j]), hi_of(o[8 * j + 1])), bf2(hi_of(o[8 * j + 2]), hi_of(o[8 * j + 3])),
                                                bf2(hi_of(o[8 * j + 4]), hi_of(o[8 * j + 5])), bf2(hi_of(o[8 * j + 6]), hi_of(o[8 * j + 7])));
                         }
                     }
@@ -628,7 +638,7 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
     __syncwarp();
 }
 
-template <int OUT_MODE>
+template <int OUT_MODE, bool NOSUB>
 __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM)
 k0_vit2_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, const int16_t* __restrict__ quant,
                const rgbnm_plan* __restrict__ plans, rgbnm_k0_tables tb, const float* __restrict__ stats_all, void* __restrict__ out_,
@@ -689,10 +699,10 @@ k0_vit2_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, 
         const int nrem = rem + 1, ntr = nrem / 7, ntp = nrem - ntr * 7;
         const float* stats = stats_all + size_t(img) * RGBNM_MAX_OPS * 2;
         if (OUT_MODE != RGBNM_K0_OUT_INT16_PLANES && mode == MODE_DOWN2 && ws.plan.clamp_in == 0)
-            process_quad<OUT_MODE, MODE_DOWN2, true>(ws, K, lane, img, tr, tp, mode, y_img, c_img, tb, stats, out_, wb, hc, wc, A, slot,
+            process_quad<OUT_MODE, MODE_DOWN2, true, NOSUB>(ws, K, lane, img, tr, tp, mode, y_img, c_img, tb, stats, out_, wb, hc, wc, A, slot,
                                                      has_next, ntr, ntp);
         else
-            process_quad<OUT_MODE, -1, false>(ws, K, lane, img, tr, tp, mode, y_img, c_img, tb, stats, out_, wb, hc, wc, A, slot,
+            process_quad<OUT_MODE, -1, false, NOSUB>(ws, K, lane, img, tr, tp, mode, y_img, c_img, tb, stats, out_, wb, hc, wc, A, slot,
                                               has_next, ntr, ntp);
         pre = has_next;
         if (has_next) slot ^= 1;
@@ -701,7 +711,7 @@ k0_vit2_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, 
 
 }  // namespace k0v2
 
-template <int OUT_MODE>
+template <int OUT_MODE, bool NOSUB>
 static int launch_vit2(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans, const rgbnm_k0_tables* tables,
                        const float* stats, void* out, int n, int hb, int wb, cudaStream_t st) {
     using namespace k0v2;
@@ -711,25 +721,29 @@ static int launch_vit2(const int16_t* y, const int16_t* cbcr, const int16_t* qua
         int dev = 0, v = 0;
         RGBNM_CUDA_CHECK(cudaGetDevice(&dev));
         RGBNM_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
-        RGBNM_CUDA_CHECK(cudaFuncSetAttribute(k0_vit2_kernel<OUT_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        RGBNM_CUDA_CHECK(cudaFuncSetAttribute(k0_vit2_kernel<OUT_MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        RGBNM_CUDA_CHECK(cudaFuncSetAttribute(k0_vit2_kernel<OUT_MODE, NOSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        RGBNM_CUDA_CHECK(cudaFuncSetAttribute(k0_vit2_kernel<OUT_MODE, NOSUB>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                               cudaSharedmemCarveoutMaxShared));
         sms = v;
     }
     const long long nq = (long long)n * QUADS_PER_IMAGE;
     long long ctas = (nq + WARPS - 1) / WARPS;
     if (ctas > (long long)sms * CTAS_PER_SM) ctas = (long long)sms * CTAS_PER_SM;
-    k0_vit2_kernel<OUT_MODE><<<int(ctas), WARPS * 32, smem, st>>>(y, cbcr, quant, plans, *tables, stats, out, n, hb, wb);
+    k0_vit2_kernel<OUT_MODE, NOSUB><<<int(ctas), WARPS * 32, smem, st>>>(y, cbcr, quant, plans, *tables, stats, out, n, hb, wb);
     RGBNM_CUDA_CHECK(cudaGetLastError());
     return RGBNM_OK;
 }
 
 // entry used by rgbnm_k0_fused_ex for RGBNM_K0_LAYOUT_VIT16
 int rgbnm_k0_vit2_launch(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans, const rgbnm_k0_tables* tables,
-                         const float* stats, void* out, int out_mode, int n, int hb, int wb, cudaStream_t st) {
-    if (out_mode == RGBNM_K0_OUT_F32) return launch_vit2<RGBNM_K0_OUT_F32>(y, cbcr, quant, plans, tables, stats, out, n, hb, wb, st);
-    if (out_mode == RGBNM_K0_OUT_BF16) return launch_vit2<RGBNM_K0_OUT_BF16>(y, cbcr, quant, plans, tables, stats, out, n, hb, wb, st);
-    if (out_mode == RGBNM_K0_OUT_INT16_PLANES)
-        return launch_vit2<RGBNM_K0_OUT_INT16_PLANES>(y, cbcr, quant, plans, tables, stats, out, n, hb, wb, st);
+                         const float* stats, void* out, int out_mode, int nosub, int n, int hb, int wb, cudaStream_t st) {
+#define RGBNM_VIT2_CASE(OM) \
+    if (out_mode == OM) return nosub ? launch_vit2<OM, true>(y, cbcr, quant, plans, tables, stats, out, n, hb, wb, st) \
+                                     : launch_vit2<OM, false>(y, cbcr, quant, plans, tables, stats, out, n, hb, wb, st)
+    RGBNM_VIT2_CASE(RGBNM_K0_OUT_F32);
+    RGBNM_VIT2_CASE(RGBNM_K0_OUT_BF16);
+    if (out_mode == RGBNM_K0_OUT_INT16_PLANES)      // the int16 planes do not depend on the embedding layout
+        return launch_vit2<RGBNM_K0_OUT_INT16_PLANES, false>(y, cbcr, quant, plans, tables, stats, out, n, hb, wb, st);
+#undef RGBNM_VIT2_CASE
     return RGBNM_ERR_ARG;
 }

@@ -19,7 +19,7 @@ from . import lib as _lib
 from . import plan as P
 
 OUT_F32, OUT_BF16, OUT_INT16_PLANES = 0, 1, 2
-LAYOUT_VIT16, LAYOUT_SWIN4 = 0, 1
+LAYOUT_VIT16, LAYOUT_SWIN4, LAYOUT_VIT16_NOSUB = 0, 1, 2
 PLANE_ELEMS = (28 * 28 + 2 * 14 * 14) * 64
 # out_size (luma blocks per side after the resize) -> (layout, tokens, features per token)
 GEOMETRY = {28: (LAYOUT_VIT16, 196, 384), 32: (LAYOUT_SWIN4, 4096, 24)}
@@ -31,17 +31,23 @@ class FusedDCT:
     >>> tf = FusedDCT(device, kind="train", ops_list=plan.AUGLIST_VITS, num_ops=2, ops_magnitude=9)
     >>> x = tf(y_q, c_q, quant)            # (B,196,384) operand of the patch-projection Linear
 
-    `out_size=32` selects the SwinV2 data path (datasets.py:370-382, models/swinv2.py:505-576): planes resized to
+    `subblock=False` (ViT only) writes the `--no_subblock` operand: the same token layout with the un-converted 16 x 16 luma tile
+    (four 8 x 8 blocks, no A16 products).  `out_size=32` selects the SwinV2 data path (datasets.py:370-382, models/swinv2.py:505-576): planes resized to
     32 x 32 luma blocks, every 8 x 8 block decomposed into 4 x 4 (Y) / 2 x 2 (CbCr) sub-blocks -> (B, 4096, 24).
     """
 
     def __init__(self, device, kind: str = "test", ops_list: Optional[Sequence[str]] = None, num_ops: int = 2,
-                 ops_magnitude: int = 10, out_dtype: torch.dtype = torch.float32, out_size: int = 28):
+                 ops_magnitude: int = 10, out_dtype: torch.dtype = torch.float32, out_size: int = 28, subblock: bool = True):
         if out_size not in GEOMETRY:
             raise NotImplementedError("rgbnm: only the 28-block (ViT, patch 16) and 32-block (SwinV2, patch 4) geometries "
                                       "are on the hot path")
         self.out_size = out_size
         self.layout, self.tokens, self.feat = GEOMETRY[out_size]
+        if not subblock:
+            # `--no_subblock` (use_subblock = False, plainvit.py:173-216): the luma tile of a token stays un-converted
+            if out_size != 28:
+                raise NotImplementedError("rgbnm: SwinV2's patch-4 embedding always decomposes blocks (models/swinv2.py:505-576)")
+            self.layout = LAYOUT_VIT16_NOSUB
         self.plane_elems = (out_size * out_size + 2 * (out_size // 2) ** 2) * 64
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -161,15 +167,15 @@ def split_planes(planes: torch.Tensor, out_size: int = 28):
 
 
 def get_transform(dataset: str = "imagenet_dct", type: str = "train", ops_list=None, num_ops: int = 2,
-                  ops_magnitude: int = 10, dtype=torch.float32, device="cuda"):
+                  ops_magnitude: int = 10, dtype=torch.float32, device="cuda", subblock: bool = True):
     """Same selector as the reference's datasets.get_transform (datasets.py:305-390) for the
     DCT datasets; returns a batch transform bound to `device`."""
     if dataset not in ("imagenet_dct", "imagenet_dct_swin"):
         raise NotImplementedError(f"rgbnm: dataset '{dataset}' is outside the B200 hot path (SURVEY.md 8f)")
     size = 28 if dataset == "imagenet_dct" else 32          # datasets.py:355-366 / :370-382
     if type == "train":
-        return FusedDCT(device, "train", ops_list, num_ops, ops_magnitude, dtype, out_size=size)
+        return FusedDCT(device, "train", ops_list, num_ops, ops_magnitude, dtype, out_size=size, subblock=subblock)
     if type in ("val", "test"):
-        return FusedDCT(device, "test", None, 0, 0, dtype, out_size=size)
+        return FusedDCT(device, "test", None, 0, 0, dtype, out_size=size, subblock=subblock)
     print("Unrecognized dataset type! Returning 'None' transform")
     return None

@@ -52,11 +52,16 @@ def sincos_posemb(h: int, w: int, e: int, device) -> torch.Tensor:
     return torch.cat((pw.sin(), pw.cos(), ph.sin(), ph.cos()), dim=-1).contiguous()
 
 
-def embed_input_from_planes(y: torch.Tensor, cbcr: torch.Tensor) -> torch.Tensor:
+def embed_input_from_planes(y: torch.Tensor, cbcr: torch.Tensor, subblock: bool = True) -> torch.Tensor:
     """Compatibility path for reference-format inputs (B,1,28,28,8,8) + (B,2,14,14,8,8), already ToRange'd:
     the tail of the fused kernel (2x2 luma blocks -> 16x16 sub-block, collapse, concat; plainvit.py:200-216)
-    expressed with torch ops on the GPU.  The fast path never comes here: FusedDCT writes this tensor directly."""
+    expressed with torch ops on the GPU.  The fast path never comes here: FusedDCT writes this tensor directly.
+    subblock = False: the un-converted 16 x 16 tile (`--no_subblock`, FusedDCT(subblock=False))."""
     b = y.shape[0]
+    if not subblock:
+        yy = y.float().reshape(b, 14, 2, 14, 2, 8, 8).permute(0, 1, 3, 2, 5, 4, 6).reshape(b, 14, 14, 256)
+        cc = cbcr.float().permute(0, 2, 3, 1, 4, 5).reshape(b, 14, 14, 128)
+        return torch.cat([yy, cc], dim=3).reshape(b, TOKENS, IN_FEAT)
     n = torch.arange(8, dtype=torch.float32, device=y.device)
 
     def basis(L):
@@ -77,12 +82,19 @@ def embed_input_from_planes(y: torch.Tensor, cbcr: torch.Tensor) -> torch.Tensor
 # Engine
 # ------------------------------------------------------------------------------------------------
 class _Lin:
-    """One nn.Linear of the model: fp32 master views + bf16 working copies."""
+    """One nn.Linear of the model: fp32 master views + bf16 working copies.  `weight` / `bias` may also be plain fp32 tensors
+    assembled from several parameters (the block-diagonal first stage of the separate embeddings)."""
 
-    def __init__(self, name: str, weight: nn.Parameter, bias: nn.Parameter, qkv_heads: int = 0):
+    def __init__(self, name: str, weight, bias, qkv_heads: int = 0):
         self.name, self.weight, self.bias, self.qkv_heads = name, weight, bias, qkv_heads
         self.n, self.k = weight.shape
         self.wb = self.wt = self.bias_k = None      # bf16 [n,k], bf16 [k,n], fp32 bias in kernel order
+
+
+def _gelu_grad(u: torch.Tensor) -> torch.Tensor:
+    """d/du gelu_erf(u) (nn.GELU() default), fp32."""
+    uf = u.float()
+    return 0.5 * (1.0 + torch.erf(uf * 0.7071067811865476)) + uf * torch.exp(-0.5 * uf * uf) * 0.3989422804014327
 
 
 class ViTEngine:
@@ -118,7 +130,38 @@ class ViTEngine:
                 off += n
         self.params = named
         P = named
-        self.lin_embed = _Lin("embed", P["patchembed.projection.0.weight"], P["patchembed.projection.0.bias"])
+        # patch embedding (plainvit.py:140-283): "group" = one Linear on the K0 operand (embed_type 1); "sep_sub" / "sep" = embed_type 2
+        # with / without sub-block conversion: per-group Linears (a block-diagonal first stage, assembled into ONE [E, 384] matrix on
+        # the K0 column order) -> GELU -> channel-mixing Linear (+ residual for sep_sub)
+        self.embed_kind = model.embed_kind
+        self.lin_mix = None
+        if self.embed_kind == "group":
+            self.lin_embed = _Lin("embed", P["patchembed.projection.0.weight"], P["patchembed.projection.0.bias"])
+        else:
+            self.emb_groups = []          # (weight param, bias param, first output row, K0 column index of every input feature)
+            if self.embed_kind == "sep_sub":
+                wy, wc = P["patchembed.projection_Y.1.weight"], P["patchembed.projection_C.1.weight"]
+                self.emb_groups.append((wy, P["patchembed.projection_Y.1.bias"], 0, torch.arange(0, 256, device=device)))
+                self.emb_groups.append((wc, P["patchembed.projection_C.1.bias"], wy.shape[0], torch.arange(256, 384, device=device)))
+                mix = ("patchembed.linearMix.weight", "patchembed.linearMix.bias")
+            else:
+                eo = self.E // 6
+                p12 = torch.arange(64, device=device)
+                for g in range(4):        # LinearY[g]: block (pdh, pdw) = (g // 2, g % 2) of the un-converted 16 x 16 tile, row-major
+                    cols = ((g // 2) * 8 + p12 // 8) * 16 + (g % 2) * 8 + p12 % 8
+                    self.emb_groups.append((P[f"patchembed.LinearY.{g}.weight"], P[f"patchembed.LinearY.{g}.bias"], g * eo, cols))
+                for ci in range(2):
+                    self.emb_groups.append((P[f"patchembed.LinearC.{ci}.weight"], P[f"patchembed.LinearC.{ci}.bias"], (4 + ci) * eo,
+                                            256 + ci * 64 + p12))
+                mix = ("patchembed.LinearMix.weight", "patchembed.LinearMix.bias")
+            n1 = sum(g[0].shape[0] for g in self.emb_groups)
+            if n1 != self.E:
+                raise NotImplementedError("rgbnm: separate embeddings need emb_size divisible by 6")
+            self.W1 = torch.zeros((n1, IN_FEAT), dtype=torch.float32, device=device)
+            self.b1 = torch.zeros(n1, dtype=torch.float32, device=device)
+            self.gW1 = torch.zeros_like(self.W1)
+            self.lin_embed = _Lin("embed1", self.W1, self.b1)
+            self.lin_mix = _Lin("mix", P[mix[0]], P[mix[1]])
         self.layers = []
         for l in range(self.depth):
             pre = f"encoder.{l}."
@@ -141,6 +184,7 @@ class ViTEngine:
             if lin.qkv_heads:
                 lin.bias_k = torch.empty(lin.n, dtype=torch.float32, device=device)
         self.posemb = sincos_posemb(14, 14, self.E, device)
+        self.posemb_bf16 = self.posemb.to(torch.bfloat16)
         self._versions = None
         self._wprep = None
         self.bufs = None
@@ -149,7 +193,7 @@ class ViTEngine:
         self.refresh_weights()
 
     def _all_lins(self) -> List[_Lin]:
-        out = [self.lin_embed]
+        out = [self.lin_embed] + ([self.lin_mix] if self.lin_mix is not None else [])
         for ly in self.layers:
             out += [ly["qkv"], ly["proj"], ly["fc1"], ly["fc2"]]
         return out
@@ -161,6 +205,11 @@ class ViTEngine:
     def refresh_weights(self) -> None:
         """fp32 master -> bf16 working copies (+ transposes for dgrad, qkv rows and bias regrouped q|k|v): one launch
         over a device-resident descriptor table (the pointers into the flat buffer never change)."""
+        if self.embed_kind != "group":
+            with torch.no_grad():         # assemble the block-diagonal first stage on the K0 column order
+                for w, b, r0, cols in self.emb_groups:
+                    self.W1[r0:r0 + w.shape[0]].index_copy_(1, cols, w.data)
+                    self.b1[r0:r0 + w.shape[0]].copy_(b.data)
         if self._wprep is None:
             import ctypes as C
             import numpy as np
@@ -169,7 +218,7 @@ class ViTEngine:
             tiles = 0
             for i, lin in enumerate(lins):
                 d = arr[i]
-                d.w, d.w_bf16, d.wt_bf16 = lin.weight.data.data_ptr(), lin.wb.data_ptr(), lin.wt.data_ptr()
+                d.w, d.w_bf16, d.wt_bf16 = lin.weight.data_ptr(), lin.wb.data_ptr(), lin.wt.data_ptr()
                 d.bias = lin.bias.data.data_ptr() if lin.qkv_heads else None
                 d.bias_k = lin.bias_k.data_ptr() if lin.qkv_heads else None
                 d.n, d.k, d.qkv_heads, d.head_dim, d.first_tile = lin.n, lin.k, lin.qkv_heads, self.D if lin.qkv_heads else 0, tiles
@@ -201,7 +250,9 @@ class ViTEngine:
                           u=torch.empty((M, 4 * E), **bf), f=torch.empty((M, 4 * E), **bf), x_out=torch.empty((M, E), **bf),
                           mean1=torch.empty(M, **f32), rstd1=torch.empty(M, **f32), mean2=torch.empty(M, **f32),
                           rstd2=torch.empty(M, **f32), lse=torch.empty((B, self.H, TOKENS), **f32)))
-        self.bufs = dict(layers=L, x0=torch.empty((M, E), **bf), hN=torch.empty((M, E), **bf), meanH=torch.empty(M, **f32),
+        extra = {} if self.embed_kind == "group" else dict(emb_u=torch.empty((M, E), **bf), emb_f=torch.empty((M, E), **bf),
+                                                           emb_df=torch.empty((M, E), **bf))
+        self.bufs = dict(layers=L, **extra, x0=torch.empty((M, E), **bf), hN=torch.empty((M, E), **bf), meanH=torch.empty(M, **f32),
                          rstdH=torch.empty(M, **f32),
                          # backward scratch (shared by all layers)
                          dA=torch.empty((M, E), **bf), dB=torch.empty((M, E), **bf), dC=torch.empty((M, E), **bf),
@@ -242,7 +293,16 @@ class ViTEngine:
         self._alloc(B)
         bufs = self.bufs
         bufs["x_embed_in"] = x_in
-        x = self._gemm(x_in, self.lin_embed.wb, G.EPI_POSEMB, bias=self.lin_embed.bias.data, posemb=self.posemb, out=bufs["x0"])
+        if self.embed_kind == "group":
+            x = self._gemm(x_in, self.lin_embed.wb, G.EPI_POSEMB, bias=self.lin_embed.bias.data, posemb=self.posemb, out=bufs["x0"])
+        else:
+            # per-group Linears -> GELU (plainvit.py:263-271, 342-347) -> channel mix (+ residual, :348-350) -> sincos
+            self._gemm(x_in, self.lin_embed.wb, G.EPI_GELU, bias=self.b1, out=bufs["emb_u"], out2=bufs["emb_f"])
+            if self.embed_kind == "sep_sub":
+                x = self._gemm(bufs["emb_f"], self.lin_mix.wb, G.EPI_RESIDUAL, bias=self.lin_mix.bias.data, aux=bufs["emb_f"], out=bufs["x0"])
+                x.view(B, TOKENS, self.E).add_(self.posemb_bf16)
+            else:
+                x = self._gemm(bufs["emb_f"], self.lin_mix.wb, G.EPI_POSEMB, bias=self.lin_mix.bias.data, posemb=self.posemb, out=bufs["x0"])
         for l, ly in enumerate(self.layers):
             b = bufs["layers"][l]
             b["x_in"] = x
@@ -329,11 +389,26 @@ class ViTEngine:
             self._attn_bwd(do, b["qkv"], b["o"], b["lse"], bufs["dQKV"], B)
             self._wgrad(bufs["dQKV"], b["h1"], ly["qkv"], splits)
             dh1 = self._gemm(bufs["dQKV"], ly["qkv"].wt, G.EPI_STORE, out=spare1)
-            below = self.layers[l - 1]["fc2"].bias if l > 0 else self.lin_embed.bias
+            below = self.layers[l - 1]["fc2"].bias if l > 0 else (self.lin_embed.bias if self.lin_mix is None else self.lin_mix.bias)
             K.layernorm_bwd(dh1, b["x_in"], b["mean1"], b["rstd1"], ly["ln1"][0].data, dx_mid, dx,
                             self.grad_of(ly["ln1"][0]), self.grad_of(ly["ln1"][1]), dxsum=self.grad_of(below))
             self.launches += 1
-        self._wgrad(dx, bufs["x_embed_in"], self.lin_embed, splits, bias_done=True)
+        if self.embed_kind == "group":
+            self._wgrad(dx, bufs["x_embed_in"], self.lin_embed, splits, bias_done=True)
+            return
+        # separate embeddings: x0 = mix(f) (+ f) + posemb, f = gelu(u), u = x_in W1^T + b1
+        self._wgrad(dx, bufs["emb_f"], self.lin_mix, splits, bias_done=True)
+        if self.embed_kind == "sep_sub":
+            df = self._gemm(dx, self.lin_mix.wt, G.EPI_RESIDUAL, aux=dx, out=bufs["emb_df"])
+        else:
+            df = self._gemm(dx, self.lin_mix.wt, G.EPI_STORE, out=bufs["emb_df"])
+        du = (df.float() * _gelu_grad(bufs["emb_u"])).to(torch.bfloat16)
+        self.gW1.zero_()
+        self._wgrad_gemm(du, bufs["x_embed_in"], self.gW1, splits)
+        db1 = du.float().sum(0)
+        for w, b, r0, cols in self.emb_groups:            # the assembled matrix back to the parameters it was built from
+            self.grad_of(w).add_(self.gW1[r0:r0 + w.shape[0]].index_select(1, cols))
+            self.grad_of(b).add_(db1[r0:r0 + w.shape[0]])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -362,9 +437,12 @@ class ViT(nn.Module):
                  depth: int = 12, n_classes: int = 1000, drop_p=0.1, pixel_space="RGB", ver=1, use_subblock=True,
                  device="cpu", dtype=torch.float32, num_heads: int = 8, head_size: int = 64, **kwargs):
         super().__init__()
-        if str(pixel_space).lower() != "dct" or ver != 1 or not use_subblock or patch_size != 16:
-            raise NotImplementedError("rgbnm: only pixel_space='DCT', ver=1, use_subblock=True, patch_size=16 is on the "
-                                      "B200 hot path (SURVEY.md 8f rank 4)")
+        if str(pixel_space).lower() not in ("dct", "rgb2dct") or patch_size != 16:
+            raise NotImplementedError("rgbnm: only the DCT pixel space with patch_size=16 is on the B200 hot path (SURVEY.md 8f)")
+        if ver not in (1, 2):
+            # embed_type 3 (PatchEmbedding_DCT_Concat, plainvit.py:352-410) makes 294 tokens (196 luma + 2 x 49 chroma): a different
+            # sequence length than the attention kernels are built for
+            raise NotImplementedError("rgbnm: embed_type 3 (concatenated Y / CbCr token sequences) is outside the B200 hot path")
         if drop_p not in (0, 0.0):
             raise NotImplementedError("rgbnm: dropout > 0 is not on the hot path (reference default TRAIN.DROP = 0.0)")
         if input_embed not in (-1, emb_size) or num_heads * head_size != emb_size or head_size != 64:
@@ -376,13 +454,25 @@ class ViT(nn.Module):
         self.emb_size, self.depth, self.n_classes = emb_size, depth, n_classes
         self.num_heads, self.head_size = num_heads, head_size
         self.pixel_space = pixel_space
+        self.ver, self.use_subblock = ver, bool(use_subblock)
+        self.embed_kind = "group" if ver == 1 else ("sep_sub" if use_subblock else "sep")
         E, HD = emb_size, num_heads * head_size
         dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
 
         def lin(i, o):
             return nn.Linear(i, o, device=dev, dtype=torch.float32)
         self.patchembed = _Box()
-        self.patchembed.projection = nn.Sequential(lin(IN_FEAT, E))
+        if self.embed_kind == "group":            # PatchEmbedding_DCT_Group (plainvit.py:173-216), with or without sub-block conversion
+            self.patchembed.projection = nn.Sequential(lin(IN_FEAT, E))
+        elif self.embed_kind == "sep_sub":        # PatchEmbedding_DCT_Separate_subblock (:285-350)
+            self.patchembed.projection_Y = nn.Sequential(nn.Identity(), lin(256, E // 6 * 4))
+            self.patchembed.projection_C = nn.Sequential(nn.Identity(), lin(128, E // 6 * 2))
+            self.patchembed.linearMix = lin(E, E)
+        else:                                     # PatchEmbedding_DCT_Separate (:220-283); `projection.1` is the same module as LinearMix
+            self.patchembed.LinearY = nn.ModuleList([lin(64, E // 6) for _ in range(4)])
+            self.patchembed.LinearC = nn.ModuleList([lin(64, E // 6) for _ in range(2)])
+            self.patchembed.LinearMix = lin(E // 6 * 6, E)
+            self.patchembed.projection = nn.Sequential(nn.Identity(), self.patchembed.LinearMix)
         blocks = []
         for _ in range(depth):
             mha = _Box()
@@ -423,7 +513,7 @@ class ViT(nn.Module):
         """forward(y, cbcr) with reference-format tensors (plainvit.py:601-612), or forward(x) with the
         (B,196,384) tensor FusedDCT writes."""
         if cbcr is not None:
-            x = embed_input_from_planes(x, cbcr)
+            x = embed_input_from_planes(x, cbcr, subblock=self.use_subblock)
         elif x.dim() != 3 or x.shape[1:] != (TOKENS, IN_FEAT):
             raise ValueError("rgbnm ViT: expected (y, cbcr) in the reference layout or a (B,196,384) embed input")
         eng = self.prepare(x.device)

@@ -316,3 +316,40 @@ def test_bad_arguments_fail_loudly():
         tf.run(y.to(DEV), c.to(DEV), q.to(DEV), [P.Plan(0, 0, 20)] * 2)           # unsupported crop size
     with pytest.raises(ValueError):
         tf.run(y, c, q, [P.Plan(0, 0, 28)] * 2)                                    # host tensors
+
+
+@pytest.mark.parametrize("crop", [14, 28, 56])
+def test_embed_input_without_subblock_conversion(crop):
+    """--no_subblock (RGBNM_K0_LAYOUT_VIT16_NOSUB): the luma 16 x 16 tile stays four un-converted 8 x 8 blocks, written row-major
+    '(pdh p1) (pdw p2)' as PatchEmbedding_DCT_Group does without sub-block conversion (plainvit.py:176-183).  No arithmetic after
+    ToRange on this path -> bit exact in f32, one bf16 rounding in bf16."""
+    B = 8
+    y, c, q = _random_batch(B, 91 + crop, False)
+    plans = [P.Plan(crop_i=2 * (b % 3), crop_j=4, crop_size=crop, flip=bool(b & 1), train=False, ops=[]) for b in range(B)]
+    tf = TF.FusedDCT(DEV, "test", subblock=False)
+    tfs = TF.FusedDCT(DEV, "test")
+    out = tf.run(y.to(DEV), c.to(DEV), q.to(DEV), plans, out_mode=TF.OUT_F32).cpu()
+    outb = tf.run(y.to(DEV), c.to(DEV), q.to(DEV), plans, out_mode=TF.OUT_BF16).cpu()
+    sub = tfs.run(y.to(DEV), c.to(DEV), q.to(DEV), plans, out_mode=TF.OUT_F32).cpu()
+    py, pc = _run_planes(tf, y, c, q, plans)
+    for b in range(B):
+        ref = O.embed_input(O.to_range(py[b]).unsqueeze(0), O.to_range(pc[b]).unsqueeze(0), subblock=False).reshape(196, 384)
+        assert torch.equal(out[b], ref)
+        assert torch.equal(outb[b], ref.to(torch.bfloat16))
+        assert torch.equal(out[b][:, 256:], sub[b][:, 256:])                    # chroma columns do not depend on the switch
+    assert not torch.equal(out[:, :, :256], sub[:, :, :256])
+
+
+def test_train_plans_without_subblock_conversion():
+    """Training plans (resize, ops, flip) through the no-subblock layout: same planes as the sub-block layout, only the last
+    stage differs."""
+    B = 16
+    y, c, q = _random_batch(B, 5, True)
+    tf = TF.FusedDCT(DEV, "train", P.AUGLIST_VITS, 2, 9, subblock=False)
+    torch.manual_seed(3)
+    plans = tf.sample_plans(B)
+    out = tf.run(y.to(DEV), c.to(DEV), q.to(DEV), plans, out_mode=TF.OUT_F32).cpu()
+    py, pc = _run_planes(tf, y, c, q, plans)
+    for b in range(B):
+        ref = O.embed_input(O.to_range(py[b]).unsqueeze(0), O.to_range(pc[b]).unsqueeze(0), subblock=False).reshape(196, 384)
+        assert torch.equal(out[b], ref), b

@@ -188,3 +188,38 @@ def test_vit_oracle_train_step_matches_reference_loop():
         d_got = sd[k].reshape(-1)[:4096].numpy() - init[k].reshape(-1)[:4096].numpy()
         cos = float((d_ref * d_got).sum() / (np.linalg.norm(d_ref) * np.linalg.norm(d_got) + 1e-30))
         assert cos > 0.999, (k, cos)         # fp32 both sides; Adam's m / sqrt(v) amplifies last-bit gradient differences near 0
+
+
+@pytest.mark.parametrize("ver,sub", [(2, True), (2, False), (1, False)])
+def test_vit_oracle_embedding_variants_match_reference(ver, sub):
+    """embed_type 2 (with / without sub-block conversion) and embed_type 1 --no_subblock: oracle tokens / logits / loss / embedding
+    gradients vs the reference's own pvit.ViT (tests/golden/embed_variants.npz, tools/make_golden.py::gen_embed_variants)."""
+    from oracle import vit_oracle as VO
+    from tests.helpers import seeded_state_dict, golden_vits_inputs
+    from rgb_no_more_b200 import vit as V
+    g = load("embed_variants.npz")
+    tag = f"v{ver}{'s' if sub else 'n'}"
+    shell = V.ViT(patch_size=16, emb_size=192, depth=2, n_classes=1000, drop_p=0.0, num_heads=3, head_size=64, pixel_space="DCT",
+                  ver=ver, use_subblock=sub)
+    assert sorted(shell.state_dict().keys()) == list(g[f"{tag}:state_keys"])
+    # through load_state_dict, like the generator: PatchEmbedding_DCT_Separate registers its mixing Linear twice (LinearMix and
+    # projection.1 are one tensor), so the two seeded entries collapse to whichever is loaded last -- in both module trees
+    shell.load_state_dict(seeded_state_dict(shell))
+    sd = {k: v.detach().clone() for k, v in shell.state_dict().items()}
+    yf, cf = golden_vits_inputs(g["input_seed"], batch=3)
+    emb_in = O.embed_input(yf, cf, subblock=sub)
+    assert np.abs(VO.tokens(sd, emb_in)[0].numpy() - g[f"{tag}:tokens"]).max() < 5e-5
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    logits = VO.forward_embedded(params, emb_in, depth=2)
+    assert np.abs(logits.detach().numpy() - g[f"{tag}:logits"]).max() < 2e-4
+    labels = torch.zeros((3, 1000))
+    labels[0, 3], labels[0, 7], labels[1, 999], labels[2, 500] = 0.7, 0.3, 1.0, 1.0
+    loss = torch.nn.CrossEntropyLoss()(logits, labels)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g[f"{tag}:loss"])) < 1e-4
+    for key in g.files:
+        if key.startswith(f"{tag}:grad:"):
+            k = key.split(":", 2)[2]
+            ref = g[key]
+            got = params[k].grad.reshape(-1)[:ref.size].numpy()
+            assert np.abs(got - ref).max() < 2e-4 * max(1e-3, np.abs(ref).max()), k

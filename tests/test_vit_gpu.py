@@ -351,3 +351,54 @@ def test_train_stage_follows_reference_optimiser_loop(use_graph):
         assert cos > 0.9, (k, cos)
         assert abs(float(d_got.norm()) / float(d_ref.norm()) - 1.0) < 5e-2, k
         # and the decoupled decay acted on '.weight' matrices only (custom_optims.py:37-43): covered by the size check above
+
+
+# ---- embed_type 2 and --no_subblock, against the reference's own modules ---------------------------
+@pytest.mark.parametrize("ver,sub", [(2, True), (2, False), (1, False)])
+def test_embedding_variants_match_reference(ver, sub):
+    """PatchEmbedding_DCT_Separate_subblock / _Separate / _Group without sub-block conversion (plainvit.py:312-350, :245-283,
+    :146-198) on the tcgen05 path: tokens of image 0 (the engine's encoder-input buffer), logits, loss and every embedding gradient vs tests/golden/embed_variants.npz (the reference's pvit.ViT, fp32)."""
+    from tests.helpers import golden_vits_inputs
+    g = load("embed_variants.npz")
+    tag = f"v{ver}{'s' if sub else 'n'}"
+    m = V.ViT(patch_size=16, emb_size=192, depth=2, n_classes=1000, drop_p=0.0, num_heads=3, head_size=64, pixel_space="DCT",
+              ver=ver, use_subblock=sub)
+    assert sorted(m.state_dict().keys()) == list(g[f"{tag}:state_keys"])
+    m.load_state_dict(seeded_state_dict(m))
+    m = m.to(DEV)
+    yf, cf = golden_vits_inputs(g["input_seed"], batch=3)
+    m.eval()
+    with torch.no_grad():
+        logits = m(yf.to(DEV), cf.to(DEV)).float().cpu()
+    ref = torch.from_numpy(g[f"{tag}:logits"])
+    assert float((logits - ref).abs().max()) < 2e-2 * float(ref.abs().max()), (float((logits - ref).abs().max()), float(ref.abs().max()))
+    tok = m.prepare().bufs["x0"].view(3, 196, 192)[0].float().cpu()             # the encoder's input of the forward just run
+    rt = torch.from_numpy(g[f"{tag}:tokens"])
+    assert float((tok - rt).abs().max()) < 2e-2 * float(rt.abs().max()), float((tok - rt).abs().max())
+    m.train()
+    labels = torch.zeros((3, 1000))
+    labels[0, 3], labels[0, 7], labels[1, 999], labels[2, 500] = 0.7, 0.3, 1.0, 1.0
+    loss = torch.nn.CrossEntropyLoss()(m(yf.to(DEV), cf.to(DEV)), labels.to(DEV))
+    loss.backward()
+    assert abs(float(loss) - float(g[f"{tag}:loss"])) < 1e-2 * abs(float(g[f"{tag}:loss"]))
+    sd = dict(m.named_parameters())
+    seen = 0
+    for key in g.files:
+        if key.startswith(f"{tag}:grad:"):
+            k = key.split(":", 2)[2]
+            if k not in sd:                                                     # an alias key of a shared tensor (LinearMix / projection.1)
+                continue
+            refg = torch.from_numpy(g[key])
+            got = sd[k].grad.reshape(-1).float().cpu()[:refg.numel()]
+            cos = float(F.cosine_similarity(got, refg, dim=0))
+            assert cos > 0.99, (k, cos)
+            gn = float(g[f"{tag}:gradnorm:" + k])
+            assert abs(float(sd[k].grad.norm()) - gn) < 5e-2 * gn, (k, float(sd[k].grad.norm()), gn)
+            seen += 1
+    assert seen >= 4
+
+
+def test_embed_type_3_is_refused():
+    """PatchEmbedding_DCT_Concat yields 294 tokens (plainvit.py:352-389): outside the drop-in's scope, and it says so."""
+    with pytest.raises(NotImplementedError):
+        V.ViT(patch_size=16, emb_size=192, depth=2, n_classes=10, num_heads=3, head_size=64, pixel_space="DCT", ver=3, use_subblock=True)

@@ -366,9 +366,42 @@ def gen_vit_s():
     print("vit_s done; loss", float(loss), "train losses", losses)
 
 
+EMBED_VARIANTS = ((2, True), (2, False), (1, False))          # (embed_type, use_subblock); (1, True) is embed_vit.npz / vit_s.npz
+
+
+def gen_embed_variants():
+    """The other patch embeddings of `--domain dct`: embed_type 2 with / without sub-block conversion
+    (PatchEmbedding_DCT_Separate_subblock / _Separate, plainvit.py:220-350) and embed_type 1 with --no_subblock, from the
+    reference's own pvit.ViT (E = 192, depth 2, batch 3): tokens, logits, loss and the gradients of every embedding parameter."""
+    out = {"input_seed": np.int64(6)}
+    yf, cf = golden_vits_inputs(6, batch=3)
+    labels = torch.zeros((3, 1000))
+    labels[0, 3], labels[0, 7], labels[1, 999], labels[2, 500] = 0.7, 0.3, 1.0, 1.0
+    for ver, sub in EMBED_VARIANTS:
+        tag = f"v{ver}{'s' if sub else 'n'}"
+        model = pvit.ViT(patch_size=16, emb_size=192, depth=2, n_classes=1000, drop_p=0.0, num_heads=3, head_size=64,
+                         pixel_space="DCT", ver=ver, use_subblock=sub)
+        model.load_state_dict(seeded_state_dict(model))
+        model.eval()
+        with torch.no_grad():
+            out[f"{tag}:tokens"] = model.patchembed(yf, cf)[0].numpy()
+            out[f"{tag}:logits"] = model(yf, cf).numpy()
+        model.train()
+        loss = torch.nn.CrossEntropyLoss()(model(yf, cf), labels)
+        loss.backward()
+        out[f"{tag}:loss"] = loss.detach().numpy()
+        for k, p_ in model.named_parameters():
+            if k.startswith("patchembed") or k in ("encoder.0.0.fn.eb_mha.qkv.weight", "classhead.ch_linear2.bias"):
+                out[f"{tag}:grad:{k}"] = p_.grad.reshape(-1)[:4096].numpy()
+                out[f"{tag}:gradnorm:{k}"] = p_.grad.norm().numpy()
+        out[f"{tag}:state_keys"] = np.array(sorted(model.state_dict().keys()))
+    np.savez_compressed(os.path.join(OUT, "embed_variants.npz"), **out)
+    print("embed_variants done")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    todo = sys.argv[1:] or ["ops_small", "ops_extra", "resize", "pipeline", "embed_vit", "vit_s"]
+    todo = sys.argv[1:] or ["ops_small", "ops_extra", "resize", "pipeline", "embed_vit", "vit_s", "embed_variants"]
     for name in todo:
         globals()["gen_" + name]()
     for f in sorted(os.listdir(OUT)):
