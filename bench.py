@@ -189,13 +189,7 @@ def run_ours(args):
     def step_device(i, timed=False):
         k = i % N_POOL
         y, c, q = dev_pool[k]
-        if timed:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        x = tf.run(y, c, q, None, plans_dev=dev_plans[k], out=out_buf)
-        if timed:
-            e1.record()
-            k0_ms.append((e0, e1))
+        x = tf.run(y, c, q, None, plans_dev=dev_plans[k], out=out_buf, timing=k0_ms if timed else None)
         if stage is not None:
             return stage.step(x, labels_pool[k])
         return x
@@ -314,7 +308,8 @@ def run_ours(args):
                             "K0, train step; decode of the next batches overlaps the GPU"}
 
     # K0 kernel(s) alone: average over the timed region (events on the launching stream)
-    k0_avg_ms = float(np.mean([a.elapsed_time(b) for a, b in k0_ms[-args.steps:]]))
+    k0_avg_ms = float(np.mean([a.elapsed_time(c) for a, _, c in k0_ms[-args.steps:]]))         # statistics pre-pass + fused kernel
+    k0_fused_ms = float(np.mean([b.elapsed_time(c) for _, b, c in k0_ms[-args.steps:]]))      # the fused kernel's own launches
     out_bytes = 2 if out_dtype == torch.bfloat16 else 4
     alg = float(np.mean([algorithmic_bytes(p, out_bytes) for p in plan_pool]))
     pk, pk_src = peaks()
@@ -408,12 +403,17 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
         "gpu_launches": launches * args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k0_dcstats + k0_fused (train mix)", "achieved": alg / (k0_avg_ms * 1e-3) / 1e9,
+        # the dominant kernel of the data path = k0_vit2_kernel, timed by events around its own launches inside the timed steps
+        # (training mix of crop sizes and ops); `with_prepass` adds the DC-statistics launch in front of it
+        "roofline": {"bound": "hbm", "kernel": "k0_vit2_kernel (train mix), launches inside the timed steps",
+                     "achieved": alg / (k0_fused_ms * 1e-3) / 1e9,
                      "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s",
-                     "frac": alg / (k0_avg_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                     "frac": alg / (k0_fused_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                      # dram__bytes_read.sum + dram__bytes_write.sum of one train-mix launch (ncu --set full, batch 256)
                      "traffic": k0_ncu_traffic("train")[0] if B == 256 else None, "traffic_source": k0_ncu_traffic("train")[1],
-                     "algorithmic_bytes_per_launch": alg, "kernel_ms": k0_avg_ms},
+                     "algorithmic_bytes_per_launch": alg, "kernel_ms": k0_fused_ms,
+                     "with_prepass": {"kernel": "k0_dcstats + k0_vit2_kernel", "kernel_ms": k0_avg_ms,
+                                      "achieved": alg / (k0_avg_ms * 1e-3) / 1e9, "frac": alg / (k0_avg_ms * 1e-3) / 1e9 / pk["hbm_gbs"]}},
         "roofline_eval_geometry": {"bound": "hbm", "achieved": alg_eval / (ms_eval * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                                    "unit": "GB/s", "frac": alg_eval / (ms_eval * 1e-3) / 1e9 / pk["hbm_gbs"],
                                    "traffic": k0_ncu_traffic("eval")[0] if B == 256 else None,

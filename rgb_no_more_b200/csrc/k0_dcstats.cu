@@ -17,7 +17,10 @@
 
 namespace k0 {
 
-constexpr int STATS_THREADS = 256;
+// 1024 threads: the DC gather (1176 / 1536 post-resize blocks per image, up to 8 dependent-free 16-byte loads each) is one round of
+// loads per thread plus a short second one -- with 256 threads it was five serial rounds of DRAM latency.
+constexpr int STATS_THREADS = 1024;
+constexpr int EQ_BINS_PER_THREAD = 2048 / STATS_THREADS;
 
 // DC of the resized block at post-resize position (r, c) of plane `comp`, computed with the
 // exact operation sequence of the fused kernel's row pass + column pass.
@@ -94,13 +97,13 @@ k0_dcstats_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbc
     __shared__ int iscratch[STATS_THREADS / 32 + 2];
     if (threadIdx.x < int(sizeof(rgbnm_plan) / 4))
         reinterpret_cast<int*>(&pl)[threadIdx.x] = __ldg(reinterpret_cast<const int*>(plans + img) + threadIdx.x);
-    __syncthreads();
-    if (!pl.needs_stats) return;
-    for (int k = threadIdx.x; k < 192; k += STATS_THREADS) {
+    else if (threadIdx.x >= 32 && threadIdx.x < 32 + 192) {            // the tables travel together with the plan
+        const int k = threadIdx.x - 32;
         qf[k] = float(__ldg(quant + size_t(img) * 192 + k));
         cqf[k] = -DEQ_BIAS * qf[k];
     }
     __syncthreads();
+    if (!pl.needs_stats) return;
 
     const int hc = hb >> 1, wc = wb >> 1;
     const int mode = mode_of(pl.crop_size, GRID_Y);
@@ -149,11 +152,11 @@ k0_dcstats_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbc
             __syncthreads();
             for (int e = threadIdx.x; e < NY; e += STATS_THREADS) atomicAdd(&eq[int(src[e]) + 1024], 1);
             __syncthreads();
-            int loc[8], sum = 0, first = 4096;
+            int loc[EQ_BINS_PER_THREAD], sum = 0, first = 4096;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                loc[j] = eq[threadIdx.x * 8 + j];
-                if (loc[j] != 0 && first == 4096) first = threadIdx.x * 8 + j;
+            for (int j = 0; j < EQ_BINS_PER_THREAD; ++j) {
+                loc[j] = eq[threadIdx.x * EQ_BINS_PER_THREAD + j];
+                if (loc[j] != 0 && first == 4096) first = threadIdx.x * EQ_BINS_PER_THREAD + j;
                 sum += loc[j];
             }
             // block-wide exclusive scan of `sum` and minimum of `first`
@@ -176,8 +179,8 @@ k0_dcstats_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbc
             __syncthreads();
             int running = base + incl - sum;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int b = threadIdx.x * 8 + j;
+            for (int j = 0; j < EQ_BINS_PER_THREAD; ++j) {
+                const int b = threadIdx.x * EQ_BINS_PER_THREAD + j;
                 running += loc[j];
                 int val = b - 1024;                        // one distinct DC value (0 / 0 in the reference): unchanged
                 if (mn > 0) val = int(rint_magic(__fdiv_rn(float(running - h0), float(mn)) * 2039.0f)) - 1024;

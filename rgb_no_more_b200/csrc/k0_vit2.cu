@@ -20,10 +20,12 @@
 //     16 consecutive columns and 16-byte row reads of 8 consecutive rows are all bank-conflict free with plain linear addressing
 //     (compile-time offsets, no swizzle arithmetic).  Pairs travel as 64-bit registers (mov.b64 views, ld/st.shared.b64 on
 //     32-bit shared-window addresses): no pack / unpack moves, no generic-address conversion.
-//   * Quads are dealt to warps in equal contiguous ranges (49 quads per image; 20 warps per SM resident), so per-image state
-//     (plan, fp32 tables) is loaded about once per warp and all warps finish together.
+//   * Quads are dealt to warps DYNAMICALLY (a device ticket counter; 49 quads per image, 20 warps per SM resident): the work of a
+//     quad depends on its image's plan (x2-down reads 4x the coefficients of x2-up, RandAugment ops add column-pass work) and a
+//     batch of 256 images holds only ~4 quads per warp, so fixed ranges left warps idle at the end of the training mix.
 //
 // HBM-bound by design; CUDA cores only (north_star reserves the tensor cores for the ViT contractions).
+#include <atomic>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -37,11 +39,10 @@ namespace k0v2 {
 using namespace k0;
 
 typedef unsigned long long p2;            // packed pair: token 0 in the low word, token 1 in the high word
-// 16 resident warps / SM (4 CTAs x 4 warps, <= 128 registers: 106 used, no spills).  Measured on B200 (profiles/r02_k0_experiments.md):
-// 12, 16 and 20 warps / SM all land within 3 % of each other in the eval geometry; 20 warps need a 96-register cap that spills
-// the quad loop's control variables.
+// 20 resident warps / SM (4 CTAs x 5 warps, <= 96 registers: 92 used, no spills).  Measured on B200 (profiles/r02_k0_experiments.md):
+// 16, 18 and 20 warps / SM land within 4 % of each other; 20 is the best in both the eval geometry and the training mix.
 #ifndef K0V2_WARPS
-#define K0V2_WARPS 4
+#define K0V2_WARPS 5
 #endif
 #ifndef K0V2_CTAS
 #define K0V2_CTAS 4
@@ -59,8 +60,8 @@ struct __align__(16) WarpSmem {
     unsigned char T[2 * TILE_B];      // tile of pair p at T + p * TILE_B: rows of 16 p2 (+ pad), row-major
     unsigned char qt[24 * QROW_B];    // per (component, coefficient row): q[8] and cq[8] = -(2^23 + 2^15) * q (dequantisation bias)
     rgbnm_plan plan;
-    int info[2][24];                  // per block of the quad: source block index, child flags, zeroing op (pack_info); two slots:
-                                      // the next quad's blocks are traced (and its first loads issued) before this quad ends
+    int info[24];                     // per block of the quad: source block index, child flags, zeroing op (pack_info)
+    int pad_[8];
 };
 static_assert(sizeof(WarpSmem) % 16 == 0, "warp slices must stay 16-byte aligned");
 static_assert(CTAS_PER_SM * (WARPS * sizeof(WarpSmem) + 1024) <= 228 * 1024, "the resident CTAs of an SM must fit");
@@ -386,10 +387,9 @@ __device__ __forceinline__ unsigned bf2(float a, float b) {
     return *reinterpret_cast<unsigned*>(&t);
 }
 
-// ---- block bookkeeping of one quad: lanes 0..23 trace one block each into info slot `slot`
+// ---- block bookkeeping of one quad: lanes 0..23 trace one block each into ws.info
 //      (block id = p*12 + [luma: tok*4 + bi*2 + bj | chroma: 8 + tok*2 + comp-1]) ------------------------------------------------
-__device__ __forceinline__ void trace_quad(WarpSmem& ws, int lane, int tr, int tp, int mode, int wb, int wc, int slot,
-                                           const unsigned char* __restrict__ y_img, const unsigned char* __restrict__ c_img, size_t hcwc128) {
+__device__ __forceinline__ void trace_quad(WarpSmem& ws, int lane, int tr, int tp, int mode, int wb, int wc) {
     const rgbnm_plan& pl = ws.plan;
     if (lane < 24) {
         const int p = lane >= 12, bb = lane - 12 * p;
@@ -411,20 +411,12 @@ __device__ __forceinline__ void trace_quad(WarpSmem& ws, int lane, int tr, int t
         else if (mode == MODE_IDENT) { sr = ci + t.r; sc = cj + t.c; }
         else { sr = ci + (t.r >> 1); sc = cj + (t.c >> 1); chr = t.r & 1; chc = t.c & 1; }
         const int W = comp == 0 ? wb : wc;
-        ws.info[slot][lane] = pack_info(sr * W + sc, chr, chc, t.zero);
-        // pull the block's source rows into L2 now (they are loaded a quad later): one line per source block
-        const unsigned char* src = (comp == 0 ? y_img : c_img + size_t(comp - 1) * hcwc128) + size_t(sr * W + sc) * 128;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
-        if (mode == MODE_DOWN2) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 128));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + size_t(W) * 128));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + size_t(W) * 128 + 128));
-        }
+        ws.info[lane] = pack_info(sr * W + sc, chr, chc, t.zero);
     }
 }
 
 // first luma loads of a quad (x2-down: round (pair 0, block row 0); else the single round of both pairs: A.l0 / A.l1 = pair 0
-// tokens 0 / 1, A.r0 / A.r1 = pair 1).  16 registers: what can be carried through the chroma column pass without spilling.
+// tokens 0 / 1, A.r0 / A.r1 = pair 1).
 __device__ __forceinline__ void luma_first_loads(uint32_t info, int lane, const unsigned char* __restrict__ y_img, int wb, int mode,
                                                  RowLoads& A) {
     if (mode == MODE_DOWN2) {
@@ -439,23 +431,20 @@ __device__ __forceinline__ void luma_first_loads(uint32_t info, int lane, const 
 // ---- one quad -------------------------------------------------------------------------------------------------------------------
 // MODE_T >= 0 / NOCLAMP_T: compile-time resize case / "dequantisation clamp proven idle" (the x2-down, no-clamp instance is the
 // hot one in both the eval geometry and the training mix); MODE_T = -1: everything decided at run time.
-// On entry info slot `slot` is traced and A holds the quad's first luma loads; if `has_next`, the next quad (ntr, ntp) of the
-// same image is traced into the other slot and its first loads are issued into A before the chroma column pass, so that they
-// are in flight during the tail of this quad.
+// On entry ws.info is traced and A holds the quad's first luma loads.  `sched` / `grabbed`: ticket of the dynamic quad queue, drawn
+// before the read-out phase (see the kernel).
 // NOSUB: RGBNM_K0_LAYOUT_VIT16_NOSUB (`--no_subblock`, plainvit.py:173-216 with use_subblock = False): no A16 products; the luma part of
 // the token is the 16 x 16 tile of the four un-converted blocks, row-major ('b c (h pdh) (w pdw) p1 p2 -> b c h w (pdh p1) (pdw p2)').
 template <int OUT_MODE, int MODE_T, bool NOCLAMP_T, bool NOSUB>
 __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int lane, int img, int tr, int tp, int mode_rt,
                                              const unsigned char* __restrict__ y_img, const unsigned char* __restrict__ c_img,
                                              const rgbnm_k0_tables& tb, const float* __restrict__ stats, void* __restrict__ out_, int wb,
-                                             int hc, int wc, RowLoads& A, int slot, bool has_next, int ntr, int ntp) {
+                                             int hc, int wc, RowLoads& A, unsigned* __restrict__ sched, unsigned& grabbed) {
     const rgbnm_plan& pl = ws.plan;
     const int mode = MODE_T >= 0 ? MODE_T : mode_rt;
     const bool clamp = NOCLAMP_T ? false : (pl.clamp_in != 0);
-    const uint32_t info = K.info + slot * 96;
+    const uint32_t info = K.info;
     const int b3 = (lane >> 3) & 1, b4 = lane >> 4;
-    // the next quad is traced first: its source lines travel to L2 while this quad computes (its slot is read after the chroma row pass)
-    if (has_next) trace_quad(ws, lane, ntr, ntp, mode, wb, wc, slot ^ 1, y_img, c_img, size_t(hc) * wc * 128);
     // ---- R, luma ----------------------------------------------------------------------------------------------------------------
     if (mode == MODE_DOWN2) {
         // rounds (pair, block row) = (0,0) (0,1) (1,0) (1,1); the loads of round r+2 are issued as round r is consumed
@@ -484,6 +473,9 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
     for (int k = 0; k < 3; ++k) {
         if (k == 2) {
             __syncwarp();                                                  // S complete (transposed blocks are written across columns)
+            // dynamic schedule: ask for the next quad now, the answer is needed when this one is stored (atomic latency hidden,
+            // and a quad is held by a busy warp for the last third of an iteration only)
+            if (lane == 0) grabbed = atomicAdd(sched, 1u);
             if (OUT_MODE != RGBNM_K0_OUT_INT16_PLANES) {
                 // ---- P2b: column half of the sub-block conversion, in place: S -> A16 . S ------------------------------------
                 if (!NOSUB) {
@@ -554,8 +546,6 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
                 else r_small_compute<MODE_IDENT>(a0, a1, info, b4 * 12 + 8 + b3, 2, qr, K.rst_c, clamp);
             }
             __syncwarp();
-            // the next quad's first luma loads: in flight during the chroma column pass and read-out of this one
-            if (has_next) luma_first_loads(K.info + (slot ^ 1) * 96, lane, y_img, wb, mode, A);
         }
         // ---- the column pass proper ----------------------------------------------------------------------------------------
         const int b0 = p * 12 + (k < 2 ? k * 2 + half : 8 + half);
@@ -642,7 +632,7 @@ template <int OUT_MODE, bool NOSUB>
 __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM)
 k0_vit2_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, const int16_t* __restrict__ quant,
                const rgbnm_plan* __restrict__ plans, rgbnm_k0_tables tb, const float* __restrict__ stats_all, void* __restrict__ out_,
-               int n_images, int hb, int wb) {
+               int n_images, int hb, int wb, unsigned* __restrict__ sched) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpSmem& ws = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
@@ -660,17 +650,17 @@ k0_vit2_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, 
     }
     const long long nq = (long long)n_images * QUADS_PER_IMAGE;
     const long long gw = (long long)blockIdx.x * WARPS + warp, tw = (long long)gridDim.x * WARPS;
-    const int q_begin = int(gw * nq / tw), q_end = int((gw + 1) * nq / tw);
     const int hc = hb >> 1, wc = wb >> 1;
-#ifdef K0V2_STAGGER_NS
-    __nanosleep(unsigned(gw & 3) * K0V2_STAGGER_NS);        // experiment: de-phase the warps of a scheduler
-#endif
-    int cur = -1, mode = MODE_BAD, slot = 0;
-    bool pre = false;                   // info slot `slot` traced and A loaded by the previous quad
+    int cur = -1, mode = MODE_BAD;
     RowLoads A;
     A.l0 = A.r0 = A.l1 = A.r1 = make_int4(0, 0, 0, 0);
-    for (int q = q_begin; q < q_end; ++q) {
-        const int img = q / QUADS_PER_IMAGE, rem = q - img * QUADS_PER_IMAGE;
+    // Quads are dealt DYNAMICALLY: a warp's first quad is its global index, every further one comes from a device counter
+    // (sched[0]; quad = warps + ticket).  The work of a quad depends on the image's plan (x2-down reads 4x the coefficients of x2-up,
+    // RandAugment ops add column-pass work) and a launch holds only ~5 quads per warp, so fixed ranges left warps idle for the
+    // last quarter of the kernel.  The last warp to leave (sched[1] counts them) zeroes both words for the next launch.
+    long long q = gw;
+    while (q < nq) {
+        const int img = int(q / QUADS_PER_IMAGE), rem = int(q - (long long)img * QUADS_PER_IMAGE);
         if (img != cur) {
             __syncwarp();
             const int* psrc = reinterpret_cast<const int*>(plans + img);
@@ -684,32 +674,58 @@ k0_vit2_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, 
             __syncwarp();
             cur = img;
             mode = mode_of(ws.plan.crop_size, GRID_Y);
-            pre = false;
         }
-        if (mode == MODE_BAD) continue;
-        const int tr = rem / 7, tp = rem - tr * 7;
-        const unsigned char* y_img = reinterpret_cast<const unsigned char*>(y + size_t(img) * hb * wb * 64);
-        const unsigned char* c_img = reinterpret_cast<const unsigned char*>(cbcr + size_t(img) * 2 * hc * wc * 64);
-        if (!pre) {
-            trace_quad(ws, lane, tr, tp, mode, wb, wc, slot, y_img, c_img, size_t(hc) * wc * 128);
+        unsigned grabbed = 0;
+        if (mode != MODE_BAD) {
+            const int tr = rem / 7, tp = rem - tr * 7;
+            const unsigned char* y_img = reinterpret_cast<const unsigned char*>(y + size_t(img) * hb * wb * 64);
+            const unsigned char* c_img = reinterpret_cast<const unsigned char*>(cbcr + size_t(img) * 2 * hc * wc * 64);
+            trace_quad(ws, lane, tr, tp, mode, wb, wc);
             __syncwarp();
-            luma_first_loads(K.info + slot * 96, lane, y_img, wb, mode, A);
+            luma_first_loads(K.info, lane, y_img, wb, mode, A);
+            const float* stats = stats_all + size_t(img) * RGBNM_MAX_OPS * 2;
+            if (OUT_MODE != RGBNM_K0_OUT_INT16_PLANES && mode == MODE_DOWN2 && ws.plan.clamp_in == 0)
+                process_quad<OUT_MODE, MODE_DOWN2, true, NOSUB>(ws, K, lane, img, tr, tp, mode, y_img, c_img, tb, stats, out_, wb, hc, wc, A, sched, grabbed);
+            else
+                process_quad<OUT_MODE, -1, false, NOSUB>(ws, K, lane, img, tr, tp, mode, y_img, c_img, tb, stats, out_, wb, hc, wc, A, sched, grabbed);
+        } else if (lane == 0) {
+            grabbed = atomicAdd(sched, 1u);
         }
-        const bool has_next = (q + 1 < q_end) && (rem + 1 < QUADS_PER_IMAGE);
-        const int nrem = rem + 1, ntr = nrem / 7, ntp = nrem - ntr * 7;
-        const float* stats = stats_all + size_t(img) * RGBNM_MAX_OPS * 2;
-        if (OUT_MODE != RGBNM_K0_OUT_INT16_PLANES && mode == MODE_DOWN2 && ws.plan.clamp_in == 0)
-            process_quad<OUT_MODE, MODE_DOWN2, true, NOSUB>(ws, K, lane, img, tr, tp, mode, y_img, c_img, tb, stats, out_, wb, hc, wc, A, slot,
-                                                     has_next, ntr, ntp);
-        else
-            process_quad<OUT_MODE, -1, false, NOSUB>(ws, K, lane, img, tr, tp, mode, y_img, c_img, tb, stats, out_, wb, hc, wc, A, slot,
-                                              has_next, ntr, ntp);
-        pre = has_next;
-        if (has_next) slot ^= 1;
+        q = tw + (long long)__shfl_sync(0xffffffffu, grabbed, 0);
+    }
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(sched + 1, 1u) == unsigned(tw - 1)) {
+            sched[0] = 0;
+            sched[1] = 0;
+            __threadfence();
+        }
     }
 }
 
 }  // namespace k0v2
+
+// Scheduler words of the dynamic quad queue: {next ticket, warps that left}.  A launch leaves its pair zeroed, launches of one stream
+// serialise, and concurrent launches on different streams get different pairs (round robin over SCHED_SLOTS).
+constexpr int SCHED_SLOTS = 256;
+__device__ unsigned g_k0v2_sched[SCHED_SLOTS][2];
+
+static int next_sched_slot(unsigned** out) {
+    static std::atomic<unsigned> turn{0};
+    static std::atomic<unsigned*> base[64];
+    int dev = 0;
+    RGBNM_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return RGBNM_ERR_ARG;
+    unsigned* b = base[dev].load(std::memory_order_acquire);
+    if (b == nullptr) {
+        void* p = nullptr;
+        RGBNM_CUDA_CHECK(cudaGetSymbolAddress(&p, g_k0v2_sched));
+        b = static_cast<unsigned*>(p);
+        base[dev].store(b, std::memory_order_release);
+    }
+    *out = b + 2 * (turn.fetch_add(1, std::memory_order_relaxed) % SCHED_SLOTS);
+    return RGBNM_OK;
+}
 
 template <int OUT_MODE, bool NOSUB>
 static int launch_vit2(const int16_t* y, const int16_t* cbcr, const int16_t* quant, const rgbnm_plan* plans, const rgbnm_k0_tables* tables,
@@ -729,7 +745,9 @@ static int launch_vit2(const int16_t* y, const int16_t* cbcr, const int16_t* qua
     const long long nq = (long long)n * QUADS_PER_IMAGE;
     long long ctas = (nq + WARPS - 1) / WARPS;
     if (ctas > (long long)sms * CTAS_PER_SM) ctas = (long long)sms * CTAS_PER_SM;
-    k0_vit2_kernel<OUT_MODE, NOSUB><<<int(ctas), WARPS * 32, smem, st>>>(y, cbcr, quant, plans, *tables, stats, out, n, hb, wb);
+    unsigned* sched = nullptr;
+    if (int rc = next_sched_slot(&sched)) return rc;
+    k0_vit2_kernel<OUT_MODE, NOSUB><<<int(ctas), WARPS * 32, smem, st>>>(y, cbcr, quant, plans, *tables, stats, out, n, hb, wb, sched);
     RGBNM_CUDA_CHECK(cudaGetLastError());
     return RGBNM_OK;
 }

@@ -97,11 +97,12 @@ class FusedDCT:
     # -- launch ---------------------------------------------------------------------------
     def run(self, y_q: torch.Tensor, c_q: torch.Tensor, quant: torch.Tensor, plans, clamp_in=None,
             out_mode: Optional[int] = None, out: Optional[torch.Tensor] = None,
-            plans_dev: Optional[torch.Tensor] = None, needs_stats: Optional[bool] = None) -> torch.Tensor:
+            plans_dev: Optional[torch.Tensor] = None, needs_stats: Optional[bool] = None, timing: Optional[list] = None) -> torch.Tensor:
         """y_q int16 [B,hb,wb,64] (or [B,1,hb,wb,8,8]), c_q int16 [B,2,hb/2,wb/2,64], quant int16 [B,3,64],
         all on `device`.  `plans`: list[Plan] or packed numpy array (or pass `plans_dev`).
         `needs_stats=False` (known on the host: no plan of the batch holds a statistics op, e.g. the eval transform) skips the
-        DC-statistics pre-pass launch; None = decide from `plans` when they are given as a list, else launch it."""
+        DC-statistics pre-pass launch; None = decide from `plans` when they are given as a list, else launch it.
+        `timing`: a list that receives (before, between, after) CUDA events recorded around the two launches (bench.py)."""
         B = y_q.shape[0]
         if y_q.dim() == 6:
             hb, wb = y_q.shape[2], y_q.shape[3]
@@ -143,12 +144,20 @@ class FusedDCT:
         self._tables.equalize_lut = self._eq_lut.data_ptr()
         st = _lib.stream_ptr()
         L = self._lib
+        if timing is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
         if needs_stats:
             _lib.check(L.rgbnm_k0_dcstats_ex(y_q.data_ptr(), c_q.data_ptr(), quant.data_ptr(), plans_dev.data_ptr(),
                                              C.byref(self._tables), stats.data_ptr(), B, hb, wb, self.layout, st), "rgbnm_k0_dcstats")
+        if timing is not None:
+            ev[1].record()
         _lib.check(L.rgbnm_k0_fused_ex(y_q.data_ptr(), c_q.data_ptr(), quant.data_ptr(), plans_dev.data_ptr(),
                                        C.byref(self._tables), stats.data_ptr(), out.data_ptr(), out_mode, self.layout, B, hb, wb, st),
                    "rgbnm_k0_fused")
+        if timing is not None:
+            ev[2].record()
+            timing.append(tuple(ev))
         self.last_stats = stats
         return out
 

@@ -12,5 +12,5 @@ name=None
 for ln in sys.stdin:
     if ln.startswith('=='): name=ln.strip()
     elif ln.startswith('{'):
-        d=json.loads(ln); print(name, 'eval', d['eval']['ms_per_batch_incl_dcstats'], d['eval']['frac'], 'train', d['train']['ms_per_batch_incl_dcstats'], d['train']['frac'])
+        d=json.loads(ln); print(name, *[(k, d[k]['ms_per_batch_incl_dcstats'], d[k]['frac']) for k in ('eval','train','train_fused_only') if k in d])
 "

@@ -20,20 +20,21 @@ for i in range(NB):
     y, c, q = synth.synth_coefficients(B, 64, 64, seed=50 + i, dense=False)
     batches.append((torch.from_numpy(y).to(dev), torch.from_numpy(c).to(dev), torch.from_numpy(q).to(dev)))
 res = {}
-for kind in ("eval", "train"):
-    tf = TF.FusedDCT(dev, "train" if kind == "train" else "test", P.AUGLIST_VITS, 2, 9, torch.bfloat16)
+for kind in ("eval", "train", "train_fused_only"):       # the last: the same plans without the statistics pre-pass launch (timing only)
+    tf = TF.FusedDCT(dev, "train" if kind != "eval" else "test", P.AUGLIST_VITS, 2, 9, torch.bfloat16)
+    ns = False if kind != "train" else None
     torch.manual_seed(5)
     plans = tf.sample_plans(B)
     pdev = torch.from_numpy(P.pack_plans(plans, [False] * B).view(np.uint8).reshape(B, -1)).to(dev)
     out = torch.empty((B, 196, 384), dtype=torch.bfloat16, device=dev)
     byt = sum(p.crop_size ** 2 * 128 + 2 * (p.crop_size // 2) ** 2 * 128 + 496 + 196 * 384 * 2 for p in plans)
     for i in range(3):
-        tf.run(*batches[i % NB], None, plans_dev=pdev, out=out)
+        tf.run(*batches[i % NB], None, plans_dev=pdev, out=out, needs_stats=ns)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         for i in range(NB):
-            tf.run(*batches[i], None, plans_dev=pdev, out=out)
+            tf.run(*batches[i], None, plans_dev=pdev, out=out, needs_stats=ns)
     for _ in range(3):
         g.replay()
     torch.cuda.synchronize()
