@@ -448,26 +448,18 @@ def run_ours(args):
 
 
 def swin_train_step(args, dev, dev_pool, timed_loop, rank, world, local):
-    """BASELINE config 5 (SwinV2-T DCT, window 8, bf16, DDP): batch 64 per GPU (reference: 512 over 8 GPUs, configs.py:137),
-    drop_path 0.2, fresh plans per step from the batched sampler, the reference's own loop shape: DistributedDataParallel around
-    `swin.SwinTransformerV2` (gradients through one autograd.Function), torch AdamW.  Whole-job images/s, max over ranks."""
-    import torch.nn.functional as F
-    from rgb_no_more_b200 import plan as P, swin as S, transforms as TF
+    """BASELINE config 5 (SwinV2-T DCT, window 8, bf16, data parallel): batch 64 per GPU (reference: 512 over 8 GPUs, configs.py:138),
+    drop_path 0.2, mixup 0.2, fresh plans per step from the batched sampler; train_step.TrainStage(arch='swinv2t'): K0 in the Swin
+    layout -> mixup -> forward / backward (one CUDA graph) -> flat NCCL all-reduce -> clip + AdamW + decay kernel + working-copy
+    refresh (second graph).  Whole-job images/s, max over ranks."""
+    from rgb_no_more_b200 import plan as P, train_step as TS, transforms as TF
     B = 64
-    with torch.random.fork_rng(devices=[dev]):
-        torch.manual_seed(11997733)
-        model = S.SwinTransformerV2(img_size=256, patch_size=4, embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24],
-                                    window_size=8, mlp_ratio=4, drop_path_rate=0.2, pretrained_window_sizes=[0, 0, 0, 0],
-                                    device="cpu", pixel_space="dct")
-        with torch.no_grad():       # the reference zero-initialises the block post-norms (identity blocks): randomise them
-            for p_ in model.parameters():
-                if p_.ndim == 1:
-                    p_.add_(0.1 * torch.randn_like(p_))
-    model.train().to(dev)
-    net = model
-    if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], output_device=local)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    stage = TS.TrainStage(dev, arch="swinv2t", batch=B, world=world, rank=rank, use_graph=not args.no_graph)
+    with torch.no_grad():           # the reference zero-initialises the block post-norms (identity blocks): randomise them
+        with torch.random.fork_rng(devices=[dev]):
+            torch.manual_seed(11997733)
+            stage.eng.flat.add_(0.1 * torch.randn_like(stage.eng.flat) * (stage.eng.flat == 0))
+    stage.eng.refresh_weights()
     tf = TF.FusedDCT(dev, "train", P.AUGLIST_VITS, 2, 9, torch.bfloat16, out_size=32)
     labels = torch.randint(0, 1000, (B,), device=dev)
     gen = torch.Generator().manual_seed(7 + rank)
@@ -476,19 +468,16 @@ def swin_train_step(args, dev, dev_pool, timed_loop, rank, world, local):
     def step(i):
         y, c, q = (t[:B] for t in dev_pool[i % len(dev_pool)])
         plans = tf.sample_plans_packed(B, 64, 64, clamp_in=[False] * B, generator=gen)
-        x = tf.run(y, c, q, plans, needs_stats=bool(plans["needs_stats"].any()))
-        opt.zero_grad(set_to_none=True)
-        loss = F.cross_entropy(net(x), labels)
-        loss.backward()
-        opt.step()
-        losses.append(loss.detach())
-    n = max(args.steps // 4, 5)
-    ms = timed_loop(step, n, 3) / n
+        x = tf.run(y, c, q, plans, needs_stats=bool(plans["needs_stats"].any()), out=stage.x_static)
+        losses.append(stage.step(x, labels).clone())
+    n = max(args.steps, 10)
+    ms = timed_loop(step, n, 4) / n
     return {"value": B * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch_per_gpu": B, "n_gpus": world,
             "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
-            "what": "SwinV2-T DCT (window 8) train step: K0 in the Swin layout (RandAugment mix, fresh plans per step) -> forward with "
-                    "saved activations -> CE -> backward -> " + ("DDP all-reduce (NCCL) -> " if world > 1 else "") + "torch AdamW; eager "
-                    "launches; tcgen05 GEMMs, mma.sync window attention forward, CUDA-core attention / LayerNorm backward"}
+            "what": "SwinV2-T DCT (window 8) train step: K0 in the Swin layout (RandAugment mix, fresh plans per step) -> mixup -> forward with "
+                    "saved activations -> CE -> backward (CUDA graph) -> " + ("flat all-reduce (NCCL) -> " if world > 1 else "") +
+                    "clip + AdamW + decoupled decay kernel + bf16 working-copy refresh (CUDA graph); tcgen05 GEMMs, mma.sync window "
+                    "attention forward and backward, CUDA-core LayerNorm backward"}
 
 
 def vitti_configs(args, dev, dev_pool, dev_plans, tf, tf_eval, labels_pool, timed_loop):

@@ -7,6 +7,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "../../include/rgbnm_b200.h"
 #include "common.cuh"
 
@@ -286,6 +288,317 @@ window_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat1
     if ((t & 31) == 0) atomicAdd(dscale + head, dscale_acc);
 }
 
+// ------------------------------------------------------------------------------------------
+// Window attention backward on warp-level tensor-core MMAs (mma.sync m16n8k16, bf16 x bf16 -> fp32), the backward twin of
+// swin_kernels.cu::window_attn_mma_kernel.  CTA = 4 warps = one (window, head) per iteration, grid-strided over the windows
+// of one head (blockIdx.y): the head's bias tile is staged once and d(bias tile) accumulates in REGISTERS (a thread owns
+// the same 32 (row, column) positions of every window), flushed with one atomic per element at the end.
+//   stage      q, k, v, dO (64 x 32 bf16 each) -> shared memory, 1 / |q_i|, 1 / |k_j|
+//   row phase  warp w = query rows 16w .. 16w+15:  S = Q K^T and dP = dO V^T (A fragments by ldmatrix, B = K / V rows),
+//              cos = S / (|q||k|), logits = scale * cos + bias (+ -100 across shift regions), P = softmax, delta = sum_j P dP,
+//              dS = P (dP - delta) -> d(bias), d(scale) += dS cos;  dqn = (scale dS / |k_j|) K   (A from the accumulator
+//              registers, B = K through ldmatrix.trans);  dq = (dqn - qn (qn . dqn)) / |q|
+//              P and E = scale dS / |q_i| (bf16) -> shared memory
+//   col phase  warp w = keys 16w .. 16w+15:  dV = P^T dO, dkn = E^T Q (A = ldmatrix.trans of P / E, B = ldmatrix.trans of
+//              dO / Q);  dk = (dkn - kn (kn . dkn)) / |k|
+// The cosine normalisation is applied to fp32 accumulators of the RAW bf16 operands (no extra rounding), as in the forward.
+// ------------------------------------------------------------------------------------------
+constexpr int QLD = 40;       // bf16 per staged q / k / v / dO row (32 + 8 pad: 80 B, conflict-free ldmatrix)
+constexpr int PLD = 72;       // bf16 per row of P / E (64 + 8 pad)
+constexpr int BLD = 72;       // floats per staged bias row
+constexpr float LOG2E_B = 1.4426950408889634f;
+
+struct AttnBwdMmaSmem {
+    __nv_bfloat16 Q[WT * QLD], K[WT * QLD], V[WT * QLD], dO[WT * QLD];
+    __nv_bfloat16 P[WT * PLD], E[WT * PLD];
+    float Bs[WT * BLD];
+    float rq[WT], rk[WT];
+};
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4(unsigned (&r)[4], const void* p) {
+    const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(p));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(unsigned (&r)[4], const void* p) {
+    const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(p));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ float sumsq_bf2(unsigned w) {
+    const float2 f = bf2_to_f2(w);
+    return f.x * f.x + f.y * f.y;
+}
+__device__ __forceinline__ float sumsq_u4(const uint4& a) { return sumsq_bf2(a.x) + sumsq_bf2(a.y) + sumsq_bf2(a.z) + sumsq_bf2(a.w); }
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+
+#ifndef RGBNM_WATTN_BWD_MINBLOCKS
+#define RGBNM_WATTN_BWD_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(128, RGBNM_WATTN_BWD_MINBLOCKS)
+window_attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout, const float* __restrict__ bias,
+                           const float* __restrict__ scale, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias,
+                           float* __restrict__ dscale, int H, int W, int C, int shift, int n_windows) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    AttnBwdMmaSmem& sm = *reinterpret_cast<AttnBwdMmaSmem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int head = blockIdx.y;
+    for (int e = tid; e < WT * (WT / 4); e += 128) {
+        const int row = e >> 4, c4 = e & 15;
+        float4 b = __ldg(reinterpret_cast<const float4*>(bias + (size_t(head) * WT + row) * WT) + c4);
+        b.x *= LOG2E_B; b.y *= LOG2E_B; b.z *= LOG2E_B; b.w *= LOG2E_B;               // logits are kept in log2 units
+        *reinterpret_cast<float4*>(sm.Bs + row * BLD + c4 * 4) = b;
+    }
+    const float sc = __ldg(scale + head);
+    const int wpr = W / WS, wpi = (H / WS) * wpr;
+    const int R0 = warp * 16 + g, R1 = R0 + 8;
+    float dB[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) dB[nt][0] = dB[nt][1] = dB[nt][2] = dB[nt][3] = 0.0f;
+    float dscale_acc = 0.0f;
+    const int m4 = lane >> 3, l8 = lane & 7;
+
+    for (int win = blockIdx.x; win < n_windows; win += gridDim.x) {
+        __syncthreads();                                   // the previous window's shared-memory reads are done
+        // ---- stage: thread = (row, 16-dim half) ----
+        const int sr = tid >> 1, half = tid & 1;
+        const int stok = window_token(win, sr, H, W, wpr, wpi, shift);
+        {
+            const __nv_bfloat16* row = qkv + size_t(stok) * (3 * size_t(C)) + head * HD + half * 16;
+            const __nv_bfloat16* drow = dout + size_t(stok) * C + head * HD + half * 16;
+            const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(row)), q1 = __ldg(reinterpret_cast<const uint4*>(row) + 1);
+            const uint4 k0 = __ldg(reinterpret_cast<const uint4*>(row + C)), k1 = __ldg(reinterpret_cast<const uint4*>(row + C) + 1);
+            const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(row + 2 * C)), v1 = __ldg(reinterpret_cast<const uint4*>(row + 2 * C) + 1);
+            const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(drow)), d1 = __ldg(reinterpret_cast<const uint4*>(drow) + 1);
+            const int o = sr * QLD + half * 16;
+            reinterpret_cast<uint4*>(sm.Q + o)[0] = q0; reinterpret_cast<uint4*>(sm.Q + o)[1] = q1;
+            reinterpret_cast<uint4*>(sm.K + o)[0] = k0; reinterpret_cast<uint4*>(sm.K + o)[1] = k1;
+            reinterpret_cast<uint4*>(sm.V + o)[0] = v0; reinterpret_cast<uint4*>(sm.V + o)[1] = v1;
+            reinterpret_cast<uint4*>(sm.dO + o)[0] = d0; reinterpret_cast<uint4*>(sm.dO + o)[1] = d1;
+            float nq = sumsq_u4(q0) + sumsq_u4(q1), nk = sumsq_u4(k0) + sumsq_u4(k1);
+            nq += __shfl_xor_sync(0xffffffffu, nq, 1);
+            nk += __shfl_xor_sync(0xffffffffu, nk, 1);
+            if (half == 0) {
+                sm.rq[sr] = 1.0f / fmaxf(sqrtf(nq), 1e-12f);           // F.normalize: x / max(|x|, 1e-12)
+                sm.rk[sr] = 1.0f / fmaxf(sqrtf(nk), 1e-12f);
+            }
+        }
+        __syncthreads();
+
+        // ---- row phase ----
+        unsigned qa[2][4], da[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const int off = (warp * 16 + l8 + (m4 & 1) * 8) * QLD + ks * 16 + (m4 >> 1) * 8;
+            ldmatrix_x4(qa[ks], sm.Q + off);
+            ldmatrix_x4(da[ks], sm.dO + off);
+        }
+        float cs[8][4], dp[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            cs[nt][0] = cs[nt][1] = cs[nt][2] = cs[nt][3] = 0.0f;
+            dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.0f;
+            unsigned kb[4], vb[4];
+            ldmatrix_x4(kb, sm.K + (nt * 8 + l8) * QLD + m4 * 8);
+            ldmatrix_x4(vb, sm.V + (nt * 8 + l8) * QLD + m4 * 8);
+            mma16816(cs[nt], qa[0], kb[0], kb[1]);
+            mma16816(cs[nt], qa[1], kb[2], kb[3]);
+            mma16816(dp[nt], da[0], vb[0], vb[1]);
+            mma16816(dp[nt], da[1], vb[2], vb[3]);
+        }
+        const float rq0 = sm.rq[R0], rq1 = sm.rq[R1];
+        const int wrem = win % wpi;
+        const bool last_y = shift > 0 && (wrem / wpr) == (H / WS) - 1, last_x = shift > 0 && (wrem % wpr) == wpr - 1;
+        const int cut = WS - shift;
+        const int hr0 = last_y ? (2 * warp < cut ? 1 : 2) : 0, hr1 = last_y ? (2 * warp + 1 < cut ? 1 : 2) : 0;
+        const int wrr = last_x ? (g < cut ? 1 : 2) : 0;
+        const int wc0 = last_x ? (2 * t < cut ? 1 : 2) : 0, wc1 = last_x ? (2 * t + 1 < cut ? 1 : 2) : 0;
+        float pr[8][4];
+        float m0 = -3.0e38f, m1 = -3.0e38f;
+        const float scl = sc * LOG2E_B;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int col = nt * 8 + 2 * t;
+            const float rk0 = sm.rk[col], rk1 = sm.rk[col + 1];
+            const float2 b0 = *reinterpret_cast<const float2*>(sm.Bs + R0 * BLD + col);
+            const float2 b1 = *reinterpret_cast<const float2*>(sm.Bs + R1 * BLD + col);
+            cs[nt][0] *= rq0 * rk0; cs[nt][1] *= rq0 * rk1; cs[nt][2] *= rq1 * rk0; cs[nt][3] *= rq1 * rk1;       // cosines
+            pr[nt][0] = fmaf(cs[nt][0], scl, b0.x);
+            pr[nt][1] = fmaf(cs[nt][1], scl, b0.y);
+            pr[nt][2] = fmaf(cs[nt][2], scl, b1.x);
+            pr[nt][3] = fmaf(cs[nt][3], scl, b1.y);
+            if (last_y || last_x) {
+                const int hc = last_y ? (nt < cut ? 1 : 2) : 0;
+                if (hc != hr0 || wc0 != wrr) pr[nt][0] += -100.0f * LOG2E_B;
+                if (hc != hr0 || wc1 != wrr) pr[nt][1] += -100.0f * LOG2E_B;
+                if (hc != hr1 || wc0 != wrr) pr[nt][2] += -100.0f * LOG2E_B;
+                if (hc != hr1 || wc1 != wrr) pr[nt][3] += -100.0f * LOG2E_B;
+            }
+            m0 = fmaxf(m0, fmaxf(pr[nt][0], pr[nt][1]));
+            m1 = fmaxf(m1, fmaxf(pr[nt][2], pr[nt][3]));
+        }
+        m0 = quad_max(m0);
+        m1 = quad_max(m1);
+        float l0 = 0.0f, l1 = 0.0f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            pr[nt][0] = ex2_fast(pr[nt][0] - m0);
+            pr[nt][1] = ex2_fast(pr[nt][1] - m0);
+            pr[nt][2] = ex2_fast(pr[nt][2] - m1);
+            pr[nt][3] = ex2_fast(pr[nt][3] - m1);
+            l0 += pr[nt][0] + pr[nt][1];
+            l1 += pr[nt][2] + pr[nt][3];
+        }
+        const float i0 = 1.0f / quad_sum(l0), i1 = 1.0f / quad_sum(l1);
+        float de0 = 0.0f, de1 = 0.0f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            pr[nt][0] *= i0; pr[nt][1] *= i0; pr[nt][2] *= i1; pr[nt][3] *= i1;
+            de0 = fmaf(pr[nt][0], dp[nt][0], fmaf(pr[nt][1], dp[nt][1], de0));
+            de1 = fmaf(pr[nt][2], dp[nt][2], fmaf(pr[nt][3], dp[nt][3], de1));
+        }
+        de0 = quad_sum(de0);
+        de1 = quad_sum(de1);
+        unsigned* Pw = reinterpret_cast<unsigned*>(sm.P);
+        unsigned* Ew = reinterpret_cast<unsigned*>(sm.E);
+        // dp becomes scale * dS / |k_j| (the A operand of dqn); P and E = scale * dS / |q_i| go to shared memory for the column phase
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int col = nt * 8 + 2 * t;
+            const float rk0 = sm.rk[col], rk1 = sm.rk[col + 1];
+            const float s0 = pr[nt][0] * (dp[nt][0] - de0), s1 = pr[nt][1] * (dp[nt][1] - de0);
+            const float s2 = pr[nt][2] * (dp[nt][2] - de1), s3 = pr[nt][3] * (dp[nt][3] - de1);
+            dB[nt][0] += s0; dB[nt][1] += s1; dB[nt][2] += s2; dB[nt][3] += s3;
+            dscale_acc = fmaf(s0, cs[nt][0], fmaf(s1, cs[nt][1], fmaf(s2, cs[nt][2], fmaf(s3, cs[nt][3], dscale_acc))));
+            Pw[(R0 * PLD + col) >> 1] = f2_to_bf2(pr[nt][0], pr[nt][1]);
+            Pw[(R1 * PLD + col) >> 1] = f2_to_bf2(pr[nt][2], pr[nt][3]);
+            Ew[(R0 * PLD + col) >> 1] = f2_to_bf2(s0 * sc * rq0, s1 * sc * rq0);
+            Ew[(R1 * PLD + col) >> 1] = f2_to_bf2(s2 * sc * rq1, s3 * sc * rq1);
+            dp[nt][0] = s0 * sc * rk0; dp[nt][1] = s1 * sc * rk1; dp[nt][2] = s2 * sc * rk0; dp[nt][3] = s3 * sc * rk1;
+        }
+        // dqn = (scale dS / |k|) K : 4 key steps x 4 dim tiles
+        float acc[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const unsigned pa[4] = {f2_to_bf2(dp[2 * kk][0], dp[2 * kk][1]), f2_to_bf2(dp[2 * kk][2], dp[2 * kk][3]),
+                                    f2_to_bf2(dp[2 * kk + 1][0], dp[2 * kk + 1][1]), f2_to_bf2(dp[2 * kk + 1][2], dp[2 * kk + 1][3])};
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                unsigned kb[4];
+                ldmatrix_x4_trans(kb, sm.K + (kk * 16 + (m4 & 1) * 8 + l8) * QLD + (2 * np + (m4 >> 1)) * 8);
+                mma16816(acc[2 * np], pa, kb[0], kb[1]);
+                mma16816(acc[2 * np + 1], pa, kb[2], kb[3]);
+            }
+        }
+        {
+            // dq = (dqn - qn (qn . dqn)) / |q|; the accumulator positions (row, dims 8 nt + 2t, +1) are the A-fragment words of Q
+            float dot0 = 0.0f, dot1 = 0.0f;
+            float2 q0v[4], q1v[4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                q0v[nt] = bf2_to_f2(qa[nt >> 1][(nt & 1) * 2]);
+                q1v[nt] = bf2_to_f2(qa[nt >> 1][(nt & 1) * 2 + 1]);
+                q0v[nt].x *= rq0; q0v[nt].y *= rq0; q1v[nt].x *= rq1; q1v[nt].y *= rq1;
+                dot0 = fmaf(q0v[nt].x, acc[nt][0], fmaf(q0v[nt].y, acc[nt][1], dot0));
+                dot1 = fmaf(q1v[nt].x, acc[nt][2], fmaf(q1v[nt].y, acc[nt][3], dot1));
+            }
+            dot0 = quad_sum(dot0);
+            dot1 = quad_sum(dot1);
+            unsigned* o0 = reinterpret_cast<unsigned*>(dqkv + size_t(window_token(win, R0, H, W, wpr, wpi, shift)) * (3 * size_t(C)) + head * HD);
+            unsigned* o1 = reinterpret_cast<unsigned*>(dqkv + size_t(window_token(win, R1, H, W, wpr, wpi, shift)) * (3 * size_t(C)) + head * HD);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                o0[nt * 4 + t] = f2_to_bf2((acc[nt][0] - q0v[nt].x * dot0) * rq0, (acc[nt][1] - q0v[nt].y * dot0) * rq0);
+                o1[nt * 4 + t] = f2_to_bf2((acc[nt][2] - q1v[nt].x * dot1) * rq1, (acc[nt][3] - q1v[nt].y * dot1) * rq1);
+            }
+        }
+        __syncthreads();                                   // P and E of all four warps are in shared memory
+
+        // ---- column phase: warp w = keys 16w .. 16w+15 ----
+        float dv[4][4], dk[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            dv[nt][0] = dv[nt][1] = dv[nt][2] = dv[nt][3] = 0.0f;
+            dk[nt][0] = dk[nt][1] = dk[nt][2] = dk[nt][3] = 0.0f;
+        }
+#pragma unroll
+        for (int kq = 0; kq < 4; ++kq) {
+            // A = P^T / E^T: matrix m of the x4 load = queries 16 kq + 8 (m >> 1) .. +7 (stored rows), keys 16 w + 8 (m & 1) .. +7
+            unsigned pa[4], ea[4];
+            const int aoff = (kq * 16 + (m4 >> 1) * 8 + l8) * PLD + warp * 16 + (m4 & 1) * 8;
+            ldmatrix_x4_trans(pa, sm.P + aoff);
+            ldmatrix_x4_trans(ea, sm.E + aoff);
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                unsigned db[4], qb[4];
+                const int boff = (kq * 16 + (m4 & 1) * 8 + l8) * QLD + (2 * np + (m4 >> 1)) * 8;
+                ldmatrix_x4_trans(db, sm.dO + boff);
+                ldmatrix_x4_trans(qb, sm.Q + boff);
+                mma16816(dv[2 * np], pa, db[0], db[1]);
+                mma16816(dv[2 * np + 1], pa, db[2], db[3]);
+                mma16816(dk[2 * np], ea, qb[0], qb[1]);
+                mma16816(dk[2 * np + 1], ea, qb[2], qb[3]);
+            }
+        }
+        {
+            const float rk0 = sm.rk[R0], rk1 = sm.rk[R1];
+            const unsigned* Kw = reinterpret_cast<const unsigned*>(sm.K);
+            float dot0 = 0.0f, dot1 = 0.0f;
+            float2 k0v[4], k1v[4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                k0v[nt] = bf2_to_f2(Kw[(R0 * QLD + nt * 8 + 2 * t) >> 1]);
+                k1v[nt] = bf2_to_f2(Kw[(R1 * QLD + nt * 8 + 2 * t) >> 1]);
+                k0v[nt].x *= rk0; k0v[nt].y *= rk0; k1v[nt].x *= rk1; k1v[nt].y *= rk1;
+                dot0 = fmaf(k0v[nt].x, dk[nt][0], fmaf(k0v[nt].y, dk[nt][1], dot0));
+                dot1 = fmaf(k1v[nt].x, dk[nt][2], fmaf(k1v[nt].y, dk[nt][3], dot1));
+            }
+            dot0 = quad_sum(dot0);
+            dot1 = quad_sum(dot1);
+            unsigned* o0 = reinterpret_cast<unsigned*>(dqkv + size_t(window_token(win, R0, H, W, wpr, wpi, shift)) * (3 * size_t(C)) + head * HD);
+            unsigned* o1 = reinterpret_cast<unsigned*>(dqkv + size_t(window_token(win, R1, H, W, wpr, wpi, shift)) * (3 * size_t(C)) + head * HD);
+            const int ck = C >> 1;                           // 32-bit words per qkv third
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                o0[ck + nt * 4 + t] = f2_to_bf2((dk[nt][0] - k0v[nt].x * dot0) * rk0, (dk[nt][1] - k0v[nt].y * dot0) * rk0);
+                o1[ck + nt * 4 + t] = f2_to_bf2((dk[nt][2] - k1v[nt].x * dot1) * rk1, (dk[nt][3] - k1v[nt].y * dot1) * rk1);
+                o0[2 * ck + nt * 4 + t] = f2_to_bf2(dv[nt][0], dv[nt][1]);
+                o1[2 * ck + nt * 4 + t] = f2_to_bf2(dv[nt][2], dv[nt][3]);
+            }
+        }
+    }
+    // ---- d(bias tile), d(scale) of this CTA's windows ----
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int col = nt * 8 + 2 * t;
+        float* b0 = dbias + (size_t(head) * WT + R0) * WT + col;
+        float* b1 = dbias + (size_t(head) * WT + R1) * WT + col;
+        atomicAdd(b0, dB[nt][0]);
+        atomicAdd(b0 + 1, dB[nt][1]);
+        atomicAdd(b1, dB[nt][2]);
+        atomicAdd(b1 + 1, dB[nt][3]);
+    }
+    dscale_acc = warp_sum(dscale_acc);
+    if (lane == 0) atomicAdd(dscale + head, dscale_acc);
+}
+
 // dx[b][2*h2 + (q & 1)][2*w2 + (q >> 1)][c] = dy[b][h2][w2][q * C + c]   (inverse of patch_merge_kernel)
 __global__ void __launch_bounds__(256)
 patch_merge_scatter_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, int H, int W, int C8, size_t total) {
@@ -365,6 +678,24 @@ extern "C" int rgbnm_window_attention_bwd(const void* qkv, const void* dout, con
         configured = true;
     }
     const int n_windows = B * (H / WS) * (W / WS);
+    static const bool simt = [] { const char* e = std::getenv("RGBNM_WATTN_BWD_SIMT"); return e != nullptr && e[0] == '1'; }();
+    if (!simt) {
+        static bool configured_mma = false;
+        if (!configured_mma) {
+            RGBNM_CUDA_CHECK(cudaFuncSetAttribute(window_attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  int(sizeof(AttnBwdMmaSmem))));
+            configured_mma = true;
+        }
+        // one resident wave of CTAs, each walking the windows of one head
+        int per_head = swinb_num_sms() * RGBNM_WATTN_BWD_MINBLOCKS / heads;
+        if (per_head < 1) per_head = 1;
+        if (per_head > n_windows) per_head = n_windows;
+        window_attn_bwd_mma_kernel<<<dim3(per_head, heads), 128, sizeof(AttnBwdMmaSmem), static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), bias, scale, static_cast<__nv_bfloat16*>(dqkv),
+            dbias, dscale, H, W, C, shift, n_windows);
+        RGBNM_CUDA_CHECK(cudaGetLastError());
+        return RGBNM_OK;
+    }
     int ctas = swinb_num_sms() * 2 / heads;
     if (ctas < 1) ctas = 1;
     if (ctas > n_windows) ctas = n_windows;

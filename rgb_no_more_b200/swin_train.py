@@ -43,6 +43,8 @@ class SwinTrainEngine:
         depths = [len(layer.blocks) for layer in model.layers]
         self.dpr = [float(v) for v in torch.linspace(0, model.drop_path_rate, sum(depths))]      # swinv2.py:648
         self._lins: Dict[int, tuple] = {}
+        self.static_weights = False      # SwinFlatEngine: working copies are refreshed by one table launch, never rebuilt here
+        self.grads_static = None         # SwinFlatEngine: gradient views into its flat buffer (zeroed by the caller)
 
     # ---------------------------------------------------------------------------------------------
     def _lin(self, weight) -> "_Lin":
@@ -50,6 +52,8 @@ class SwinTrainEngine:
         if not hasattr(self, "_lins"):
             self._lins = {}
         hit = self._lins.get(id(weight))
+        if hit is not None and self.static_weights:
+            return hit[1]
         if hit is None or hit[0] != weight._version or hit[1].w.device != self.device:
             hit = (weight._version, _Lin(weight, self.device))
             self._lins[id(weight)] = hit
@@ -186,7 +190,8 @@ class SwinTrainEngine:
     def backward(self, dlogits: torch.Tensor) -> Dict[str, torch.Tensor]:
         m, dev, sv = self.model, self.device, self.saved
         B = sv["B"]
-        self.grads = {k: torch.zeros_like(p, dtype=torch.float32, device=dev) for k, p in m.named_parameters()}
+        self.grads = self.grads_static if self.grads_static is not None else \
+            {k: torch.zeros_like(p, dtype=torch.float32, device=dev) for k, p in m.named_parameters()}
         gr = self.grads
         dlogits = dlogits.float()
         gr["head.weight"] += dlogits.t() @ sv["pooled"]
@@ -247,3 +252,64 @@ class SwinFunction(torch.autograd.Function):
     def backward(ctx, dlogits):
         grads = ctx.engine.backward(dlogits.contiguous())
         return (None, None, None, *[grads[n].to(torch.float32) for n in ctx.names])
+
+
+class SwinFlatEngine:
+    """SwinTrainEngine behind the interface train_step.TrainStage drives (flat fp32 parameter / gradient buffers, forward,
+    backward, refresh_weights): the parameters become views into ONE flat buffer -- first the group the reference's WeightDecay
+    optimiser acts on ('.weight' in the name, pipeline_utils.py:537), then the rest -- so that the step is one flat all-reduce, one
+    clip + AdamW + decay kernel and one weight-refresh launch, and forward + backward can be captured in a CUDA graph."""
+    ALIGN = 8          # elements: every parameter starts on a 32-byte boundary (vector reds of the wgrad epilogue)
+
+    def __init__(self, model, device: torch.device):
+        import ctypes as C
+        import numpy as np
+        self.model, self.dev = model, torch.device(device)
+        self.inner = SwinTrainEngine(model, self.dev)
+        named = list(model.named_parameters())
+        decay = [(k, p) for k, p in named if ".weight" in k]
+        rest = [(k, p) for k, p in named if ".weight" not in k]
+        pad = lambda n: -(-n // self.ALIGN) * self.ALIGN
+        self.n_decay = sum(pad(p.numel()) for _, p in decay)
+        total = self.n_decay + sum(pad(p.numel()) for _, p in rest)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.flat_grad = torch.zeros_like(self.flat)
+        grads, off = {}, 0
+        with torch.no_grad():
+            for k, p in decay + rest:
+                n = p.numel()
+                self.flat[off:off + n].copy_(p.data.reshape(-1))
+                p.data = self.flat[off:off + n].view(p.shape)
+                grads[k] = self.flat_grad[off:off + n].view(p.shape)
+                off += pad(n)
+        self.inner.grads_static = grads
+        # bf16 working copies of every Linear the engine multiplies with, refreshed by one launch over a descriptor table
+        lins = [model.patch_embed.projection[0].weight]
+        for layer in model.layers:
+            for blk in layer.blocks:
+                lins += [blk.attn.qkv.weight, blk.attn.proj.weight, blk.mlp.fc1.weight, blk.mlp.fc2.weight]
+            if layer.downsample is not None:
+                lins.append(layer.downsample.reduction.weight)
+        arr = (_lib.WPrepDesc * len(lins))()
+        tiles = 0
+        for i, w in enumerate(lins):
+            lin = _Lin(w, self.dev)
+            self.inner._lins[id(w)] = (None, lin)
+            d = arr[i]
+            d.w, d.w_bf16, d.wt_bf16, d.bias, d.bias_k = w.data_ptr(), lin.w.data_ptr(), lin.wt.data_ptr(), None, None
+            d.n, d.k, d.qkv_heads, d.head_dim, d.first_tile = w.shape[0], w.shape[1], 0, 0, tiles
+            tiles += -(-w.shape[0] // 32) * -(-w.shape[1] // 32)
+        self.inner.static_weights = True
+        self._wprep = (torch.from_numpy(np.frombuffer(bytes(arr), dtype=np.uint8).copy()).to(self.dev), len(lins), tiles)
+        self.launches = 0
+
+    def forward(self, x_in: torch.Tensor) -> torch.Tensor:
+        return self.inner.forward(x_in)
+
+    def backward(self, dlogits: torch.Tensor) -> None:
+        self.flat_grad.zero_()
+        self.inner.backward(dlogits)
+
+    def refresh_weights(self) -> None:
+        table, n, tiles = self._wprep
+        _lib.check(self.inner.L.rgbnm_weight_prep_batch(table.data_ptr(), n, tiles, _lib.stream_ptr()), "rgbnm_weight_prep_batch")

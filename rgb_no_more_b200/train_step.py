@@ -18,7 +18,9 @@ from . import ops as K
 from . import vit as V
 
 ARCHS = {"vitti": dict(emb_size=192, depth=12, num_heads=3, wd=1e-4), "vits": dict(emb_size=384, depth=12, num_heads=6, wd=3e-4),
-         "vitb": dict(emb_size=768, depth=12, num_heads=12, wd=3e-4)}
+         "vitb": dict(emb_size=768, depth=12, num_heads=12, wd=3e-4),
+         # SwinV2-T DCT, window 8 (utils/configs.py:123-138; TRAIN.WD default :26): same loop, swin_train.SwinFlatEngine underneath
+         "swinv2t": dict(swin=True, wd=3e-4)}
 
 
 class TrainStage:
@@ -36,10 +38,22 @@ class TrainStage:
         # the augmentation plans are drawn from torch's global CPU generator, seeded SEED + rank by the caller (train.py:119)
         with torch.random.fork_rng(devices=[self.dev] if self.dev.type == "cuda" else []):
             torch.manual_seed(seed)
-            self.model = V.ViT(patch_size=16, emb_size=cfg["emb_size"], depth=cfg["depth"], n_classes=1000, drop_p=0.0,
-                               pixel_space="DCT", ver=1, use_subblock=True, device=self.dev, num_heads=cfg["num_heads"],
-                               head_size=64, attention=attention)
-        self.eng = self.model.prepare(self.dev)
+            if cfg.get("swin"):
+                from . import swin as S
+                self.model = S.SwinTransformerV2(img_size=256, patch_size=4, embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24],
+                                                 window_size=8, mlp_ratio=4, drop_path_rate=0.2, pretrained_window_sizes=[0, 0, 0, 0],
+                                                 device=self.dev, pixel_space="dct").train()
+            else:
+                self.model = V.ViT(patch_size=16, emb_size=cfg["emb_size"], depth=cfg["depth"], n_classes=1000, drop_p=0.0,
+                                   pixel_space="DCT", ver=1, use_subblock=True, device=self.dev, num_heads=cfg["num_heads"],
+                                   head_size=64, attention=attention)
+        if cfg.get("swin"):
+            from . import swin_train as ST
+            self.eng = ST.SwinFlatEngine(self.model, self.dev)
+            tokens, feat = 4096, 24
+        else:
+            self.eng = self.model.prepare(self.dev)
+            tokens, feat = V.TOKENS, V.IN_FEAT
         self.base_lr, self.wd = lr, cfg["wd"]
         self.warmup_steps, self.total_steps = warmup_steps, total_steps
         self.m = torch.zeros_like(self.eng.flat)
@@ -61,7 +75,7 @@ class TrainStage:
         self.use_graph = use_graph
         self.g_fb: Optional[torch.cuda.CUDAGraph] = None
         self.g_opt: Optional[torch.cuda.CUDAGraph] = None
-        self.x_static = torch.zeros((batch, V.TOKENS, V.IN_FEAT), dtype=torch.bfloat16, device=self.dev)
+        self.x_static = torch.zeros((batch, tokens, feat), dtype=torch.bfloat16, device=self.dev)
         self.x_mixed = torch.zeros_like(self.x_static)
         self.y_static = torch.zeros((batch,), dtype=torch.int64, device=self.dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
@@ -125,7 +139,7 @@ class TrainStage:
 
     # ---- public ---------------------------------------------------------------------------------------------
     def step(self, x: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
-        """x: (B,196,384) bf16 from FusedDCT, labels (B,) int64.  Returns the device scalar loss of this step."""
+        """x: (B,196,384) bf16 from FusedDCT ((B,4096,24) for swinv2t), labels (B,) int64.  Returns the device scalar loss of this step."""
         self._set_hyper()
         if x.data_ptr() != self.x_static.data_ptr():          # FusedDCT can write straight into x_static (out=stage.x_static)
             self.x_static.copy_(x, non_blocking=True)

@@ -159,3 +159,54 @@ def test_swin_training_step_with_stochastic_depth_learns():
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0], losses
+
+
+def test_swin_flat_engine_matches_the_autograd_path():
+    """swin_train.SwinFlatEngine (parameters as views of one flat buffer, gradients written into its flat twin, working copies
+    refreshed by one table launch) against the same model through the autograd.Function path: identical logits, gradients equal
+    up to the atomics' summation order; after an in-place update of the flat buffer + refresh_weights() the logits follow."""
+    from rgb_no_more_b200 import swin as S, swin_train as ST
+    from tests.helpers import seeded_swin_state_dict
+
+    def build():
+        m = S.SwinTransformerV2(img_size=256, patch_size=4, embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=8,
+                                drop_path_rate=0.0, pretrained_window_sizes=[0, 0, 0, 0], device="cpu", pixel_space="dct")
+        m.load_state_dict(seeded_swin_state_dict(m))
+        return m.train().to(DEV)
+    a, b = build(), build()
+    x = (torch.randn(2, 4096, 24, generator=torch.Generator().manual_seed(4)) * 0.5).to(DEV).to(torch.bfloat16)
+    y = torch.tensor([7, 123], device=DEV)
+    loss = F.cross_entropy(a(x), y)
+    loss.backward()
+    eng = ST.SwinFlatEngine(b, torch.device(DEV))
+    assert eng.n_decay % 8 == 0 and all(p.data_ptr() % 32 == 0 for p in b.parameters())
+    logits = eng.forward(x)
+    assert torch.equal(logits, a(x).detach())
+    dlogits = (torch.softmax(logits, 1) - F.one_hot(y, 1000).float()) / 2
+    eng.backward(dlogits)
+    torch.cuda.synchronize()
+    for (k, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        gq = eng.inner.grads_static[k]
+        assert _rel(gq, p.grad) < 2e-3, k
+    with torch.no_grad():
+        eng.flat.mul_(1.01)
+        for p, q in zip(a.parameters(), b.parameters()):
+            p.mul_(1.01)
+    eng.refresh_weights()
+    assert float((eng.forward(x) - a(x).detach()).abs().max()) < 1e-3 * float(logits.abs().max())
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_swin_train_stage_learns(use_graph):
+    """train_step.TrainStage(arch='swinv2t'): mixup -> SwinV2-T forward / backward (stochastic depth 0.2) -> clip + AdamW + decoupled
+    decay kernel -> working-copy refresh, as two CUDA graphs or eagerly: finite, decreasing loss on one repeated batch."""
+    from rgb_no_more_b200 import train_step as TS
+    st = TS.TrainStage(DEV, arch="swinv2t", batch=4, lr=1e-3, warmup_steps=2, total_steps=100, mixup_alpha=0.0, use_graph=use_graph)
+    with torch.no_grad():                                   # the reference zero-initialises the block post-norms
+        st.eng.flat.add_(0.05 * torch.randn_like(st.eng.flat) * (st.eng.flat == 0))
+    st.eng.refresh_weights()
+    x = (torch.randn(4, 4096, 24, generator=torch.Generator().manual_seed(1)) * 0.5).to(DEV).to(torch.bfloat16)
+    y = torch.tensor([1, 5, 9, 2], device=DEV)
+    losses = [float(st.step(x, y)) for _ in range(12)]
+    assert all(l == l for l in losses), losses
+    assert losses[-1] < 0.7 * losses[0], losses
