@@ -52,7 +52,7 @@ class SwinTrainEngine:
         if not hasattr(self, "_lins"):
             self._lins = {}
         hit = self._lins.get(id(weight))
-        if hit is not None and self.static_weights:
+        if hit is not None and getattr(self, "static_weights", False):
             return hit[1]
         if hit is None or hit[0] != weight._version or hit[1].w.device != self.device:
             hit = (weight._version, _Lin(weight, self.device))
@@ -190,7 +190,7 @@ class SwinTrainEngine:
     def backward(self, dlogits: torch.Tensor) -> Dict[str, torch.Tensor]:
         m, dev, sv = self.model, self.device, self.saved
         B = sv["B"]
-        self.grads = self.grads_static if self.grads_static is not None else \
+        self.grads = self.grads_static if getattr(self, "grads_static", None) is not None else \
             {k: torch.zeros_like(p, dtype=torch.float32, device=dev) for k, p in m.named_parameters()}
         gr = self.grads
         dlogits = dlogits.float()
