@@ -149,6 +149,139 @@ ln_res_bwd_kernel(const unsigned* __restrict__ dy, const unsigned* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// The same two kernels with G lanes per row (E = 2 * G * PPL exactly: 96 -> 8 lanes x 6 pairs, 192 -> 16 x 6, 384 -> 32 x 6,
+// 768 -> 32 x 12).  At 96 / 192 channels a warp works on 4 / 2 rows at once: no idle lanes (a 96-wide row fills 48 of a warp's 64
+// pair slots otherwise), reductions of 3 / 4 shuffle steps shared by the rows, gamma / beta held in registers.
+// ------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int G, int PPL>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_res_scaled_fwd_g_kernel(const unsigned* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                           const unsigned* __restrict__ res, const float* __restrict__ row_scale, int rows_per_scale,
+                           unsigned* __restrict__ y, int rows, float eps) {
+    constexpr int RPW = 32 / G, PAIRS = G * PPL;
+    const int lane = threadIdx.x & 31, grp = lane / G, j = lane % G;
+    const float inv_e = 1.0f / float(2 * PAIRS);
+    float2 gm[PPL], bt[PPL];
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) {
+        gm[k] = *reinterpret_cast<const float2*>(gamma + 2 * (k * G + j));
+        bt[k] = *reinterpret_cast<const float2*>(beta + 2 * (k * G + j));
+    }
+    for (int base = (blockIdx.x * LN_WARPS + (threadIdx.x >> 5)) * RPW; base < rows; base += gridDim.x * LN_WARPS * RPW) {
+        const int row = base + grp;
+        const bool live = row < rows;
+        const unsigned* xr = x + size_t(live ? row : 0) * PAIRS;
+        float2 v[PPL];
+        unsigned rr[PPL];
+        float s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+            v[k] = bf2_to_f2(__ldg(xr + k * G + j));
+            rr[k] = (res != nullptr) ? __ldg(res + size_t(live ? row : 0) * PAIRS + k * G + j) : 0u;
+            s += v[k].x + v[k].y;
+        }
+        const float mean = group_sum<G>(s) * inv_e;
+        float q = 0.0f;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) { const float a = v[k].x - mean, b = v[k].y - mean; q += a * a + b * b; }
+        const float rstd = rsqrtf(group_sum<G>(q) * inv_e + eps);
+        const float sc = (row_scale != nullptr && live) ? __ldg(row_scale + row / rows_per_scale) : 1.0f;
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < PPL; ++k) {
+                const float2 r = bf2_to_f2(rr[k]);
+                const float o0 = sc * ((v[k].x - mean) * rstd * gm[k].x + bt[k].x) + r.x;
+                const float o1 = sc * ((v[k].y - mean) * rstd * gm[k].y + bt[k].y) + r.y;
+                y[size_t(row) * PAIRS + k * G + j] = f2_to_bf2(o0, o1);
+            }
+        }
+    }
+}
+
+template <int G, int PPL>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_res_bwd_g_kernel(const unsigned* __restrict__ dy, const unsigned* __restrict__ x, const float* __restrict__ gamma,
+                    const float* __restrict__ row_scale, int rows_per_scale, unsigned* __restrict__ dx, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, int rows, float eps) {
+    constexpr int RPW = 32 / G, PAIRS = G * PPL, E = 2 * PAIRS;
+    __shared__ float red[LN_WARPS * RPW][E];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / G, j = lane % G;
+    const float inv_e = 1.0f / float(E);
+    float2 gm[PPL], ag[PPL], ab[PPL];
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) {
+        gm[k] = *reinterpret_cast<const float2*>(gamma + 2 * (k * G + j));
+        ag[k] = ab[k] = make_float2(0.0f, 0.0f);
+    }
+    for (int base = (blockIdx.x * LN_WARPS + warp) * RPW; base < rows; base += gridDim.x * LN_WARPS * RPW) {
+        const int row = base + grp;
+        const bool live = row < rows;
+        const size_t ro = size_t(live ? row : 0) * PAIRS;
+        float2 v[PPL], g[PPL];
+        float s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+            v[k] = bf2_to_f2(__ldg(x + ro + k * G + j));
+            g[k] = live ? bf2_to_f2(__ldg(dy + ro + k * G + j)) : make_float2(0.0f, 0.0f);
+            s += v[k].x + v[k].y;
+        }
+        const float mean = group_sum<G>(s) * inv_e;
+        float q = 0.0f;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) { const float a = v[k].x - mean, b = v[k].y - mean; q += a * a + b * b; }
+        const float rstd = rsqrtf(group_sum<G>(q) * inv_e + eps);
+        const float sc = (row_scale != nullptr && live) ? __ldg(row_scale + row / rows_per_scale) : 1.0f;
+        float m1 = 0.0f, m2 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+            v[k].x = (v[k].x - mean) * rstd;                         // xhat
+            v[k].y = (v[k].y - mean) * rstd;
+            g[k].x *= sc;
+            g[k].y *= sc;
+            ab[k].x += g[k].x;
+            ab[k].y += g[k].y;
+            ag[k].x += g[k].x * v[k].x;
+            ag[k].y += g[k].y * v[k].y;
+            g[k].x *= gm[k].x;                                       // dxhat
+            g[k].y *= gm[k].y;
+            m1 += g[k].x + g[k].y;
+            m2 += g[k].x * v[k].x + g[k].y * v[k].y;
+        }
+        m1 = group_sum<G>(m1) * inv_e;
+        m2 = group_sum<G>(m2) * inv_e;
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < PPL; ++k)
+                dx[ro + k * G + j] = f2_to_bf2(rstd * (g[k].x - m1 - v[k].x * m2), rstd * (g[k].y - m1 - v[k].y * m2));
+        }
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+            const float2 a = pass == 0 ? ag[k] : ab[k];
+            red[warp * RPW + grp][2 * (k * G + j)] = a.x;
+            red[warp * RPW + grp][2 * (k * G + j) + 1] = a.y;
+        }
+        __syncthreads();
+        float* out = pass == 0 ? dgamma : dbeta;
+        for (int c = threadIdx.x; c < E; c += LN_WARPS * 32) {
+            float t = 0.0f;
+#pragma unroll
+            for (int w = 0; w < LN_WARPS * RPW; ++w) t += red[w][c];
+            atomicAdd(out + c, t);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Window attention backward, CUDA cores.  CTA = 64 threads, walks the windows of one head (blockIdx.y) so that the head's
 // bias-gradient tile accumulates in shared memory and is flushed once.  Row pass (thread = query i): s, P, dP = dO . V^T,
 // delta, dS -> shared; dq.  Column pass (thread = key j): dV = P^T dO, dk.  Cosine normalisation differentiated explicitly:
@@ -643,6 +776,19 @@ extern "C" int rgbnm_layernorm_res_scaled_fwd(const void* x, const float* gamma,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int grid = (rows + LN_WARPS - 1) / LN_WARPS;
     if (grid > swinb_num_sms() * 8) grid = swinb_num_sms() * 8;
+#define SWINB_LN_FWD_G(GG, PP)                                                                                                         \
+    ln_res_scaled_fwd_g_kernel<GG, PP><<<grid, LN_WARPS * 32, 0, st>>>(static_cast<const unsigned*>(x), gamma, beta,                   \
+                                                                        static_cast<const unsigned*>(res), row_scale, rows_per_scale, \
+                                                                        static_cast<unsigned*>(y), rows, eps)
+    if (emb == 96 || emb == 192 || emb == 384 || emb == 768) {
+        if (emb == 96) SWINB_LN_FWD_G(8, 6);
+        else if (emb == 192) SWINB_LN_FWD_G(16, 6);
+        else if (emb == 384) SWINB_LN_FWD_G(32, 6);
+        else SWINB_LN_FWD_G(32, 12);
+        RGBNM_CUDA_CHECK(cudaGetLastError());
+        return RGBNM_OK;
+    }
+#undef SWINB_LN_FWD_G
     SWINB_LN_DISPATCH(ln_res_scaled_fwd_kernel, static_cast<const unsigned*>(x), gamma, beta, static_cast<const unsigned*>(res), row_scale,
                       rows_per_scale, static_cast<unsigned*>(y), rows, emb, eps);
     RGBNM_CUDA_CHECK(cudaGetLastError());
@@ -658,6 +804,19 @@ extern "C" int rgbnm_layernorm_res_bwd(const void* dy, const void* x, const floa
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int grid = (rows + LN_WARPS - 1) / LN_WARPS;
     if (grid > swinb_num_sms() * 4) grid = swinb_num_sms() * 4;
+#define SWINB_LN_BWD_G(GG, PP)                                                                                                     \
+    ln_res_bwd_g_kernel<GG, PP><<<grid, LN_WARPS * 32, 0, st>>>(static_cast<const unsigned*>(dy), static_cast<const unsigned*>(x), \
+                                                                 gamma, row_scale, rows_per_scale, static_cast<unsigned*>(dx),     \
+                                                                 dgamma, dbeta, rows, eps)
+    if (emb == 96 || emb == 192 || emb == 384 || emb == 768) {
+        if (emb == 96) SWINB_LN_BWD_G(8, 6);
+        else if (emb == 192) SWINB_LN_BWD_G(16, 6);
+        else if (emb == 384) SWINB_LN_BWD_G(32, 6);
+        else SWINB_LN_BWD_G(32, 12);
+        RGBNM_CUDA_CHECK(cudaGetLastError());
+        return RGBNM_OK;
+    }
+#undef SWINB_LN_BWD_G
     SWINB_LN_DISPATCH(ln_res_bwd_kernel, static_cast<const unsigned*>(dy), static_cast<const unsigned*>(x), gamma, row_scale, rows_per_scale,
                       static_cast<unsigned*>(dx), dgamma, dbeta, rows, emb, eps);
     RGBNM_CUDA_CHECK(cudaGetLastError());

@@ -88,9 +88,8 @@ class SwinTrainEngine:
                                                      window, shift, _lib.stream_ptr()), "rgbnm_window_attention_fwd")
         return att
 
-    def _attn_bwd(self, qkv, datt, bias, scale, B, H, Cd, heads, window, shift):
+    def _attn_bwd(self, qkv, datt, bias, scale, dbias, dscale, B, H, Cd, heads, window, shift):
         dqkv = torch.empty_like(qkv)
-        dbias, dscale = torch.zeros_like(bias), torch.zeros_like(scale)
         _lib.check(self.L.rgbnm_window_attention_bwd(qkv.data_ptr(), datt.data_ptr(), bias.data_ptr(), scale.data_ptr(), dqkv.data_ptr(),
                                                      dbias.data_ptr(), dscale.data_ptr(), B, H, H, Cd, heads, window, shift, _lib.stream_ptr()),
                    "rgbnm_window_attention_bwd")
@@ -116,6 +115,62 @@ class SwinTrainEngine:
             K.colsum(dy, self.grads[bname])
 
     # ---------------------------------------------------------------------------------------------
+    # The parameter-only graph behind the attention tables (swinv2.py:158-168): bias tile = 16 * sigmoid(cpb_mlp(coords table))
+    # gathered by relative_position_index, logit scale = exp(min(logit_scale, log 100)).  Evaluated and differentiated for all blocks
+    # of a (heads, window) group at once with batched matmuls (12 blocks x ~45 tiny launches each otherwise).
+    def _table_groups(self):
+        groups = {}
+        for li, layer in enumerate(self.model.layers):
+            for bi, blk in enumerate(layer.blocks):
+                groups.setdefault((blk.attn.num_heads, blk.attn.window_size[0]), []).append((li, bi, blk.attn))
+        return groups
+
+    def _tables_forward(self, sv: dict) -> dict:
+        out, sv["tables"] = {}, []
+        cap = math.log(1.0 / 0.01)
+        for (heads, ws), members in self._table_groups().items():
+            a0 = members[0][2]
+            nb, n = len(members), ws * ws
+            coords = a0.relative_coords_table.reshape(-1, 2).float()                       # (R, 2), R = (2 ws - 1)^2
+            idx = a0.relative_position_index.reshape(-1)                                   # (n * n,)
+            W0 = torch.stack([a.cpb_mlp[0].weight.detach() for _, _, a in members])         # (nb, 512, 2)
+            b0 = torch.stack([a.cpb_mlp[0].bias.detach() for _, _, a in members])           # (nb, 512)
+            W2 = torch.stack([a.cpb_mlp[2].weight.detach() for _, _, a in members])         # (nb, heads, 512)
+            ls = torch.stack([a.logit_scale.detach().reshape(heads) for _, _, a in members])   # (nb, heads)
+            cx = coords.unsqueeze(0).expand(nb, -1, -1)
+            pre = torch.baddbmm(b0.unsqueeze(1), cx, W0.transpose(1, 2))                    # (nb, R, 512)
+            hh = torch.relu(pre)
+            tt = torch.bmm(hh, W2.transpose(1, 2))                                          # (nb, R, heads)
+            sg = torch.sigmoid(tt.index_select(1, idx))                                     # (nb, n * n, heads)
+            bias = (16.0 * sg).permute(0, 2, 1).reshape(nb, heads, n, n).contiguous()
+            scale = torch.clamp(ls, max=cap).exp().contiguous()
+            dbias, dscale = torch.zeros_like(bias), torch.zeros_like(scale)
+            for k, (li, bi, _) in enumerate(members):
+                out[(li, bi)] = (bias[k], scale[k], dbias[k], dscale[k])
+            sv["tables"].append(dict(members=members, heads=heads, n=n, coords=cx, idx=idx, W2=W2, ls=ls, pre=pre, hh=hh, sg=sg, scale=scale,
+                                     dbias=dbias, dscale=dscale, cap=cap))
+        return out
+
+    def _tables_backward(self, sv: dict) -> None:
+        gr = self.grads
+        for t in sv["tables"]:
+            members, heads, n = t["members"], t["heads"], t["n"]
+            nb = len(members)
+            sg = t["sg"]
+            dg = t["dbias"].reshape(nb, heads, n * n).permute(0, 2, 1) * (16.0 * sg * (1.0 - sg))      # (nb, n * n, heads)
+            dtt = torch.zeros((nb, t["coords"].shape[1], heads), dtype=torch.float32, device=dg.device).index_add_(1, t["idx"], dg)
+            dW2 = torch.bmm(dtt.transpose(1, 2), t["hh"])                                    # (nb, heads, 512)
+            dpre = torch.bmm(dtt, t["W2"]) * (t["pre"] > 0)                                  # (nb, R, 512)
+            dW0 = torch.bmm(dpre.transpose(1, 2), t["coords"])                               # (nb, 512, 2)
+            db0 = dpre.sum(1)
+            dls = t["dscale"] * t["scale"] * (t["ls"] <= t["cap"])
+            names = [f"layers.{li}.blocks.{bi}.attn" for li, bi, _ in members]
+            torch._foreach_add_([gr[p + ".cpb_mlp.0.weight"] for p in names], list(dW0.unbind(0)))
+            torch._foreach_add_([gr[p + ".cpb_mlp.0.bias"] for p in names], list(db0.unbind(0)))
+            torch._foreach_add_([gr[p + ".cpb_mlp.2.weight"] for p in names], list(dW2.unbind(0)))
+            torch._foreach_add_([gr[p + ".logit_scale"] for p in names], [g_.reshape(heads, 1, 1) for g_ in dls.unbind(0)])
+
+    # ---------------------------------------------------------------------------------------------
     def forward(self, x_in: torch.Tensor) -> torch.Tensor:
         """x_in (B, 4096, 24) -> fp32 logits; keeps what the backward needs in self.saved."""
         m, dev = self.model, self.device
@@ -131,6 +186,7 @@ class SwinTrainEngine:
         sv["e"] = e
         x = self._ln_fwd(e, (self._f32(pe.norm.weight), self._f32(pe.norm.bias)), None, None, 1, bf(T0, m.embed_dim))
         blk_index = 0
+        tables = self._tables_forward(sv)
         for li, layer in enumerate(m.layers):
             H, Cd = layer.input_resolution[0], layer.dim
             T = B * H * H
@@ -139,14 +195,7 @@ class SwinTrainEngine:
                 a = blk.attn
                 heads = a.num_heads
                 pfx = f"layers.{li}.blocks.{bi}"
-                # attention tables with autograd history (parameter-only graph)
-                with torch.enable_grad():
-                    hh = F.relu(F.linear(a.relative_coords_table, a.cpb_mlp[0].weight, a.cpb_mlp[0].bias))
-                    tt = F.linear(hh, a.cpb_mlp[2].weight).view(-1, heads)
-                    n = a.window_size[0] * a.window_size[1]
-                    bias_t = 16 * torch.sigmoid(tt[a.relative_position_index.view(-1)].view(n, n, heads).permute(2, 0, 1)).contiguous()
-                    scale_t = torch.clamp(a.logit_scale, max=math.log(1.0 / 0.01)).exp().reshape(heads)
-                bias_d, scale_d = bias_t.detach().float().contiguous(), scale_t.detach().float().contiguous()
+                bias_d, scale_d, dbias_d, dscale_d = tables[(li, bi)]
                 keep = 1.0 - self.dpr[blk_index]
                 blk_index += 1
                 s1 = s2 = None
@@ -164,8 +213,8 @@ class SwinTrainEngine:
                 g2 = self._f32(blk.norm2.weight)
                 x2 = self._ln_fwd(mm, (g2, self._f32(blk.norm2.bias)), x1, s2, H * H, bf(T, Cd))
                 st["blocks"].append(dict(pfx=pfx, attn=a, heads=heads, window=a.window_size[0], shift=blk.shift_size, x=x, qkv=qkv, att=att, p=p, x1=x1,
-                                         u=u, f=f, m=mm, g1=g1, g2=g2, s1=s1, s2=s2, lq=lq, lp=lp, l1=l1, l2=l2, bias_t=bias_t, scale_t=scale_t,
-                                         bias_d=bias_d, scale_d=scale_d))
+                                         u=u, f=f, m=mm, g1=g1, g2=g2, s1=s1, s2=s2, lq=lq, lp=lp, l1=l1, l2=l2,
+                                         bias_d=bias_d, scale_d=scale_d, dbias_d=dbias_d, dscale_d=dscale_d))
                 x = x2
             if layer.downsample is not None:
                 ds = layer.downsample
@@ -224,17 +273,13 @@ class SwinTrainEngine:
                 dp = self._ln_bwd(dx1, b["p"], b["g1"], b["s1"], H * H, pfx + ".norm1.weight", pfx + ".norm1.bias")
                 self._wgrad(dp, b["att"], pfx + ".attn.proj.weight", pfx + ".attn.proj.bias")
                 datt = G.gemm(dp, b["lp"].wt, G.EPI_STORE)
-                dqkv, dbias, dscale = self._attn_bwd(b["qkv"], datt, b["bias_d"], b["scale_d"], B, H, Cd, b["heads"], b["window"], b["shift"])
+                dqkv, _, _ = self._attn_bwd(b["qkv"], datt, b["bias_d"], b["scale_d"], b["dbias_d"], b["dscale_d"], B, H, Cd, b["heads"],
+                                            b["window"], b["shift"])
                 self._wgrad(dqkv, b["x"], pfx + ".attn.qkv.weight")
                 K.colsum(dqkv[:, :Cd], gr[pfx + ".attn.q_bias"])
                 K.colsum(dqkv[:, 2 * Cd:], gr[pfx + ".attn.v_bias"])
                 dx = G.gemm(dqkv, b["lq"].wt, G.EPI_RESIDUAL, aux=dx1)
-                # parameter-only graph behind the attention tables
-                a = b["attn"]
-                tg = torch.autograd.grad([b["bias_t"], b["scale_t"]], [a.cpb_mlp[0].weight, a.cpb_mlp[0].bias, a.cpb_mlp[2].weight, a.logit_scale],
-                                         [dbias, dscale])
-                for name, g_ in zip((".attn.cpb_mlp.0.weight", ".attn.cpb_mlp.0.bias", ".attn.cpb_mlp.2.weight", ".attn.logit_scale"), tg):
-                    gr[pfx + name] += g_
+        self._tables_backward(sv)
         # patch embedding: x0 = norm(e), e = x_in W^T + b
         de = self._ln_bwd(dx, sv["e"], self._f32(m.patch_embed.norm.weight), None, 1, "patch_embed.norm.weight", "patch_embed.norm.bias")
         self._wgrad(de, sv["x_in"], "patch_embed.projection.0.weight", "patch_embed.projection.0.bias")

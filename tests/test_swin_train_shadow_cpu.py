@@ -89,12 +89,14 @@ class ShadowEngine(ST.SwinTrainEngine):
     def _attn_fwd(self, qkv, bias, scale, B, H, Cd, heads, window, shift):
         return self._attn(qkv.float(), bias, scale, B, H, Cd, heads, shift).to(BF)
 
-    def _attn_bwd(self, qkv, datt, bias, scale, B, H, Cd, heads, window, shift):
+    def _attn_bwd(self, qkv, datt, bias, scale, dbias, dscale, B, H, Cd, heads, window, shift):
         with torch.enable_grad():
             q = qkv.float().requires_grad_(True)
             b, s = bias.clone().requires_grad_(True), scale.clone().requires_grad_(True)
             self._attn(q, b, s, B, H, Cd, heads, shift).backward(datt.float())
-        return q.grad.to(BF), b.grad, s.grad
+        dbias.add_(b.grad)                       # the kernel accumulates into the group's preallocated slices
+        dscale.add_(s.grad)
+        return q.grad.to(BF), dbias, dscale
 
     def _gather(self, x, B, H, Cd):
         x = x.view(B, H, H, Cd)
