@@ -47,10 +47,6 @@ typedef unsigned long long p2;            // packed pair: token 0 in the low wor
 #ifndef K0V2_CTAS
 #define K0V2_CTAS 4
 #endif
-#ifndef K0V2_ASYNC
-#define K0V2_ASYNC 0
-#endif
-constexpr int STAGE_ROUNDS = 6;           // x2-down: 4 luma + 2 chroma rounds of 4 x 16 bytes per lane
 constexpr int WARPS = K0V2_WARPS;         // warps per CTA (independent: no block-level barrier)
 constexpr int CTAS_PER_SM = K0V2_CTAS;    // shared memory: CTAS x (WARPS x 11,440 + 1 KB) <= 228 KB
 constexpr int PITCH = 144;                // tile row pitch in bytes (16 pairs + 2 pad)
@@ -66,9 +62,6 @@ struct __align__(16) WarpSmem {
     rgbnm_plan plan;
     int info[24];                     // per block of the quad: source block index, child flags, zeroing op (pack_info)
     int pad_[8];
-#if K0V2_ASYNC
-    unsigned char stage[STAGE_ROUNDS * 2048];   // cp.async landing zone: [round][chunk 0..3][lane] x 16 bytes (a lane reads back its own chunks)
-#endif
 };
 static_assert(sizeof(WarpSmem) % 16 == 0, "warp slices must stay 16-byte aligned");
 static_assert(CTAS_PER_SM * (WARPS * sizeof(WarpSmem) + 1024) <= 228 * 1024, "the resident CTAs of an SM must fit");
@@ -201,7 +194,6 @@ struct LaneK {
     uint32_t prow;       // P3 row: T + bit4 * TILE_B + (lane & 15) * PITCH
     uint32_t qrow;       // table row of the lane's coefficient row: qt + i8 * QROW_B
     uint32_t info;       // info[0]
-    uint32_t stage;      // cp.async staging area (K0V2_ASYNC)
 };
 
 __device__ __forceinline__ void load_q(uint32_t qrow, float (&q)[8], float (&cq)[8]) {
@@ -218,49 +210,6 @@ __device__ __forceinline__ void load_q(uint32_t qrow, float (&q)[8], float (&cq)
 struct RowLoads {
     int4 l0, r0, l1, r1;
 };
-#if K0V2_ASYNC
-// cp.async variant: every load of a quad is issued up front into the warp's staging area (no registers held while in flight, up to
-// 12 KB per warp outstanding); a lane later reads back exactly the chunks it requested, so completion is the per-thread wait_group.
-__device__ __forceinline__ void cp16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ int4 lds_i4(uint32_t a) {
-    int4 v;
-    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void r_down2_issue(uint32_t info, int lane, const unsigned char* __restrict__ plane, int wbytes, int b0,
-                                              int tok_stride, uint32_t st) {
-    const uint32_t lc = ((lane >> 3) & 1) * wbytes + (lane & 7) * 16;
-    const uint32_t ia = info + 4 * (b0 + (lane >> 4));
-    const uint32_t o0 = (uint32_t(lds32(ia)) & 0xffffu) * 128u + lc, o1 = (uint32_t(lds32(ia + 4 * tok_stride)) & 0xffffu) * 128u + lc;
-    const uint32_t d = st + lane * 16;
-    cp16(d, plane + o0);
-    cp16(d + 512, plane + o0 + 128);
-    cp16(d + 1024, plane + o1);
-    cp16(d + 1536, plane + o1 + 128);
-    cp_commit();
-}
-__device__ __forceinline__ RowLoads r_fetch(uint32_t st, int lane) {
-    const uint32_t d = st + lane * 16;
-    RowLoads L;
-    L.l0 = lds_i4(d);
-    L.r0 = lds_i4(d + 512);
-    L.l1 = lds_i4(d + 1024);
-    L.r1 = lds_i4(d + 1536);
-    return L;
-}
-__device__ __forceinline__ void r_small_issue(uint32_t info, int lane, const unsigned char* __restrict__ plane, int b0, int tok_stride,
-                                              uint32_t st) {                       // two chunks at st, st + 512
-    const int inf0 = lds32(info + 4 * b0), inf1 = lds32(info + 4 * (b0 + tok_stride));
-    const uint32_t lc = (lane & 7) * 16;
-    cp16(st + lane * 16, plane + (uint32_t(inf0) & 0xffffu) * 128u + lc);
-    cp16(st + 512 + lane * 16, plane + (uint32_t(inf1) & 0xffffu) * 128u + lc);
-}
-#endif
 __device__ __forceinline__ RowLoads r_down2_load(uint32_t info, int lane, const unsigned char* __restrict__ plane, int wbytes, int b0,
                                                  int tok_stride) {
     const uint32_t lc = ((lane >> 3) & 1) * wbytes + (lane & 7) * 16;
@@ -497,44 +446,6 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
     const uint32_t info = K.info;
     const int b3 = (lane >> 3) & 1, b4 = lane >> 4;
     // ---- R, luma ----------------------------------------------------------------------------------------------------------------
-#if K0V2_ASYNC
-    if (mode == MODE_DOWN2) {
-        // every load of the quad is in flight from here on: rounds 0-3 luma (pair, block row) = (0,0) (0,1) (1,0) (1,1), 4-5 chroma
-        const int wbytes = wb * 128;
-        r_down2_issue(info, lane, y_img, wbytes, 0, 4, K.stage);
-        r_down2_issue(info, lane, y_img, wbytes, 2, 4, K.stage + 2048);
-        r_down2_issue(info, lane, y_img, wbytes, 12, 4, K.stage + 2 * 2048);
-        r_down2_issue(info, lane, y_img, wbytes, 14, 4, K.stage + 3 * 2048);
-        const unsigned char* plane = c_img + size_t(b4) * hc * wc * 128;
-        r_down2_issue(info, lane, plane, wc * 128, 8, 2, K.stage + 4 * 2048);
-        r_down2_issue(info, lane, plane, wc * 128, 20, 2, K.stage + 5 * 2048);
-        cp_wait<5>();
-        r_down2_compute(r_fetch(K.stage, lane), K.qrow, K.rst, clamp);
-        cp_wait<4>();
-        r_down2_compute(r_fetch(K.stage + 2048, lane), K.qrow, K.rst + 16 * PITCH, clamp);
-        cp_wait<3>();
-        r_down2_compute(r_fetch(K.stage + 2 * 2048, lane), K.qrow, K.rst + TILE_B, clamp);
-        cp_wait<2>();
-        r_down2_compute(r_fetch(K.stage + 3 * 2048, lane), K.qrow, K.rst + TILE_B + 16 * PITCH, clamp);
-    } else {
-        // group 0: luma (lane = (row i8, block row b3, block column b4): pair 0 at chunks 0 / 1, pair 1 at chunks 2 / 3); group 1: chroma
-        r_small_issue(info, lane, y_img, b3 * 2 + b4, 4, K.stage);
-        r_small_issue(info, lane, y_img, 12 + b3 * 2 + b4, 4, K.stage + 1024);
-        cp_commit();
-        r_small_issue(info, lane, c_img + size_t(b3) * hc * wc * 128, b4 * 12 + 8 + b3, 2, K.stage + 2048);
-        cp_commit();
-        cp_wait<1>();
-        const RowLoads L = r_fetch(K.stage, lane);
-        if (mode == MODE_UP2) {
-            r_small_compute<MODE_UP2>(L.l0, L.r0, info, b3 * 2 + b4, 4, K.qrow, K.rst, clamp);
-            r_small_compute<MODE_UP2>(L.l1, L.r1, info, 12 + b3 * 2 + b4, 4, K.qrow, K.rst + TILE_B, clamp);
-        } else {
-            r_small_compute<MODE_IDENT>(L.l0, L.r0, info, b3 * 2 + b4, 4, K.qrow, K.rst, clamp);
-            r_small_compute<MODE_IDENT>(L.l1, L.r1, info, 12 + b3 * 2 + b4, 4, K.qrow, K.rst + TILE_B, clamp);
-        }
-    }
-    __syncwarp();
-#else
     if (mode == MODE_DOWN2) {
         // rounds (pair, block row) = (0,0) (0,1) (1,0) (1,1); the loads of round r+2 are issued as round r is consumed
         const int wbytes = wb * 128;
@@ -553,7 +464,6 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
         r_small_compute<MODE_IDENT>(A.r0, A.r1, info, 12 + b3 * 2 + b4, 4, K.qrow, K.rst + TILE_B, clamp);
     }
     __syncwarp();
-#endif
 
     // ---- C: three rounds (k = 0, 1: luma block rows; k = 2: chroma, whose row pass runs once the luma tokens are stored) ----------
     // lane = (pair p = b4, tile column c16)
@@ -620,30 +530,17 @@ __device__ __forceinline__ void process_quad(WarpSmem& ws, const LaneK& K, int l
             // ---- R, chroma: tile of pair p, rows = source rows, 16 columns = [Cb 8 | Cr 8] ----------------------------------------
             if (mode == MODE_DOWN2) {
                 // lane bit 4 = component (the block-column `half` of r_down2_*); chroma block ids 8 + tok*2 + (comp-1), token stride 2
-#if K0V2_ASYNC
-                cp_wait<1>();
-                const RowLoads CA = r_fetch(K.stage + 4 * 2048, lane);
-                cp_wait<0>();
-                const RowLoads CB = r_fetch(K.stage + 5 * 2048, lane);
-#else
                 const unsigned char* plane = c_img + size_t(b4) * hc * wc * 128;
                 const RowLoads CA = r_down2_load(info, lane, plane, wc * 128, 8, 2);
                 const RowLoads CB = r_down2_load(info, lane, plane, wc * 128, 20, 2);
-#endif
                 const uint32_t qr = K.qrow + (1 + b4) * 8 * QROW_B;
                 r_down2_compute(CA, qr, K.rst, clamp);
                 r_down2_compute(CB, qr, K.rst + TILE_B, clamp);
             } else {
                 // lane = (row i8, component b3, pair b4)
-                int4 a0, a1;
-#if K0V2_ASYNC
-                cp_wait<0>();
-                a0 = lds_i4(K.stage + 2048 + lane * 16);
-                a1 = lds_i4(K.stage + 2048 + 512 + lane * 16);
-#else
                 const unsigned char* plane = c_img + size_t(b3) * hc * wc * 128;
+                int4 a0, a1;
                 r_small_load(info, lane, plane, b4 * 12 + 8 + b3, 2, a0, a1);
-#endif
                 const uint32_t qr = K.qrow + (1 + b3) * 8 * QROW_B;
                 if (mode == MODE_UP2) r_small_compute<MODE_UP2>(a0, a1, info, b4 * 12 + 8 + b3, 2, qr, K.rst_c, clamp);
                 else r_small_compute<MODE_IDENT>(a0, a1, info, b4 * 12 + 8 + b3, 2, qr, K.rst_c, clamp);
@@ -750,11 +647,6 @@ k0_vit2_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, 
         K.prow = base + b4 * TILE_B + (lane & 15) * PITCH;
         K.qrow = base + uint32_t(offsetof(WarpSmem, qt)) + i8 * QROW_B;
         K.info = base + uint32_t(offsetof(WarpSmem, info));
-#if K0V2_ASYNC
-        K.stage = base + uint32_t(offsetof(WarpSmem, stage));
-#else
-        K.stage = 0;
-#endif
     }
     const long long nq = (long long)n_images * QUADS_PER_IMAGE;
     const long long gw = (long long)blockIdx.x * WARPS + warp, tw = (long long)gridDim.x * WARPS;
@@ -790,9 +682,7 @@ k0_vit2_kernel(const int16_t* __restrict__ y, const int16_t* __restrict__ cbcr, 
             const unsigned char* c_img = reinterpret_cast<const unsigned char*>(cbcr + size_t(img) * 2 * hc * wc * 64);
             trace_quad(ws, lane, tr, tp, mode, wb, wc);
             __syncwarp();
-#if !K0V2_ASYNC
             luma_first_loads(K.info, lane, y_img, wb, mode, A);
-#endif
             const float* stats = stats_all + size_t(img) * RGBNM_MAX_OPS * 2;
             if (OUT_MODE != RGBNM_K0_OUT_INT16_PLANES && mode == MODE_DOWN2 && ws.plan.clamp_in == 0)
                 process_quad<OUT_MODE, MODE_DOWN2, true, NOSUB>(ws, K, lane, img, tr, tp, mode, y_img, c_img, tb, stats, out_, wb, hc, wc, A, sched, grabbed);
