@@ -44,8 +44,8 @@ struct HuffTable {
     int32_t mincode[18], maxcode[18], valptr[18];
     uint16_t look[512];  // (nbits << 8) | symbol, 0 = miss
     // AC fast path: FAST-bit window that holds a whole (run, size) code AND its magnitude bits:
-    // (value << 8) | (run << 4) | total bits; 0 = not applicable (long code, EOB/ZRL, or value does not fit)
-    static constexpr int FAST = 9;
+    // (value << 8) | (run << 4) | total bits; 0 = not applicable (long code, ZRL, or value does not fit); value 0 = EOB
+    static constexpr int FAST = 10;
     int16_t fast_ac[1 << FAST];
 
     // false: the code-length counts do not describe a prefix code (more than 2^l codes of length <= l): the canonical
@@ -78,6 +78,10 @@ struct HuffTable {
             const uint16_t e = look[i >> (FAST - 9)];
             if (!e) continue;
             const int len = e >> 8, rs = e & 0xff, run = rs >> 4, magbits = rs & 15;
+            if (rs == 0x00) {                                  // EOB: value 0, run 0 (no real symbol carries a zero value)
+                fast_ac[i] = int16_t(len);
+                continue;
+            }
             if (magbits == 0 || len + magbits > FAST) continue;
             int k = ((i << len) & ((1 << FAST) - 1)) >> (FAST - magbits);   // the magnitude bits that follow the code
             if (k < (1 << (magbits - 1))) k -= (1 << magbits) - 1;            // receive_extend
@@ -324,10 +328,171 @@ struct Decoder {
         return RGBNM_ERR_CORRUPT;
     }
 
+    // ---- fast scan path (no restart markers): the entropy-coded segment is un-stuffed once (FF 00 -> FF, stop at the first
+    // marker) into a zero-padded scratch buffer, after which the bit reader refills branch-free (no 0xFF test per byte) and the AC
+    // loop decodes two table symbols per refill.  Same outputs as decode_scan, which stays the path for DRI streams.
+    struct FastBits {
+        const uint8_t* p;
+        uint64_t acc = 0;
+        int n = 0;
+        inline void refill() {                       // afterwards n >= 56
+            uint64_t x;
+            std::memcpy(&x, p, 8);
+            acc |= __builtin_bswap64(x) >> n;
+            p += (63 - n) >> 3;
+            n |= 56;
+        }
+        inline uint32_t peek(int k) const { return uint32_t(acc >> (64 - k)); }
+        inline void skip(int k) {
+            acc <<= k;
+            n -= k;
+        }
+        inline int extend(int s) {                   // caller guarantees n >= s, s >= 1
+            const int v = int(peek(s));
+            skip(s);
+            return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+        }
+        inline int symbol(const HuffTable& t) {      // caller guarantees n >= 16
+            const uint16_t e = t.look[peek(9)];
+            if (e) {
+                skip(e >> 8);
+                return e & 0xff;
+            }
+            int code = int(peek(9)), l = 9;
+            uint64_t rest = acc << 9;
+            while (true) {
+                ++l;
+                code = (code << 1) | int(rest >> 63);
+                rest <<= 1;
+                if (l > 16) return -1;
+                if (code <= t.maxcode[l] && t.maxcode[l] >= 0) break;
+            }
+            skip(l);
+            return t.vals[t.valptr[l] + code - t.mincode[l]];
+        }
+    };
+
+    int decode_scan_fast(size_t pos, int16_t* const planes[3], int* clamp_live) {
+        static thread_local std::vector<uint8_t> buf;
+        constexpr size_t PAD = 512;                  // one block consumes < 256 bytes; the reader is re-anchored per block
+        const uint8_t* s = data + pos;
+        const uint8_t* const e = data + size;
+        buf.resize(size_t(e - s) + PAD);
+        uint8_t* w = buf.data();
+        while (s < e) {
+            const uint8_t* f = static_cast<const uint8_t*>(std::memchr(s, 0xFF, size_t(e - s)));
+            if (f == nullptr) f = e;
+            std::memcpy(w, s, size_t(f - s));
+            w += f - s;
+            s = f;
+            if (s >= e) break;
+            if (s + 1 < e && s[1] == 0x00) {         // stuffed zero
+                *w++ = 0xFF;
+                s += 2;
+            } else {
+                break;                               // marker (or a lone trailing FF): zeros from here on, as decode_scan feeds
+            }
+        }
+        std::memset(w, 0, PAD);
+        const uint8_t* const stream_end = w;
+
+        int16_t lim_lo[3][64], lim_hi[3][64];        // indexed by zig-zag position
+        int small[3];                                // |v| <= small[ci] can never leave [-1024, 1016] after dequantisation
+        for (int i = 0; i < ncomp; ++i) {
+            if (comp[i].tq > 3 || comp[i].td > 3 || comp[i].ta > 3 || !qt_present[comp[i].tq]) return RGBNM_ERR_CORRUPT;
+            if (!dc[comp[i].td].present || !ac[comp[i].ta].present) return RGBNM_ERR_CORRUPT;
+            int qmax = 1;
+            for (int k = 0; k < 64; ++k) {
+                const int qq = qt[comp[i].tq][kZigzag[k]] ? qt[comp[i].tq][kZigzag[k]] : 1;
+                lim_lo[i][k] = int16_t(-(1024 / qq));
+                lim_hi[i][k] = int16_t(1016 / qq);
+                qmax = std::max(qmax, qq);
+            }
+            small[i] = 1016 / qmax;
+            comp[i].pred = 0;
+        }
+        int bad = 0;
+        const int mcu_w = (ncomp == 1) ? comp[0].wb : (width + 8 * hmax - 1) / (8 * hmax);
+        const int mcu_h = (ncomp == 1) ? comp[0].hb : (height + 8 * vmax - 1) / (8 * vmax);
+        FastBits br;
+        br.p = buf.data();
+        int16_t scratch[64];
+        for (int my = 0; my < mcu_h; ++my) {
+            for (int mx = 0; mx < mcu_w; ++mx) {
+                for (int ci = 0; ci < ncomp; ++ci) {
+                    Component& c = comp[ci];
+                    const HuffTable& hd = dc[c.td];
+                    const HuffTable& ha = ac[c.ta];
+                    const int bh = (ncomp == 1) ? 1 : c.h, bv = (ncomp == 1) ? 1 : c.v;
+                    const int16_t* lo = lim_lo[ci];
+                    const int16_t* hi = lim_hi[ci];
+                    const unsigned sm = unsigned(small[ci]);
+                    for (int by = 0; by < bv; ++by) {
+                        for (int bx = 0; bx < bh; ++bx) {
+                            const int row = my * bv + by, col = mx * bh + bx;
+                            int16_t* blk = (row < c.hb && col < c.wb) ? planes[ci] + (size_t(row) * c.wb + col) * 64 : scratch;
+                            std::memset(blk, 0, 64 * sizeof(int16_t));
+                            if (br.p > stream_end) br.p = stream_end;          // past the data: keep reading the zero padding
+                            br.refill();
+                            const int sdc = br.symbol(hd);
+                            if (sdc < 0 || sdc > 11) return RGBNM_ERR_CORRUPT;
+                            if (sdc) c.pred += br.extend(sdc);                 // n >= 56 - 16 >= 11
+                            blk[0] = int16_t(c.pred);
+                            bad |= (c.pred < lo[0]) | (c.pred > hi[0]);
+                            int k = 1;
+                            while (k < 64) {
+                                br.refill();
+                                int fa = ha.fast_ac[br.peek(HuffTable::FAST)];
+                                if (fa) {
+                                    k += (fa >> 4) & 15;
+                                    br.skip(fa & 15);
+                                    int v = fa >> 8;
+                                    if (v == 0) break;                         // EOB
+                                    if (k > 63) return RGBNM_ERR_CORRUPT;
+                                    if (unsigned(v + int(sm)) > 2 * sm) bad |= (v < lo[k]) | (v > hi[k]);
+                                    blk[kZigzag[k++]] = int16_t(v);
+                                    if (k > 63) break;
+                                    // second symbol on the same refill (n >= 46)
+                                    fa = ha.fast_ac[br.peek(HuffTable::FAST)];
+                                    if (fa) {
+                                        k += (fa >> 4) & 15;
+                                        br.skip(fa & 15);
+                                        v = fa >> 8;
+                                        if (v == 0) break;
+                                        if (k > 63) return RGBNM_ERR_CORRUPT;
+                                        if (unsigned(v + int(sm)) > 2 * sm) bad |= (v < lo[k]) | (v > hi[k]);
+                                        blk[kZigzag[k++]] = int16_t(v);
+                                    }
+                                    continue;
+                                }
+                                const int rs = br.symbol(ha);                   // n >= 56
+                                if (rs < 0) return RGBNM_ERR_CORRUPT;
+                                const int r = rs >> 4, sz = rs & 15;
+                                if (sz == 0) {
+                                    if (r != 15) break;                        // EOB (long code)
+                                    k += 16;
+                                    continue;
+                                }
+                                k += r;
+                                if (k > 63) return RGBNM_ERR_CORRUPT;
+                                const int v = br.extend(sz);                   // n >= 56 - 16 >= 15
+                                bad |= (v < lo[k]) | (v > hi[k]);
+                                blk[kZigzag[k++]] = int16_t(v);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (clamp_live) *clamp_live = bad;
+        return RGBNM_OK;
+    }
+
     // planes[i]: component i output, wb*hb blocks of 64 int16 (natural order).
     // clamp_live (optional): set to 1 iff some dequantised coefficient leaves [-1024, 1016] (checked as each non-zero
     // coefficient is stored: x*q >= -1024 <=> x >= -floor(1024/q), x*q <= 1016 <=> x <= floor(1016/q))
     int decode_scan(size_t pos, int16_t* const planes[3], int* clamp_live = nullptr) {
+        if (restart_interval == 0) return decode_scan_fast(pos, planes, clamp_live);
         int16_t lim_lo[3][64], lim_hi[3][64];      // indexed by zig-zag position
         for (int i = 0; i < ncomp; ++i)
             if (comp[i].tq > 3 || comp[i].td > 3 || comp[i].ta > 3 || !qt_present[comp[i].tq]) return RGBNM_ERR_CORRUPT;
@@ -391,6 +556,7 @@ struct Decoder {
                                     if (k > 63) return RGBNM_ERR_CORRUPT;
                                     br.skip(fa & 15);
                                     const int v = fa >> 8;
+                                    if (v == 0) break;         // EOB
                                     bad |= (v < lo[k]) | (v > hi[k]);
                                     blk[kZigzag[k++]] = int16_t(v);
                                     continue;

@@ -171,3 +171,25 @@ def test_pil_file_reencodes_to_identical_scan_bytes(quality, subsampling, size):
     assert a == b2
     # and an independent decoder (libjpeg-turbo through PIL) reads identical pixels from both files
     assert np.array_equal(np.asarray(Image.open(io.BytesIO(again)).convert("RGB")), np.asarray(Image.open(io.BytesIO(buf)).convert("RGB")))
+
+
+@pytest.mark.parametrize("quality,subsampling,size", [(75, 2, (512, 512)), (100, 2, (200, 136)), (30, 0, (97, 61))])
+def test_restart_interval_streams_decode_to_the_same_coefficients(quality, subsampling, size):
+    """The decoder has two scan paths: streams without restart markers go through the un-stuffed, branch-free bit reader
+    (`decode_scan_fast`), DRI streams through the byte-wise one.  libjpeg writes the SAME coefficients with and without restart
+    markers (only the DC predictions are reset), so both paths must return identical planes, tables and clamp flags."""
+    rng = np.random.default_rng(quality + size[0])
+    w, h = size
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.stack([127 + 90 * np.sin(xx / 9.0 + c) * np.cos(yy / 13.0) + rng.normal(0, 18, (h, w)) for c in range(3)], -1)
+    im = Image.fromarray(np.clip(img, 0, 255).astype(np.uint8))
+    plain, dri = io.BytesIO(), io.BytesIO()
+    im.save(plain, "JPEG", quality=quality, subsampling=subsampling)
+    im.save(dri, "JPEG", quality=quality, subsampling=subsampling, restart_marker_rows=1)
+    assert b"\xff\xdd" in dri.getvalue() and b"\xff\xdd" not in plain.getvalue()
+    a = dm.read_coefficients_from_bytes(plain.getvalue())
+    b = dm.read_coefficients_from_bytes(dri.getvalue())
+    for ta, tb in zip(a, b):
+        assert (ta is None) == (tb is None)
+        if ta is not None:
+            assert torch.equal(ta, tb)
