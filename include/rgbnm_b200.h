@@ -67,6 +67,14 @@ int rgbnm_jpeg_decode_batch(const uint8_t* const* data, const size_t* sizes, int
                             int16_t* y, int16_t* cbcr, int16_t* quant, uint8_t* clamp_flags,
                             int32_t* status, int nthreads);
 
+/* Plan-first variant: last_block_row[i] (may be NULL = whole image) is the last LUMA block row image i's crop window
+ * needs (crop_i + crop_size - 1 of its plan, drawn before decoding).  The scan is decoded up to and including the MCU row
+ * that holds it and then abandoned; block rows below keep whatever the buffers held (the fused kernel reads the crop
+ * window only, custom_transforms.py:557-629), and the clamp flag covers the decoded part.  Same arguments otherwise. */
+int rgbnm_jpeg_decode_batch_rows(const uint8_t* const* data, const size_t* sizes, int n, int hb, int wb,
+                                 int16_t* y, int16_t* cbcr, int16_t* quant, uint8_t* clamp_flags,
+                                 int32_t* status, int nthreads, const int32_t* last_block_row);
+
 int rgbnm_jpeg_read_file(const char* path, uint8_t** out, size_t* size);
 void rgbnm_free(void* p);
 

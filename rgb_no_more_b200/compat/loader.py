@@ -118,22 +118,25 @@ class B200Loader:
         fd = self._feeder
         idx = self._indices()
         batches = [idx[i:i + self.batch_size] for i in range(0, len(idx), self.batch_size)]
-        queued: List[List[int]] = []
+        queued: List[tuple] = []
 
         def submit(b):
             ids = b + [b[-1]] * (self.batch_size - len(b))          # the ring has fixed-size slots: pad the last batch
-            fd.submit(list(self._io.map(self._read, ids)))
-            queued.append(b)
+            # plan first, decode second: one vectorised plan draw per batch (global torch CPU generator, seeded SEED + rank by
+            # dataset_selector); the decoder stops after the last block row a crop window needs
+            plans = self.tf.sample_plans_packed(self.batch_size, self.hb, self.wb)
+            last = plans["crop_i"].astype("int32") + plans["crop_size"].astype("int32") - 1
+            fd.submit(list(self._io.map(self._read, ids)), last_rows=last)
+            queued.append((b, plans))
         nxt = 0
         try:
             while nxt < len(batches) and len(queued) < self.prefetch:
                 submit(batches[nxt])
                 nxt += 1
             while queued:
-                b = queued.pop(0)
+                b, plans = queued.pop(0)
                 y, c, q, flags, slot = fd.get()
-                # one vectorised plan draw per batch (global torch CPU generator, seeded SEED + rank by dataset_selector)
-                plans = self.tf.sample_plans_packed(self.batch_size, self.hb, self.wb, clamp_in=flags)
+                plans["clamp_in"] = flags                            # known only after the decode (dequantised range check)
                 x = self.tf.run(y, c, q, plans, needs_stats=bool(plans["needs_stats"].any()))
                 fd.release(slot)
                 if nxt < len(batches):

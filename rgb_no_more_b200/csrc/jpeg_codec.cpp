@@ -211,6 +211,7 @@ struct Decoder {
     int width = 0, height = 0, ncomp = 0, precision = 8;
     bool progressive = false, have_sof = false;
     int hmax = 1, vmax = 1, restart_interval = 0;
+    int last_mcu_row = 0x7fffffff;       // plan-first decoding: MCU rows after this one are not needed (decode_batch_rows)
     uint16_t qt[4][64];
     bool qt_present[4] = {false, false, false, false};
     HuffTable dc[4], ac[4];
@@ -417,7 +418,7 @@ struct Decoder {
         FastBits br;
         br.p = buf.data();
         int16_t scratch[64];
-        for (int my = 0; my < mcu_h; ++my) {
+        for (int my = 0; my < mcu_h && my <= last_mcu_row; ++my) {
             for (int mx = 0; mx < mcu_w; ++mx) {
                 for (int ci = 0; ci < ncomp; ++ci) {
                     Component& c = comp[ci];
@@ -514,7 +515,7 @@ struct Decoder {
         int16_t scratch[64];
         int restarts_left = restart_interval;
         int next_rst = 0;
-        for (int my = 0; my < mcu_h; ++my) {
+        for (int my = 0; my < mcu_h && my <= last_mcu_row; ++my) {
             for (int mx = 0; mx < mcu_w; ++mx) {
                 if (restart_interval && restarts_left == 0) {
                     // align to the RSTn marker
@@ -748,9 +749,8 @@ int rgbnm_jpeg_info_from_memory(const uint8_t* data, size_t size, rgbnm_jpeg_inf
     return rc;
 }
 
-int rgbnm_jpeg_read_coefficients(const uint8_t* data, size_t size, int16_t* y, size_t y_capacity,
-                                 int16_t* cbcr, size_t c_capacity, int16_t* quant, int32_t* dims,
-                                 int32_t* clamp_flag) {
+static int read_coefficients_rows(const uint8_t* data, size_t size, int16_t* y, size_t y_capacity, int16_t* cbcr, size_t c_capacity,
+                                  int16_t* quant, int32_t* dims, int32_t* clamp_flag, int last_luma_block_row) {
     if (!data || !y || !quant) return RGBNM_ERR_ARG;
     Decoder d;
     d.data = data;
@@ -758,6 +758,7 @@ int rgbnm_jpeg_read_coefficients(const uint8_t* data, size_t size, int16_t* y, s
     size_t sos = 0;
     int rc = d.parse_headers(&sos);
     if (rc != RGBNM_OK) return rc;
+    if (last_luma_block_row >= 0) d.last_mcu_row = last_luma_block_row / (d.ncomp == 1 ? 1 : d.comp[0].v);
     const size_t ny = size_t(d.comp[0].hb) * d.comp[0].wb * 64;
     if (y_capacity < ny) return RGBNM_ERR_BUFFER;
     int16_t* planes[3] = {y, nullptr, nullptr};
@@ -784,8 +785,20 @@ int rgbnm_jpeg_read_coefficients(const uint8_t* data, size_t size, int16_t* y, s
     return RGBNM_OK;
 }
 
+int rgbnm_jpeg_read_coefficients(const uint8_t* data, size_t size, int16_t* y, size_t y_capacity,
+                                 int16_t* cbcr, size_t c_capacity, int16_t* quant, int32_t* dims,
+                                 int32_t* clamp_flag) {
+    return read_coefficients_rows(data, size, y, y_capacity, cbcr, c_capacity, quant, dims, clamp_flag, -1);
+}
+
 int rgbnm_jpeg_decode_batch(const uint8_t* const* data, const size_t* sizes, int n, int hb, int wb, int16_t* y,
                             int16_t* cbcr, int16_t* quant, uint8_t* clamp_flags, int32_t* status, int nthreads) {
+    return rgbnm_jpeg_decode_batch_rows(data, sizes, n, hb, wb, y, cbcr, quant, clamp_flags, status, nthreads, nullptr);
+}
+
+int rgbnm_jpeg_decode_batch_rows(const uint8_t* const* data, const size_t* sizes, int n, int hb, int wb, int16_t* y,
+                                 int16_t* cbcr, int16_t* quant, uint8_t* clamp_flags, int32_t* status, int nthreads,
+                                 const int32_t* last_block_row) {
     if (!data || !sizes || !y || !cbcr || !quant || n < 0 || hb <= 0 || wb <= 0 || (hb & 1) || (wb & 1))
         return RGBNM_ERR_ARG;
     const size_t ny = size_t(hb) * wb * 64, nc = size_t(hb / 2) * (wb / 2) * 64;
@@ -808,7 +821,8 @@ int rgbnm_jpeg_decode_batch(const uint8_t* const* data, const size_t* sizes, int
                 } else if (info.ncomp == 3 && (info.hb[1] != hb / 2 || info.wb[1] != wb / 2)) {
                     rc = RGBNM_ERR_UNSUPPORTED;  // not 4:2:0
                 } else {
-                    rc = rgbnm_jpeg_read_coefficients(data[i], sizes[i], yi, ny, ci, 2 * nc, qi, nullptr, &flag);
+                    rc = read_coefficients_rows(data[i], sizes[i], yi, ny, ci, 2 * nc, qi, nullptr, &flag,
+                                                last_block_row ? std::max(0, int(last_block_row[i])) : -1);
                     if (rc == RGBNM_OK && info.ncomp == 1) {
                         // grayscale: zero chroma, unit tables (datasets.py:291-293)
                         std::memset(ci, 0, 2 * nc * sizeof(int16_t));

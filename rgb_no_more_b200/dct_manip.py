@@ -62,10 +62,12 @@ def read_coefficients(path: str):
     return read_coefficients_from_bytes(buf)
 
 
-def decode_batch(jpegs: Sequence[bytes], hb: int = 64, wb: int = 64, nthreads: int = 0, pin: bool = False, out=None):
+def decode_batch(jpegs: Sequence[bytes], hb: int = 64, wb: int = 64, nthreads: int = 0, pin: bool = False, out=None, last_rows=None):
     """Multithreaded batch decode into the layout the fused kernel reads.
     Returns (y [n,hb,wb,64], cbcr [n,2,hb/2,wb/2,64], quant [n,3,64], clamp_flags uint8 [n]).
-    `out` = (y, cbcr, quant) of a previous call (e.g. one slot of a pinned staging ring) is written in place."""
+    `out` = (y, cbcr, quant) of a previous call (e.g. one slot of a pinned staging ring) is written in place.
+    `last_rows` (plan-first decoding): per image the last luma block row its crop window needs (crop_i + crop_size - 1); the scan
+    is abandoned after the MCU row that holds it and the block rows below keep the buffers' previous contents."""
     L = _lib.load()
     n = len(jpegs)
     pin = pin and torch.cuda.is_available()
@@ -82,8 +84,14 @@ def decode_batch(jpegs: Sequence[bytes], hb: int = 64, wb: int = 64, nthreads: i
     status = torch.zeros((n,), dtype=torch.int32)
     ptrs = (C.c_char_p * n)(*jpegs)
     sizes = (C.c_size_t * n)(*[len(j) for j in jpegs])
-    rc = L.rgbnm_jpeg_decode_batch(C.cast(ptrs, C.c_void_p), C.cast(sizes, C.c_void_p), n, hb, wb, y.data_ptr(),
-                                   c.data_ptr(), q.data_ptr(), flags.data_ptr(), status.data_ptr(), nthreads)
+    rows = None
+    if last_rows is not None:
+        rows = np.ascontiguousarray(np.asarray(last_rows, dtype=np.int32))
+        if rows.shape != (n,):
+            raise ValueError("rgbnm decode_batch: one last_rows entry per image")
+    rc = L.rgbnm_jpeg_decode_batch_rows(C.cast(ptrs, C.c_void_p), C.cast(sizes, C.c_void_p), n, hb, wb, y.data_ptr(),
+                                        c.data_ptr(), q.data_ptr(), flags.data_ptr(), status.data_ptr(), nthreads,
+                                        None if rows is None else rows.ctypes.data)
     if rc != 0:
         bad = int(torch.nonzero(status)[0]) if status.any() else -1
         raise RuntimeError(f"image {bad}: {L.rgbnm_strerror(rc).decode()}")

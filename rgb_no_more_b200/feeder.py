@@ -39,8 +39,9 @@ class JpegFeeder:
         self.next_slot = 0
         self.h2d_bytes = sum(t.numel() * 2 for t in self.host[0])
 
-    def submit(self, jpegs: Sequence[bytes]) -> None:
-        """Queue one batch of JPEG byte strings for decoding (returns immediately)."""
+    def submit(self, jpegs: Sequence[bytes], last_rows=None) -> None:
+        """Queue one batch of JPEG byte strings for decoding (returns immediately).  `last_rows`: plan-first decoding, see
+        dct_manip.decode_batch (the plans of the batch are drawn before it is submitted)."""
         if len(jpegs) != self.batch:
             raise ValueError("rgbnm: JpegFeeder batches have a fixed size")
         slot = self.next_slot
@@ -49,7 +50,7 @@ class JpegFeeder:
             raise RuntimeError("rgbnm: JpegFeeder ring is full; consume a batch before submitting another")
         # the previous H2D copy out of this pinned slot must be done before the decoder overwrites it
         self.copied[slot].synchronize()
-        fut = self.pool.submit(dm.decode_batch, list(jpegs), self.hb, self.wb, self.nthreads, False, self.host[slot])
+        fut = self.pool.submit(dm.decode_batch, list(jpegs), self.hb, self.wb, self.nthreads, False, self.host[slot], last_rows)
         self.pending.append((slot, fut))
 
     def get(self, stream: Optional[torch.cuda.Stream] = None):

@@ -41,6 +41,7 @@ SIGNATURES = {
     "rgbnm_jpeg_info_from_memory": (_i, [_vp, _sz, C.POINTER(JpegInfo)]),
     "rgbnm_jpeg_read_coefficients": (_i, [_vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp]),
     "rgbnm_jpeg_decode_batch": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i]),
+    "rgbnm_jpeg_decode_batch_rows": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "rgbnm_jpeg_read_file": (_i, [C.c_char_p, C.POINTER(_vp), C.POINTER(_sz)]),
     "rgbnm_free": (None, [_vp]),
     "rgbnm_jpeg_write_coefficients": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_sz)]),

@@ -193,3 +193,24 @@ def test_restart_interval_streams_decode_to_the_same_coefficients(quality, subsa
         assert (ta is None) == (tb is None)
         if ta is not None:
             assert torch.equal(ta, tb)
+
+
+def test_plan_first_decode_stops_after_the_last_needed_block_row():
+    """decode_batch(last_rows=...): the scan is abandoned after the MCU row holding the crop window's last luma block row;
+    everything up to there equals the full decode, the block rows below keep the staging buffer's previous contents."""
+    jpegs = synth.synth_jpeg_set(4)
+    full_y, full_c, full_q, full_f = dm.decode_batch(jpegs, 64, 64, nthreads=2)
+    last = [10, 63, 0, 31]
+    y = torch.full((4, 64, 64, 64), -7, dtype=torch.int16)
+    c = torch.full((4, 2, 32, 32, 64), -7, dtype=torch.int16)
+    q = torch.zeros((4, 3, 64), dtype=torch.int16)
+    y2, c2, q2, f2 = dm.decode_batch(jpegs, 64, 64, nthreads=2, out=(y, c, q), last_rows=last)
+    assert torch.equal(q2, full_q)
+    for i, r in enumerate(last):
+        mcu = r // 2                                   # 4:2:0: one MCU row = two luma block rows, one chroma block row
+        assert torch.equal(y2[i, :2 * mcu + 2], full_y[i, :2 * mcu + 2])
+        assert torch.equal(c2[i, :, :mcu + 1], full_c[i, :, :mcu + 1])
+        assert bool((y2[i, 2 * mcu + 2:] == -7).all()) and bool((c2[i, :, mcu + 1:] == -7).all())
+    assert int(f2[1]) == int(full_f[1])               # whole image decoded: same clamp flag
+    with pytest.raises(ValueError):
+        dm.decode_batch(jpegs, 64, 64, last_rows=[1, 2])
