@@ -270,6 +270,8 @@ def run_ours(args):
     if not args.no_cpu and stage is not None:
         from rgb_no_more_b200 import feeder as FD, synth
         n_threads = max(1, (os.cpu_count() or 1) // world)
+        if n_threads >= 8:
+            n_threads -= 1                            # leave a core to the thread that feeds the GPU
         jpegs = synth.synth_jpeg_set(min(B, 64))
         jpegs = (jpegs * (B // len(jpegs) + 1))[:B]
         fd = FD.JpegFeeder(dev, B, 64, 64, slots=3, nthreads=n_threads)
@@ -277,6 +279,7 @@ def run_ours(args):
         plan_host = [torch.empty((B, P.PLAN_DTYPE.itemsize), dtype=torch.uint8).pin_memory() for _ in range(3)]
         plan_dev = [torch.empty((B, P.PLAN_DTYPE.itemsize), dtype=torch.uint8, device=dev) for _ in range(3)]
         gen = torch.Generator().manual_seed(11997733 + rank)
+        plan_ev = [None, None, None]
 
         drawn = []
 
@@ -290,14 +293,17 @@ def run_ours(args):
             k = i % 3
             packed = drawn.pop(0)
             packed["clamp_in"] = flags
+            if plan_ev[k] is not None:
+                plan_ev[k].synchronize()              # the copy that last read this pinned buffer (3 steps ago) has completed
             plan_host[k].copy_(torch.from_numpy(packed.view(np.uint8).reshape(B, -1)))
             plan_dev[k].copy_(plan_host[k], non_blocking=True)
+            if plan_ev[k] is None:
+                plan_ev[k] = torch.cuda.Event()
+            plan_ev[k].record()
             x = tf.run(yj, cj, qj, None, plans_dev=plan_dev[k], out=out_buf)
             fd.release(slot)
             res = stage.step(x, labels_pool[i % N_POOL])
             result_host.copy_(res.reshape(-1)[:1].float(), non_blocking=True)
-            if i % 3 == 2:
-                torch.cuda.current_stream().synchronize()      # the pinned plan buffers are reused every 3 steps
 
         n_j = max(args.steps // 2, 5)
         ms_jpeg = timed_loop(step_jpeg, n_j, 3)
