@@ -116,3 +116,59 @@ def write_coefficients(width: int, height: int, y: torch.Tensor, cbcr: Optional[
     data = C.string_at(out, size.value)
     L.rgbnm_free(out)
     return data
+
+
+# ---- B1 "for completeness": coefficient <-> pixel conversions (dct_manip.cpp:315-375, 485-576) -----------------------------------
+# The reference implements both by a round trip through libjpeg's own compressor / decompressor; neither is on the training path
+# (their only callers, custom_transforms.ycbcr_to_rgb / rgb_to_dct at :1140-1196, are not referenced by any transform recipe).
+# Here the libjpeg half of the round trip is Pillow's bundled libjpeg(-turbo) -- the same library family, default settings
+# (ISLOW DCT, fancy up-sampling, 4:2:0) -- and the coefficient half is this repository's reader / writer.
+_ANNEX_K_LUMA = [16, 11, 10, 16, 24, 40, 51, 61, 12, 12, 14, 19, 26, 58, 60, 55, 14, 13, 16, 24, 40, 57, 69, 56, 14, 17, 22, 29, 51, 87, 80, 62,
+                 18, 22, 37, 56, 68, 109, 103, 77, 24, 35, 55, 64, 81, 104, 113, 92, 49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112,
+                 100, 103, 99]
+_ANNEX_K_CHROMA = [17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99, 24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99] + \
+                  [99] * 32
+
+
+def quality_tables(quality: int) -> torch.Tensor:
+    """jpeg_set_quality(quality, force_baseline=TRUE): the Annex K tables scaled libjpeg's way -> int16 (2, 8, 8), natural order."""
+    q = min(max(int(quality), 1), 100)
+    scale = 5000 // q if q < 50 else 200 - 2 * q
+    tabs = [[min(max((v * scale + 50) // 100, 1), 255) for v in base] for base in (_ANNEX_K_LUMA, _ANNEX_K_CHROMA)]
+    return torch.tensor(tabs, dtype=torch.int16).view(2, 8, 8)
+
+
+def decode_coeff(dimensions: torch.Tensor, quantization: torch.Tensor, Y_coefficients: torch.Tensor,
+                 CrCb_coefficients: Optional[torch.Tensor] = None, quality: int = -1) -> torch.Tensor:
+    """Quantised coefficients -> pixels, uint8 (C, H, W) (RGB, or one channel for grayscale): dct_manip.cpp:485-576.
+    `quality` > 0 replaces `quantization` by the standard tables of that quality, as the reference does."""
+    import io
+    from PIL import Image
+    h, w = int(dimensions[0][0]), int(dimensions[0][1])
+    qt = quality_tables(quality) if quality > 0 else quantization.to(torch.int16).reshape(-1, 8, 8)
+    y = Y_coefficients.to(torch.int16).reshape(-1, 64)
+    if CrCb_coefficients is None:
+        buf = write_coefficients(w, h, y, None, qt[:1].reshape(1, 64))
+    else:
+        q3 = torch.stack([qt[0], qt[1], qt[1]]).reshape(3, 64)         # set_quantization: table 0 = luma, table 1 = both chroma planes
+        buf = write_coefficients(w, h, y, CrCb_coefficients.to(torch.int16).reshape(-1, 64), q3, chroma=(2, 2))
+    im = Image.open(io.BytesIO(buf))
+    arr = np.asarray(im.convert("RGB") if CrCb_coefficients is not None else im.convert("L"))
+    t = torch.from_numpy(arr.copy())
+    return t.permute(2, 0, 1).contiguous() if t.dim() == 3 else t.unsqueeze(0)
+
+
+def quantize_at_quality(pixels: torch.Tensor, quality: int, baseline: bool = True):
+    """uint8 pixels (C, H, W) -> (dimensions, quantization, Y, CbCr | None) of the JPEG libjpeg writes at `quality` with its default
+    settings (4:2:0 for colour): dct_manip.cpp:315-375."""
+    import io
+    from PIL import Image
+    if pixels.dtype != torch.uint8 or pixels.dim() != 3 or pixels.shape[0] not in (1, 3):
+        raise RuntimeError("quantize_at_quality: uint8 pixels of shape (1 | 3, H, W) expected")
+    if not baseline:
+        raise RuntimeError("quantize_at_quality: only baseline tables (8-bit) are supported")
+    arr = pixels.permute(1, 2, 0).contiguous().numpy()
+    im = Image.fromarray(arr[..., 0], "L") if pixels.shape[0] == 1 else Image.fromarray(arr, "RGB")
+    out = io.BytesIO()
+    im.save(out, "JPEG", quality=int(quality), subsampling=2 if pixels.shape[0] == 3 else -1, optimize=False)
+    return read_coefficients_from_bytes(out.getvalue())

@@ -214,3 +214,26 @@ def test_plan_first_decode_stops_after_the_last_needed_block_row():
     assert int(f2[1]) == int(full_f[1])               # whole image decoded: same clamp flag
     with pytest.raises(ValueError):
         dm.decode_batch(jpegs, 64, 64, last_rows=[1, 2])
+
+
+def test_decode_coeff_and_quantize_at_quality_round_trip_through_libjpeg():
+    """B1 completeness (dct_manip.cpp:315-375, 485-576): quantize_at_quality = libjpeg's compressor + the coefficient reader;
+    decode_coeff = the coefficient writer + libjpeg's decompressor.  Pixels -> coefficients -> pixels must equal what libjpeg itself
+    decodes from the file it wrote, and the tables must be libjpeg's tables for that quality."""
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:96, 0:128]
+    img = np.stack([127 + 80 * np.sin(xx / 11.0 + c) * np.cos(yy / 7.0) + rng.normal(0, 10, (96, 128)) for c in range(3)], 0)
+    pix = torch.from_numpy(np.clip(img, 0, 255).astype(np.uint8))
+    for quality in (100, 60):
+        dims, quant, y, cbcr = dm.quantize_at_quality(pix, quality)
+        assert tuple(y.shape) == (1, 12, 16, 8, 8) and tuple(cbcr.shape) == (2, 6, 8, 8, 8) and dims[0].tolist() == [96, 128]
+        assert torch.equal(quant[:2], dm.quality_tables(quality)) and torch.equal(quant[1], quant[2])
+        rgb = dm.decode_coeff(dims, quant, y, cbcr)
+        buf = io.BytesIO()
+        Image.fromarray(pix.permute(1, 2, 0).numpy()).save(buf, "JPEG", quality=quality, subsampling=2)
+        ref = torch.from_numpy(np.asarray(Image.open(io.BytesIO(buf.getvalue())).convert("RGB")).copy()).permute(2, 0, 1)
+        assert rgb.dtype == torch.uint8 and torch.equal(rgb, ref)
+        assert torch.equal(dm.decode_coeff(dims, quant * 0 + 1, y, cbcr, quality=quality), ref)      # tables from `quality`
+        assert float((rgb.float() - pix.float()).abs().mean()) < 12.0       # lossy (per-channel noise vs 4:2:0), but the same picture
+    g = dm.quantize_at_quality(pix[:1], 90)
+    assert g[3] is None and tuple(dm.decode_coeff(g[0], g[1], g[2]).shape) == (1, 96, 128)
