@@ -16,7 +16,6 @@ Each function cites the reference file:line (relative to /root/reference) it fol
 from __future__ import annotations
 
 import math
-from typing import List, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -2,7 +2,6 @@
 import collections.abc
 from itertools import repeat
 
-import torch
 from torch import nn
 
 

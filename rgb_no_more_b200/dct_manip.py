@@ -13,7 +13,7 @@ a one-line shim module named `dct_manip` on sys.path -- see INTEGRATION.md.
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 import torch

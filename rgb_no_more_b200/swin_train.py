@@ -307,7 +307,6 @@ class SwinFlatEngine:
     ALIGN = 8          # elements: every parameter starts on a 32-byte boundary (vector reds of the wgrad epilogue)
 
     def __init__(self, model, device: torch.device):
-        import ctypes as C
         import numpy as np
         self.model, self.dev = model, torch.device(device)
         self.inner = SwinTrainEngine(model, self.dev)

@@ -22,7 +22,6 @@ output, plainvit.py:478), fp32 master weights.  There is no CPU fallback."""
 from __future__ import annotations
 
 import math
-import os
 from collections import OrderedDict
 from typing import Dict, List, Optional
 
@@ -211,7 +210,6 @@ class ViTEngine:
                     self.W1[r0:r0 + w.shape[0]].index_copy_(1, cols, w.data)
                     self.b1[r0:r0 + w.shape[0]].copy_(b.data)
         if self._wprep is None:
-            import ctypes as C
             import numpy as np
             lins = self._all_lins()
             arr = (_lib.WPrepDesc * len(lins))()

@@ -3,7 +3,6 @@ the reference's own transform classes run LIVE under fresh seeds -- a wider net 
 both data paths, and op lists that include every op built outside the default recipes: Invert, SolarizeAdd, FreqEnhance,
 Equalize, Solarize).  Both sides run in this process, so RandAugment_dct's hash-order-dependent list(set(...)) rebuild
 (custom_transforms.py:1115-1119) sees the same string-hash seed."""
-import numpy as np
 import pytest
 import torch
 

@@ -9,7 +9,6 @@ import os
 import subprocess
 import sys
 
-import numpy as np
 import pytest
 
 from tests.helpers import ROOT, load

@@ -1,7 +1,6 @@
 """GPU parity tests of the SwinV2 backward kernels (training; first CUDA versions) against torch
 autograd through the reference's formulas (oracle/swin_oracle.py), via the C-ABI.  Tolerance: bf16 outputs, fp32 arithmetic:
 <= 2e-2 of each gradient's range; fp32 parameter gradients (dgamma, dbeta, dbias, dscale) <= 1e-2 relative to their norm."""
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F

@@ -3,7 +3,6 @@
 Tolerances (bf16 activations and weights, fp32 accumulation / statistics -- the reference's `--amp` regime -- against
 the fp32 reference): single kernels <= 1e-2 of the output range (bf16 output rounding); whole model: logits within
 3e-2 of the logit range of the reference's own outputs (tests/golden/swin_model.npz) with the same argmax."""
-import ctypes as C
 
 import numpy as np
 import pytest

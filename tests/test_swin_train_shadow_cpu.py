@@ -3,7 +3,6 @@ gradient flows where, residual / post-norm / stochastic-depth bookkeeping, the p
 tables) checked against the reference's own loss and gradients (tests/golden/swin_train.npz).  The CUDA kernels cannot run
 here, so every kernel entry point of the engine is replaced by a few lines of torch with the same contract; the kernels
 themselves are tested one by one on the GPU (tests/test_swin_bwd_gpu.py, tests/test_swin_gpu.py)."""
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F

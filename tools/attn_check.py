@@ -3,7 +3,6 @@
 import math, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-import torch.nn.functional as F
 from rgb_no_more_b200 import attention as A
 
 dev = "cuda:0"

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """GPU diagnostic for the tcgen05 GEMM: every epilogue against torch, with error statistics printed
 (not only asserted) so that one gpurun call tells as much as possible.  Exits non-zero on failure."""
-import os, sys, time
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from rgb_no_more_b200 import gemm as G
