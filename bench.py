@@ -48,6 +48,24 @@ def k0_ncu_traffic(kind: str):
     return None, K0_NCU_FILES[kind] + " (missing)"
 
 
+def ncu_tensor_pipe():
+    """sm__pipe_tensor_cycles_active (% of peak sustained active) of the tcgen05 kernels, read from the committed `ncu --set full`
+    summaries (captured under the profiler, never timed there): {label: percent}."""
+    out = {}
+    for rel in ("profiles/r01_attn_final_ncu.txt", "profiles/r01_gemm_final_ncu.txt"):
+        label = None
+        try:
+            with open(os.path.join(ROOT, rel)) as f:
+                for ln in f:
+                    if ln.startswith("launch "):
+                        label = ln.split(":", 1)[1].strip()
+                    elif "sm__pipe_tensor_cycles_active" in ln and label is not None:
+                        out[label] = round(float(ln.split("=")[1].split()[0]), 1)
+        except OSError:
+            out[rel] = "missing"
+    return out
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -452,6 +470,9 @@ def run_ours(args):
         line["roofline_vit_step"] = {"bound": "tensor", "achieved": tf_s, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf_s / peak_tf,
                                      "note": "algorithmic GEMM + attention FLOPs of forward + backward over the whole ViT part of the "
                                              "step (LayerNorm, optimiser, bias sums included in the time, not in the FLOPs)"}
+    if stage is not None:
+        line["ncu_tensor_pipe_active_pct"] = {"source": "profiles/r01_attn_final_ncu.txt, profiles/r01_gemm_final_ncu.txt (ncu --set full; "
+                                              "the ViT kernels are unchanged since)", **ncu_tensor_pipe()}
     if world == 1 and not args.no_cpu:
         line["host_decode"] = host_decode_rate()
         line["cpu_baseline"] = cpu_baseline(args)
