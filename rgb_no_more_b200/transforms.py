@@ -124,6 +124,14 @@ class FusedDCT:
                 plans = P.pack_plans(plans, clamp_in, out_size=self.out_size)
             if len(plans) != B:
                 raise ValueError("rgbnm: one plan per image required")
+            # filter ops carry an index into THIS transform's filter bank (Sharpness / MidfreqAug): plans sampled with
+            # another FusedDCT would silently read other filters
+            codes, first = plans["ops"]["code"], plans["ops"]["p"][..., 0]
+            filt = (codes == P.OP_SHARPNESS) | (codes == P.OP_MIDFREQ)
+            used = np.arange(codes.shape[1])[None, :] < plans["n_ops"][:, None]
+            if bool((filt & used & (first >= self.bank._n)).any()):
+                raise ValueError("rgbnm: a plan refers to a filter this transform's bank does not hold "
+                                 "(plans must be sampled by the FusedDCT that runs them)")
             plans_dev = torch.from_numpy(plans.view(np.uint8).reshape(B, -1)).to(self.device, non_blocking=True)
         self._sync_tables()
         if out_mode is None:

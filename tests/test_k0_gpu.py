@@ -353,3 +353,31 @@ def test_train_plans_without_subblock_conversion():
     for b in range(B):
         ref = O.embed_input(O.to_range(py[b]).unsqueeze(0), O.to_range(pc[b]).unsqueeze(0), subblock=False).reshape(196, 384)
         assert torch.equal(out[b], ref), b
+
+
+def test_concurrent_launches_on_several_streams_do_not_share_a_queue():
+    """The quad queue of k0_vit2_kernel is a device counter pair taken round robin from a pool: launches that overlap on different
+    streams must not draw tickets from each other's counter (a shared counter would skip or repeat quads).  Four streams, several
+    launches each (large enough that most quads are dealt by ticket), every output compared with the serial result.  Each stream
+    has its own FusedDCT: plans index the filter bank of the transform that sampled them, and the statistics scratch is per instance."""
+    B = 96
+    torch.manual_seed(9)
+    cases, tfs = [], []
+    for s in range(4):
+        tf = TF.FusedDCT(DEV, "train", P.AUGLIST_VITS, 2, 9)
+        y, c, q = _random_batch(B, 300 + s, False)
+        pk = torch.from_numpy(P.pack_plans(tf.sample_plans(B), [False] * B).view(np.uint8).reshape(B, -1).copy()).to(DEV)
+        tfs.append(tf)
+        cases.append((y.to(DEV), c.to(DEV), q.to(DEV), pk))
+    serial = [tfs[i].run(y, c, q, None, plans_dev=pk, out_mode=TF.OUT_BF16).clone() for i, (y, c, q, pk) in enumerate(cases)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in cases]
+    outs = [[] for _ in cases]
+    for rep in range(6):
+        for i, (st, (y, c, q, pk)) in enumerate(zip(streams, cases)):
+            with torch.cuda.stream(st):
+                outs[i].append(tfs[i].run(y, c, q, None, plans_dev=pk, out_mode=TF.OUT_BF16))
+    torch.cuda.synchronize()
+    for i in range(len(cases)):
+        for o in outs[i]:
+            assert torch.equal(o, serial[i]), i
