@@ -230,7 +230,7 @@ class SwinTrainEngine:
         sv["x_last"] = x
         sv["gn"] = self._f32(m.norm.weight)
         xf = self._ln_fwd(x, (sv["gn"], self._f32(m.norm.bias)), None, None, 1, bf(B * Ltok, Cf))
-        pooled = xf.view(B, Ltok, Cf).float().mean(dim=1)                    # B x C work: torch (like the ViT head)
+        pooled = xf.view(B, Ltok, Cf).mean(dim=1, dtype=torch.float32)        # B x C work: torch (like the ViT head)
         sv["pooled"] = pooled
         self.saved = sv
         return F.linear(pooled, m.head.weight.detach().float(), m.head.bias.detach().float())

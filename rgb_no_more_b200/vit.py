@@ -314,7 +314,7 @@ class ViTEngine:
         bufs["x_last"] = x
         self._ln(x, self.lnh, bufs["hN"], bufs["meanH"], bufs["rstdH"])
         # classification head (plainvit.py:547-557): token mean -> Linear -> tanh -> Linear; B x E work, torch ops
-        pooled = bufs["hN"].view(B, TOKENS, self.E).float().mean(dim=1)
+        pooled = bufs["hN"].view(B, TOKENS, self.E).mean(dim=1, dtype=torch.float32)     # fp32 accumulation straight from bf16
         bufs["pooled"] = pooled
         z = torch.tanh(F.linear(pooled, self.head1[0].data, self.head1[1].data))
         bufs["z"] = z
@@ -429,7 +429,8 @@ class _ViTFunction(torch.autograd.Function):
 
 
 class ViT(nn.Module):
-    """Same constructor surface as the reference ViT (plainvit.py:563-577); DCT / ver=1 / sub-block only."""
+    """Same constructor surface as the reference ViT (plainvit.py:563-577); DCT pixel space, embed_type (`ver`) 1 or 2, with or
+    without sub-block conversion; `ver=3` raises."""
 
     def __init__(self, in_channels: int = 3, patch_size: int = 16, emb_size: int = 768, input_embed: int = -1,
                  depth: int = 12, n_classes: int = 1000, drop_p=0.1, pixel_space="RGB", ver=1, use_subblock=True,
