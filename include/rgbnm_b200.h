@@ -301,6 +301,11 @@ int rgbnm_layernorm_res_scaled_fwd(const void* x, const float* gamma, const floa
  * dy itself), dgamma / dbeta fp32 [emb] +=.  Statistics are recomputed from x. */
 int rgbnm_layernorm_res_bwd(const void* dy, const void* x, const float* gamma, const float* row_scale, int rows_per_scale,
                             void* dx, float* dgamma, float* dbeta, int rows, int emb, float eps, void* stream);
+/* The same with `dxsum` (emb floats, accumulated; may be NULL): column sums of the dx it writes = the bias gradient of the Linear
+ * whose output the LayerNorm takes (swinv2.py:302-306: fc2 / attn.proj), so no separate rgbnm_colsum_bf16 launch.  dxsum needs
+ * emb in {96, 192, 384, 768}. */
+int rgbnm_layernorm_res_bwd_ex(const void* dy, const void* x, const float* gamma, const float* row_scale, int rows_per_scale,
+                               void* dx, float* dgamma, float* dbeta, float* dxsum, int rows, int emb, float eps, void* stream);
 /* Backward of rgbnm_window_attention_fwd: dqkv bf16 [B*H*W][3*C] from dout bf16 [B*H*W][C] (P is recomputed from qkv);
  * dbias fp32 [heads][64][64] += d loss / d bias tile (the caller differentiates 16 * sigmoid(cpb_mlp(.))[index] through it),
  * dscale fp32 [heads] += d loss / d scale (scale = exp(min(logit_scale, log 100))). */

@@ -209,16 +209,18 @@ template <int G, int PPL>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_res_bwd_g_kernel(const unsigned* __restrict__ dy, const unsigned* __restrict__ x, const float* __restrict__ gamma,
                     const float* __restrict__ row_scale, int rows_per_scale, unsigned* __restrict__ dx, float* __restrict__ dgamma,
-                    float* __restrict__ dbeta, int rows, float eps) {
+                    float* __restrict__ dbeta, float* __restrict__ dxsum, int rows, float eps) {
     constexpr int RPW = 32 / G, PAIRS = G * PPL, E = 2 * PAIRS;
     __shared__ float red[LN_WARPS * RPW][E];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / G, j = lane % G;
     const float inv_e = 1.0f / float(E);
-    float2 gm[PPL], ag[PPL], ab[PPL];
+    // dxsum (optional): column sums of the dx written here = the bias gradient of the Linear whose output this LayerNorm takes
+    // (fc2 / proj of a block: no separate column-sum launch); summed from the bf16-rounded values, as the column-sum kernel would
+    float2 gm[PPL], ag[PPL], ab[PPL], ax[PPL];
 #pragma unroll
     for (int k = 0; k < PPL; ++k) {
         gm[k] = *reinterpret_cast<const float2*>(gamma + 2 * (k * G + j));
-        ag[k] = ab[k] = make_float2(0.0f, 0.0f);
+        ag[k] = ab[k] = ax[k] = make_float2(0.0f, 0.0f);
     }
     for (int base = (blockIdx.x * LN_WARPS + warp) * RPW; base < rows; base += gridDim.x * LN_WARPS * RPW) {
         const int row = base + grp;
@@ -258,20 +260,25 @@ ln_res_bwd_g_kernel(const unsigned* __restrict__ dy, const unsigned* __restrict_
         m2 = group_sum<G>(m2) * inv_e;
         if (live) {
 #pragma unroll
-            for (int k = 0; k < PPL; ++k)
-                dx[ro + k * G + j] = f2_to_bf2(rstd * (g[k].x - m1 - v[k].x * m2), rstd * (g[k].y - m1 - v[k].y * m2));
+            for (int k = 0; k < PPL; ++k) {
+                const unsigned w = f2_to_bf2(rstd * (g[k].x - m1 - v[k].x * m2), rstd * (g[k].y - m1 - v[k].y * m2));
+                dx[ro + k * G + j] = w;
+                const float2 r = bf2_to_f2(w);
+                ax[k].x += r.x;
+                ax[k].y += r.y;
+            }
         }
     }
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = 0; pass < (dxsum != nullptr ? 3 : 2); ++pass) {
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < PPL; ++k) {
-            const float2 a = pass == 0 ? ag[k] : ab[k];
+            const float2 a = pass == 0 ? ag[k] : (pass == 1 ? ab[k] : ax[k]);
             red[warp * RPW + grp][2 * (k * G + j)] = a.x;
             red[warp * RPW + grp][2 * (k * G + j) + 1] = a.y;
         }
         __syncthreads();
-        float* out = pass == 0 ? dgamma : dbeta;
+        float* out = pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum);
         for (int c = threadIdx.x; c < E; c += LN_WARPS * 32) {
             float t = 0.0f;
 #pragma unroll
@@ -797,8 +804,15 @@ extern "C" int rgbnm_layernorm_res_scaled_fwd(const void* x, const float* gamma,
 
 extern "C" int rgbnm_layernorm_res_bwd(const void* dy, const void* x, const float* gamma, const float* row_scale, int rows_per_scale,
                                        void* dx, float* dgamma, float* dbeta, int rows, int emb, float eps, void* stream) {
+    return rgbnm_layernorm_res_bwd_ex(dy, x, gamma, row_scale, rows_per_scale, dx, dgamma, dbeta, nullptr, rows, emb, eps, stream);
+}
+
+extern "C" int rgbnm_layernorm_res_bwd_ex(const void* dy, const void* x, const float* gamma, const float* row_scale, int rows_per_scale,
+                                          void* dx, float* dgamma, float* dbeta, float* dxsum, int rows, int emb, float eps,
+                                          void* stream) {
     using namespace swinb;
     if (!dy || !x || !gamma || !dx || !dgamma || !dbeta || rows < 0 || emb <= 0 || (emb & 1) || emb > 768) return RGBNM_ERR_ARG;
+    if (dxsum != nullptr && emb != 96 && emb != 192 && emb != 384 && emb != 768) return RGBNM_ERR_UNSUPPORTED;
     if (row_scale != nullptr && rows_per_scale <= 0) return RGBNM_ERR_ARG;
     if (rows == 0) return RGBNM_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -807,7 +821,7 @@ extern "C" int rgbnm_layernorm_res_bwd(const void* dy, const void* x, const floa
 #define SWINB_LN_BWD_G(GG, PP)                                                                                                     \
     ln_res_bwd_g_kernel<GG, PP><<<grid, LN_WARPS * 32, 0, st>>>(static_cast<const unsigned*>(dy), static_cast<const unsigned*>(x), \
                                                                  gamma, row_scale, rows_per_scale, static_cast<unsigned*>(dx),     \
-                                                                 dgamma, dbeta, rows, eps)
+                                                                 dgamma, dbeta, dxsum, rows, eps)
     if (emb == 96 || emb == 192 || emb == 384 || emb == 768) {
         if (emb == 96) SWINB_LN_BWD_G(8, 6);
         else if (emb == 192) SWINB_LN_BWD_G(16, 6);

@@ -68,6 +68,7 @@ SIGNATURES = {
     "rgbnm_token_mean_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "rgbnm_layernorm_res_scaled_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, C.c_float, _vp]),
     "rgbnm_layernorm_res_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, C.c_float, _vp]),
+    "rgbnm_layernorm_res_bwd_ex": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, C.c_float, _vp]),
     "rgbnm_window_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rgbnm_patch_merge_scatter": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rgbnm_adamw_step": (_i, [_vp, _vp, _vp, _vp, C.c_longlong, C.c_longlong, _vp, _vp, _vp]),

@@ -74,12 +74,14 @@ class SwinTrainEngine:
                                                          y.data_ptr(), rows, emb, 1e-5, _lib.stream_ptr()), "rgbnm_layernorm_res_scaled_fwd")
         return y
 
-    def _ln_bwd(self, dy, x, gamma, scale, rows_per_scale, gname, bname):
+    def _ln_bwd(self, dy, x, gamma, scale, rows_per_scale, gname, bname, dxsum_name=None):
+        """dxsum_name: bias of the Linear whose output `x` is -- its gradient (column sums of dx) is accumulated by the same kernel."""
         rows, emb = x.shape
         dx = torch.empty_like(x)
-        _lib.check(self.L.rgbnm_layernorm_res_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), None if scale is None else scale.data_ptr(),
-                                                  rows_per_scale, dx.data_ptr(), self.grads[gname].data_ptr(), self.grads[bname].data_ptr(),
-                                                  rows, emb, 1e-5, _lib.stream_ptr()), "rgbnm_layernorm_res_bwd")
+        _lib.check(self.L.rgbnm_layernorm_res_bwd_ex(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), None if scale is None else scale.data_ptr(),
+                                                     rows_per_scale, dx.data_ptr(), self.grads[gname].data_ptr(), self.grads[bname].data_ptr(),
+                                                     None if dxsum_name is None else self.grads[dxsum_name].data_ptr(),
+                                                     rows, emb, 1e-5, _lib.stream_ptr()), "rgbnm_layernorm_res_bwd_ex")
         return dx
 
     def _attn_fwd(self, qkv, bias, scale, B, H, Cd, heads, window, shift):
@@ -264,14 +266,14 @@ class SwinTrainEngine:
             for b in reversed(st["blocks"]):
                 pfx = b["pfx"]
                 # x2 = x1 + s2 * norm2(m)
-                dm = self._ln_bwd(dx, b["m"], b["g2"], b["s2"], H * H, pfx + ".norm2.weight", pfx + ".norm2.bias")
-                self._wgrad(dm, b["f"], pfx + ".mlp.fc2.weight", pfx + ".mlp.fc2.bias")
+                dm = self._ln_bwd(dx, b["m"], b["g2"], b["s2"], H * H, pfx + ".norm2.weight", pfx + ".norm2.bias", pfx + ".mlp.fc2.bias")
+                self._wgrad(dm, b["f"], pfx + ".mlp.fc2.weight")
                 du = G.gemm(dm, b["l2"].wt, G.EPI_DGELU, aux=b["u"])                                   # (dm W2) * gelu'(u)
                 self._wgrad(du, b["x1"], pfx + ".mlp.fc1.weight", pfx + ".mlp.fc1.bias")
                 dx1 = G.gemm(du, b["l1"].wt, G.EPI_RESIDUAL, aux=dx)                                   # + residual path
                 # x1 = x + s1 * norm1(p)
-                dp = self._ln_bwd(dx1, b["p"], b["g1"], b["s1"], H * H, pfx + ".norm1.weight", pfx + ".norm1.bias")
-                self._wgrad(dp, b["att"], pfx + ".attn.proj.weight", pfx + ".attn.proj.bias")
+                dp = self._ln_bwd(dx1, b["p"], b["g1"], b["s1"], H * H, pfx + ".norm1.weight", pfx + ".norm1.bias", pfx + ".attn.proj.bias")
+                self._wgrad(dp, b["att"], pfx + ".attn.proj.weight")
                 datt = G.gemm(dp, b["lp"].wt, G.EPI_STORE)
                 dqkv, _, _ = self._attn_bwd(b["qkv"], datt, b["bias_d"], b["scale_d"], b["dbias_d"], b["dscale_d"], B, H, Cd, b["heads"],
                                             b["window"], b["shift"])
@@ -281,8 +283,9 @@ class SwinTrainEngine:
                 dx = G.gemm(dqkv, b["lq"].wt, G.EPI_RESIDUAL, aux=dx1)
         self._tables_backward(sv)
         # patch embedding: x0 = norm(e), e = x_in W^T + b
-        de = self._ln_bwd(dx, sv["e"], self._f32(m.patch_embed.norm.weight), None, 1, "patch_embed.norm.weight", "patch_embed.norm.bias")
-        self._wgrad(de, sv["x_in"], "patch_embed.projection.0.weight", "patch_embed.projection.0.bias")
+        de = self._ln_bwd(dx, sv["e"], self._f32(m.patch_embed.norm.weight), None, 1, "patch_embed.norm.weight", "patch_embed.norm.bias",
+                          "patch_embed.projection.0.bias")
+        self._wgrad(de, sv["x_in"], "patch_embed.projection.0.weight")
         self.saved = None
         return gr
 

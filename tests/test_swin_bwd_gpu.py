@@ -50,6 +50,14 @@ def test_layernorm_res_scaled_fwd_bwd(emb, scaled):
                                         dx.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, emb, 1e-5, L.stream_ptr()))
     assert _rel(dx.float().cpu(), xr.grad) < 2e-2
     assert _rel(dg.cpu(), gr.grad) < 1e-2 and _rel(db.cpu(), br.grad) < 1e-2
+    # the _ex entry also accumulates the column sums of the dx it writes (bias gradient of the Linear in front of the LayerNorm)
+    dx2 = torch.empty_like(xd)
+    dg2, db2, dxs = torch.zeros(emb, device=DEV), torch.zeros(emb, device=DEV), torch.ones(emb, device=DEV)
+    L.check(lib.rgbnm_layernorm_res_bwd_ex(dyd.data_ptr(), xd.data_ptr(), gd.data_ptr(), None if scd is None else scd.data_ptr(), rpi,
+                                           dx2.data_ptr(), dg2.data_ptr(), db2.data_ptr(), dxs.data_ptr(), rows, emb, 1e-5, L.stream_ptr()))
+    assert torch.equal(dx2, dx)
+    want = 1.0 + dx.float().sum(0)                                     # accumulated on top of what the buffer held
+    assert float((dxs - want).abs().max()) < 1e-3 * max(1.0, float(want.abs().max()))
 
 
 @pytest.mark.parametrize("H,heads,shift", [(16, 3, 0), (16, 3, 4), (8, 6, 0), (32, 3, 4)])

@@ -54,7 +54,7 @@ class ShadowEngine(ST.SwinTrainEngine):
         y.copy_(o.to(BF))
         return y
 
-    def _ln_bwd(self, dy, x, gamma, scale, rows_per_scale, gname, bname):
+    def _ln_bwd(self, dy, x, gamma, scale, rows_per_scale, gname, bname, dxsum_name=None):
         with torch.enable_grad():               # autograd runs Function.backward with grad mode off
             xr = x.float().requires_grad_(True)
             g = gamma.clone().requires_grad_(True)
@@ -65,7 +65,10 @@ class ShadowEngine(ST.SwinTrainEngine):
             o.backward(dy.float())
         self.grads[gname] += g.grad
         self.grads[bname] += b.grad
-        return xr.grad.to(BF)
+        dx = xr.grad.to(BF)
+        if dxsum_name is not None:                  # the kernel also accumulates the column sums of the dx it writes
+            self.grads[dxsum_name] += dx.float().sum(0)
+        return dx
 
     @staticmethod
     def _attn(qkv, bias, scale, B, H, Cd, heads, shift):
