@@ -227,6 +227,11 @@ int rgbnm_layernorm_fwd(const void* x, const float* gamma, const float* beta, vo
  * saving a separate pass over dx) */
 int rgbnm_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                         const void* dres, void* dx, float* dgamma, float* dbeta, float* dxsum, int rows, int emb, void* stream);
+/* The same with broadcast upstream gradients: dy holds rows / rows_per_dy_row rows and dy row r / rows_per_dy_row serves row r
+ * (the token mean of the classification head, plainvit.py:551: every token of an image receives d(pooled) / tokens). */
+int rgbnm_layernorm_bwd_ex(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                           const void* dres, void* dx, float* dgamma, float* dbeta, float* dxsum, int rows, int emb,
+                           int rows_per_dy_row, void* stream);
 /* RandomMixup_DCT on the bf16 embed input (utils/cls_transforms.py:135-182): out[b] = lam[0] * x[b] + lam[1] * x[(b-1) mod batch];
  * lam = 2 device floats; per_image = elements per image (multiple of 8); out != x. */
 int rgbnm_mixup_bf16(const void* x, void* out, const float* lam, int batch, long long per_image, void* stream);

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(const unsigned* __restrict__ dy, const unsigned* __restrict__ x, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, const float* __restrict__ gamma, const unsigned* __restrict__ dres,
               unsigned* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum,
-              int rows) {
+              int rows, int dy_div) {
     constexpr int E = PPL * 64;
     __shared__ float red[LN_WARPS][E + 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -111,9 +111,10 @@ ln_bwd_kernel(const unsigned* __restrict__ dy, const unsigned* __restrict__ x, c
     float n_mean = 0.0f, n_rstd = 0.0f;
     auto issue = [&](int r) {
         const size_t o = size_t(r) * (E / 2);
+        const size_t od = size_t(r / dy_div) * (E / 2);          // dy_div > 1: one dy row shared by dy_div consecutive rows (token mean)
 #pragma unroll
         for (int k = 0; k < PPL; ++k) {
-            n_dy[k] = __ldg(dy + o + k * 32 + lane);
+            n_dy[k] = __ldg(dy + od + k * 32 + lane);
             n_x[k] = __ldg(x + o + k * 32 + lane);
             n_dr[k] = dres != nullptr ? __ldg(dres + o + k * 32 + lane) : 0u;
         }
@@ -458,8 +459,15 @@ int rgbnm_layernorm_fwd(const void* x, const float* gamma, const float* beta, vo
 
 int rgbnm_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                         const void* dres, void* dx, float* dgamma, float* dbeta, float* dxsum, int rows, int emb, void* stream) {
+    return rgbnm_layernorm_bwd_ex(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, dxsum, rows, emb, 1, stream);
+}
+
+int rgbnm_layernorm_bwd_ex(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                           const void* dres, void* dx, float* dgamma, float* dbeta, float* dxsum, int rows, int emb,
+                           int rows_per_dy_row, void* stream) {
     using namespace vitk;
-    if (!dy || !x || !mean || !rstd || !gamma || !dx || !dgamma || !dbeta || rows < 0) return RGBNM_ERR_ARG;
+    if (!dy || !x || !mean || !rstd || !gamma || !dx || !dgamma || !dbeta || rows < 0 || rows_per_dy_row < 1) return RGBNM_ERR_ARG;
+    const int dy_div = rows_per_dy_row;
     if (rows == 0) return RGBNM_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, sms() * 4);
@@ -467,9 +475,9 @@ int rgbnm_layernorm_bwd(const void* dy, const void* x, const float* mean, const 
     const unsigned* b = static_cast<const unsigned*>(x);
     const unsigned* r = static_cast<const unsigned*>(dres);
     unsigned* o = static_cast<unsigned*>(dx);
-    if (emb == 192) ln_bwd_kernel<3><<<grid, LN_WARPS * 32, 0, st>>>(a, b, mean, rstd, gamma, r, o, dgamma, dbeta, dxsum, rows);
-    else if (emb == 384) ln_bwd_kernel<6><<<grid, LN_WARPS * 32, 0, st>>>(a, b, mean, rstd, gamma, r, o, dgamma, dbeta, dxsum, rows);
-    else if (emb == 768) ln_bwd_kernel<12><<<grid, LN_WARPS * 32, 0, st>>>(a, b, mean, rstd, gamma, r, o, dgamma, dbeta, dxsum, rows);
+    if (emb == 192) ln_bwd_kernel<3><<<grid, LN_WARPS * 32, 0, st>>>(a, b, mean, rstd, gamma, r, o, dgamma, dbeta, dxsum, rows, dy_div);
+    else if (emb == 384) ln_bwd_kernel<6><<<grid, LN_WARPS * 32, 0, st>>>(a, b, mean, rstd, gamma, r, o, dgamma, dbeta, dxsum, rows, dy_div);
+    else if (emb == 768) ln_bwd_kernel<12><<<grid, LN_WARPS * 32, 0, st>>>(a, b, mean, rstd, gamma, r, o, dgamma, dbeta, dxsum, rows, dy_div);
     else return RGBNM_ERR_UNSUPPORTED;
     RGBNM_CUDA_CHECK(cudaGetLastError());
     return RGBNM_OK;

@@ -55,6 +55,7 @@ SIGNATURES = {
     "rgbnm_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.c_float, _vp]),
     "rgbnm_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.c_float, _vp]),
     "rgbnm_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "rgbnm_layernorm_bwd_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "rgbnm_mixup_bf16": (_i, [_vp, _vp, _vp, _i, C.c_longlong, _vp]),
     "rgbnm_colsum_bf16": (_i, [_vp, C.c_longlong, _i, _i, _vp, _i, _i, _vp]),
     "rgbnm_weight_prep": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),

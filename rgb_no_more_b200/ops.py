@@ -23,13 +23,16 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, y: t
 
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor,
                   dres: Optional[torch.Tensor], dx: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor,
-                  dxsum: Optional[torch.Tensor] = None) -> None:
-    """dxsum (fp32 [emb], optional) += column sums of dx: the bias gradient of the Linear feeding this residual stream."""
+                  dxsum: Optional[torch.Tensor] = None, rows_per_dy_row: int = 1) -> None:
+    """dxsum (fp32 [emb], optional) += column sums of dx: the bias gradient of the Linear feeding this residual stream.
+    rows_per_dy_row > 1: `dy` has rows / rows_per_dy_row rows, each shared by that many consecutive rows of x."""
     rows, emb = x.shape
-    _lib.check(_L().rgbnm_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
-                                        None if dres is None else dres.data_ptr(), dx.data_ptr(), dgamma.data_ptr(),
-                                        dbeta.data_ptr(), None if dxsum is None else dxsum.data_ptr(), rows, emb,
-                                        _lib.stream_ptr()), "rgbnm_layernorm_bwd")
+    if dy.shape[0] * rows_per_dy_row != rows or not dy.is_contiguous():
+        raise ValueError("rgbnm layernorm_bwd: dy must hold rows / rows_per_dy_row contiguous rows")
+    _lib.check(_L().rgbnm_layernorm_bwd_ex(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                           None if dres is None else dres.data_ptr(), dx.data_ptr(), dgamma.data_ptr(),
+                                           dbeta.data_ptr(), None if dxsum is None else dxsum.data_ptr(), rows, emb,
+                                           rows_per_dy_row, _lib.stream_ptr()), "rgbnm_layernorm_bwd")
 
 
 def mixup(x: torch.Tensor, out: torch.Tensor, lam: torch.Tensor) -> None:

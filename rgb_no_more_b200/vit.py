@@ -362,12 +362,12 @@ class ViTEngine:
         self.grad_of(self.head1[1]).add_(dz.sum(0))
         dpooled = dz.mm(w1) * (1.0 / TOKENS)
         dA, dB, dC = bufs["dA"], bufs["dB"], bufs["dC"]
-        dA.view(B, TOKENS, E).copy_(dpooled.to(torch.bfloat16).unsqueeze(1).expand(B, TOKENS, E))
         # every LayerNorm backward below also accumulates the column sums of the dx it writes: that is the bias gradient of
-        # the Linear whose output (+ residual) this dx is the gradient of (fc2 of the layer, proj of the layer, the embed)
-        K.layernorm_bwd(dA, bufs["x_last"], bufs["meanH"], bufs["rstdH"], self.lnh[0].data, None, dB,
+        # the Linear whose output (+ residual) this dx is the gradient of (fc2 of the layer, proj of the layer, the embed).
+        # The head's LayerNorm takes d(pooled) / tokens for every token of an image: one dy row per image, broadcast by the kernel.
+        K.layernorm_bwd(dpooled.to(torch.bfloat16), bufs["x_last"], bufs["meanH"], bufs["rstdH"], self.lnh[0].data, None, dB,
                         self.grad_of(self.lnh[0]), self.grad_of(self.lnh[1]),
-                        dxsum=self.grad_of(self.layers[-1]["fc2"].bias))
+                        dxsum=self.grad_of(self.layers[-1]["fc2"].bias), rows_per_dy_row=TOKENS)
         self.launches += 1
         dx, spare1, spare2 = dB, dA, dC
         for l in reversed(range(self.depth)):

@@ -97,6 +97,16 @@ def test_layernorm_fwd_bwd(E):
     assert _rel(dx, xr.grad + dres.float()) < 1e-2
     assert _rel(dg, gr.grad) < 1e-4 and _rel(db, br.grad) < 1e-4
     assert _rel(dsum, dx.float().sum(0)) < 1e-5            # fused bias gradient = column sums of the stored dx
+    # broadcast upstream gradient (the head's token mean): one dy row per 8 consecutive rows == the materialised expansion
+    dyb = _bf(rows // 8, E)
+    dx_b, dx_e = torch.empty_like(x), torch.empty_like(x)
+    dgb, dbb, dge, dbe = (torch.zeros(E, device=DEV) for _ in range(4))
+    K.layernorm_bwd(dyb, x, mean, rstd, g, None, dx_b, dgb, dbb, rows_per_dy_row=8)
+    K.layernorm_bwd(dyb.repeat_interleave(8, dim=0).contiguous(), x, mean, rstd, g, None, dx_e, dge, dbe)
+    assert torch.equal(dx_b, dx_e)
+    assert _rel(dgb, dge) < 1e-5 and _rel(dbb, dbe) < 1e-5        # per-CTA partial sums meet in atomics: order varies
+    with pytest.raises(ValueError):
+        K.layernorm_bwd(dyb, x, mean, rstd, g, None, dx_b, dgb, dbb, rows_per_dy_row=4)
 
 
 def test_mixup_kernel():
