@@ -106,3 +106,17 @@ def stream_ptr():
     """Raw cudaStream_t of torch's current stream."""
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def no_autocast(fn):
+    """The engines compute in their own precision (bf16 operands, fp32 accumulation and statistics): the torch ops inside them
+    (heads, attention tables, losses) must not be re-cast by a caller's `torch.autocast` region (the reference enables AMP for
+    vitb / swinv2, utils/configs.py:110, 137)."""
+    import functools
+    import torch
+
+    @functools.wraps(fn)
+    def wrapped(*a, **kw):
+        with torch.autocast(device_type="cuda", enabled=False):
+            return fn(*a, **kw)
+    return wrapped

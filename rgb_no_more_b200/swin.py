@@ -203,6 +203,7 @@ class SwinEngine:
         self.launches += 1
 
     @torch.no_grad()
+    @_lib.no_autocast
     def forward(self, x_in: torch.Tensor, collect: Optional[list] = None) -> torch.Tensor:
         """x_in: (B, 4096, 24) bf16 operand of the patch projection -> (B, n_classes) fp32 logits."""
         if x_in.dtype != torch.bfloat16:

@@ -173,6 +173,7 @@ class SwinTrainEngine:
             torch._foreach_add_([gr[p + ".logit_scale"] for p in names], [g_.reshape(heads, 1, 1) for g_ in dls.unbind(0)])
 
     # ---------------------------------------------------------------------------------------------
+    @_lib.no_autocast
     def forward(self, x_in: torch.Tensor) -> torch.Tensor:
         """x_in (B, 4096, 24) -> fp32 logits; keeps what the backward needs in self.saved."""
         m, dev = self.model, self.device
@@ -238,6 +239,7 @@ class SwinTrainEngine:
         return F.linear(pooled, m.head.weight.detach().float(), m.head.bias.detach().float())
 
     # ---------------------------------------------------------------------------------------------
+    @_lib.no_autocast
     def backward(self, dlogits: torch.Tensor) -> Dict[str, torch.Tensor]:
         m, dev, sv = self.model, self.device, self.saved
         B = sv["B"]

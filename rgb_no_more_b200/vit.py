@@ -279,6 +279,7 @@ class ViTEngine:
         self.launches += 1
         return G.gemm(*a, **kw)
 
+    @_lib.no_autocast
     def forward(self, x_in: torch.Tensor, save: bool = True) -> torch.Tensor:
         """x_in: (B, 196, 384) bf16 operand of the patch projection -> (B, n_classes) fp32 logits."""
         if x_in.dtype != torch.bfloat16:
@@ -344,6 +345,7 @@ class ViTEngine:
                 K.colsum(dy, self.grad_of(lin.bias))
                 self.launches += 1
 
+    @_lib.no_autocast
     def backward(self, dlogits: torch.Tensor, zero_grad: bool = True) -> None:
         """Fill the flat gradient buffer (and nothing else) from d(loss)/d(logits), (B, n_classes) fp32."""
         bufs = self.bufs

@@ -21,7 +21,10 @@ def _free_port():
 
 
 @pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "train.py")), reason="oracle/_ref not staged (oracle/make_ref.py)")
-def test_reference_train_py_runs_on_the_b200_backend(tmp_path):
+@pytest.mark.parametrize("arch,batch,extra", [("vits", 40, []), ("vits", 40, ["--amp", "1", "--ampdtype", "bf16"]), ("swinv2", 20, [])])
+def test_reference_train_py_runs_on_the_b200_backend(tmp_path, arch, batch, extra):
+    """ViT-S with the reference's defaults (AMP off) and under its autocast + GradScaler loop (`--amp 1 --ampdtype bf16`), SwinV2-T
+    (AMP on by default, utils/configs.py:137): the engines ignore the caller's autocast region."""
     from rgb_no_more_b200 import synth
     data = tmp_path / "data"
     data.mkdir()
@@ -36,21 +39,25 @@ def test_reference_train_py_runs_on_the_b200_backend(tmp_path):
     save = tmp_path / "out" / "model.pth"
     save.parent.mkdir()
     cmd = [sys.executable, "-m", "rgb_no_more_b200.compat.launch", "--ref", REF, "--backend", "b200", "--",
-           "--train", "--eval", "--domain", "dct", "--embed_type", "1", "--model_arch", "vits", "--batch", "40", "--epochs", "1",
+           "--train", "--eval", "--domain", "dct", "--embed_type", "1", "--model_arch", arch, "--batch", str(batch), "--epochs", "1",
            "--warmup_steps", "2", "--num_gpus", "1", "--num_cpus", "4", "--no_extract", "--no_resize", "--temp_datapath", str(data),
            "--indexpaths", f"{tmp_path / 'index_train.csv'},{tmp_path / 'index_val.csv'}", "--savepath", str(save), "--verbose", "1",
-           "--port", str(_free_port()), "--num_ops", "2", "--ops_magnitude", "9"]
+           "--port", str(_free_port()), "--num_ops", "2", "--ops_magnitude", "9"] + extra
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         env.pop(k, None)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, env=env, cwd=str(tmp_path))
     log = r.stdout + r.stderr
     assert r.returncode == 0, log[-4000:]
-    assert "rgbnm B200 backend: ViT (vits)" in log, log[-3000:]                 # the opt-in took effect in the spawned rank
+    banner = "rgbnm B200 backend: ViT (vits)" if arch == "vits" else "rgbnm B200 backend: SwinTransformerV2 (swinv2)"
+    assert banner in log, log[-3000:]                                           # the opt-in took effect in the spawned rank
     # (the reference's own INFO lines -- "Training complete", "Test Acc" -- are emitted in spawned ranks where it never configures
     #  logging; the artefacts below are the evidence that its loop, evaluation and save ran)
     sd = torch.load(save, map_location="cpu")
-    assert len(sd) == 152 and sd["encoder.0.0.fn.eb_mha.qkv.weight"].shape == (1152, 384)     # reference key set (plainvit.py)
-    assert all(torch.isfinite(v).all() for v in sd.values())
+    if arch == "vits":
+        assert len(sd) == 152 and sd["encoder.0.0.fn.eb_mha.qkv.weight"].shape == (1152, 384)     # reference key set (plainvit.py)
+    else:
+        assert len(sd) == 250 and sd["layers.0.blocks.0.attn.qkv.weight"].shape == (288, 96)      # reference key set (swinv2.py)
+    assert all(torch.isfinite(v.float()).all() for v in sd.values() if v is not None)
     ckdir = save.parent / "checkpoints"                                         # per-epoch checkpoint written by the reference loop
     assert ckdir.is_dir() and os.listdir(ckdir), os.listdir(save.parent)
