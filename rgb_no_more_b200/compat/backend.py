@@ -74,11 +74,30 @@ def unpack_data(data, dataset, avail_device, mixup=None, nomixup=False):
         K.mixup(x.contiguous(), out, lam_dev)
         labels = target * lam_dev[0] + target.roll(1, 0) * lam_dev[1]
         x = out
-    return (x, None), labels
+    return (x, L.NO_CHROMA), labels
+
+
+class B200Mixup:
+    """`utils.get_mixup(cfg)` (pipeline_utils.py:169-181) for the B200 backend: the reference's RandomMixup_DCT, which additionally
+    accepts the `(embed input, NoChroma)` pair of a DCTBatch -- the reference's benchmark loop calls `mixup((y, cbcr), labels)` itself
+    (benchmark.py:333-334) instead of going through `unpack_data`."""
+
+    def __init__(self, reference_mixup):
+        self.ref = reference_mixup
+        self.num_classes, self.alpha = reference_mixup.num_classes, reference_mixup.alpha
+
+    def __call__(self, batch, target):
+        y, cbcr = batch
+        if not getattr(cbcr, "_rgbnm_absent", False):
+            return self.ref(batch, target)                        # reference-format planes: the reference's own transform
+        (x, _), labels = unpack_data((L.DCTBatch(y), target), None, None, mixup=self)
+        return (x, cbcr), labels
 
 
 def install(utils_module) -> None:
+    ref_get_mixup = utils_module.get_mixup
     utils_module.get_model = get_model
     utils_module.get_dataset = get_dataset
     utils_module.unpack_data = unpack_data
+    utils_module.get_mixup = lambda cfg: B200Mixup(ref_get_mixup(cfg))
     utils_module._rgbnm_backend = "b200"

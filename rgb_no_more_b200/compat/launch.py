@@ -16,6 +16,11 @@ import sys
 def _child(rank, ref_root, use_b200, *args):
     from rgb_no_more_b200.compat import backend, env
     env.activate(ref_root)
+    if os.environ.get("RGBNM_CHILD_LOG"):
+        # the reference configures logging in the parent only (train.py:236), so its INFO lines ("Training complete", "Test Acc",
+        # the --benchmark FPS table) are dropped in the spawned ranks; opt-in to see them
+        import logging
+        logging.basicConfig(level=logging.INFO, format="%(message)s")
     import train as ref_train                      # the reference's train.py
     if use_b200:
         backend.install(ref_train.utils)

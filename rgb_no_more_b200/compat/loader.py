@@ -22,23 +22,35 @@ from .. import feeder as FD
 from .. import transforms as TF
 
 
+class NoChroma:
+    """Second element of a DCTBatch: the fused kernel has already merged the chroma planes into the embed input.  Survives the
+    reference's `cbcr = inputs[1].to(device)` (benchmark.py:329-332) and is recognised by the B200 model classes (`_rgbnm_absent`)."""
+    _rgbnm_absent = True
+
+    def to(self, *a, **kw):
+        return self
+
+
+NO_CHROMA = NoChroma()
+
+
 class DCTBatch:
     """What the loader yields in place of the reference's `[Y, CbCr]`: the fused kernel's output on the device.
-    Unpacks like the reference pair (`y, cbcr = inputs`): `y` is the embed input, `cbcr` is None -- the B200 model classes
-    accept exactly that (`model(x, None)`)."""
+    Unpacks like the reference pair (`y, cbcr = inputs` / `inputs[0]`, `inputs[1]`): `y` is the embed input, `cbcr` a NoChroma marker
+    -- the B200 model classes accept exactly that (`model(x, NO_CHROMA)`, like `model(x, None)`)."""
 
     def __init__(self, x: torch.Tensor):
         self.x = x
 
     def __iter__(self):
         yield self.x
-        yield None
+        yield NO_CHROMA
 
     def __len__(self):
         return 2
 
     def __getitem__(self, i):
-        return (self.x, None)[i]
+        return (self.x, NO_CHROMA)[i]
 
     def to(self, device, **kw):
         return DCTBatch(self.x.to(device, **kw))

@@ -363,6 +363,8 @@ class SwinTransformerV2(nn.Module):
     def forward(self, y, cbcr=None):
         """forward(y, cbcr) with reference-format tensors (swinv2.py:703-705), or forward(x) with the (B,4096,24) tensor
         FusedDCT(out_size=32) writes."""
+        if getattr(cbcr, "_rgbnm_absent", False):           # compat.loader.DCTBatch: chroma already merged by the fused kernel
+            cbcr = None
         if cbcr is not None:
             y = swin_embed_input_from_planes(y, cbcr)
         elif y.dim() != 3 or y.shape[2] != IN_FEAT:

@@ -513,6 +513,8 @@ class ViT(nn.Module):
     def forward(self, x, cbcr=None):
         """forward(y, cbcr) with reference-format tensors (plainvit.py:601-612), or forward(x) with the
         (B,196,384) tensor FusedDCT writes."""
+        if getattr(cbcr, "_rgbnm_absent", False):           # compat.loader.DCTBatch: chroma already merged by the fused kernel
+            cbcr = None
         if cbcr is not None:
             x = embed_input_from_planes(x, cbcr, subblock=self.use_subblock)
         elif x.dim() != 3 or x.shape[1:] != (TOKENS, IN_FEAT):

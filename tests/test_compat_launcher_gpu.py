@@ -21,10 +21,12 @@ def _free_port():
 
 
 @pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "train.py")), reason="oracle/_ref not staged (oracle/make_ref.py)")
-@pytest.mark.parametrize("arch,batch,extra", [("vits", 40, []), ("vits", 40, ["--amp", "1", "--ampdtype", "bf16"]), ("swinv2", 20, [])])
+@pytest.mark.parametrize("arch,batch,extra", [("vits", 40, []), ("vits", 40, ["--amp", "1", "--ampdtype", "bf16"]), ("swinv2", 20, []),
+                                              ("vits", 40, ["--benchmark", "2"])])
 def test_reference_train_py_runs_on_the_b200_backend(tmp_path, arch, batch, extra):
     """ViT-S with the reference's defaults (AMP off) and under its autocast + GradScaler loop (`--amp 1 --ampdtype bf16`), SwinV2-T
-    (AMP on by default, utils/configs.py:137): the engines ignore the caller's autocast region."""
+    (AMP on by default, utils/configs.py:137): the engines ignore the caller's autocast region.  `--benchmark 2` additionally runs
+    the reference's own loader / model / pipeline throughput loops (eval.py:53-180, benchmark.py) over the B200 loaders and model."""
     from rgb_no_more_b200 import synth
     data = tmp_path / "data"
     data.mkdir()
@@ -43,7 +45,7 @@ def test_reference_train_py_runs_on_the_b200_backend(tmp_path, arch, batch, extr
            "--warmup_steps", "2", "--num_gpus", "1", "--num_cpus", "4", "--no_extract", "--no_resize", "--temp_datapath", str(data),
            "--indexpaths", f"{tmp_path / 'index_train.csv'},{tmp_path / 'index_val.csv'}", "--savepath", str(save), "--verbose", "1",
            "--port", str(_free_port()), "--num_ops", "2", "--ops_magnitude", "9"] + extra
-    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), RGBNM_CHILD_LOG="1")
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         env.pop(k, None)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, env=env, cwd=str(tmp_path))
@@ -51,8 +53,10 @@ def test_reference_train_py_runs_on_the_b200_backend(tmp_path, arch, batch, extr
     assert r.returncode == 0, log[-4000:]
     banner = "rgbnm B200 backend: ViT (vits)" if arch == "vits" else "rgbnm B200 backend: SwinTransformerV2 (swinv2)"
     assert banner in log, log[-3000:]                                           # the opt-in took effect in the spawned rank
-    # (the reference's own INFO lines -- "Training complete", "Test Acc" -- are emitted in spawned ranks where it never configures
-    #  logging; the artefacts below are the evidence that its loop, evaluation and save ran)
+    assert "Test Acc" in log, log[-3000:]                                       # the reference's evaluation ran to the end
+    if "--benchmark" in extra:
+        for line in ("Train loader:", "Model F/B pass:", "Train pipeline:", "Test pipeline:"):
+            assert line in log, log[-3000:]                                     # eval.py:171-177: its FPS table, from the B200 path
     sd = torch.load(save, map_location="cpu")
     if arch == "vits":
         assert len(sd) == 152 and sd["encoder.0.0.fn.eb_mha.qkv.weight"].shape == (1152, 384)     # reference key set (plainvit.py)
