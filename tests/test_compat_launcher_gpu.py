@@ -20,17 +20,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "train.py")), reason="oracle/_ref not staged (oracle/make_ref.py)")
-@pytest.mark.parametrize("arch,batch,extra", [("vits", 40, []), ("vits", 40, ["--amp", "1", "--ampdtype", "bf16"]), ("swinv2", 20, []),
-                                              ("vits", 40, ["--benchmark", "2"])])
-def test_reference_train_py_runs_on_the_b200_backend(tmp_path, arch, batch, extra):
-    """ViT-S with the reference's defaults (AMP off) and under its autocast + GradScaler loop (`--amp 1 --ampdtype bf16`), SwinV2-T
-    (AMP on by default, utils/configs.py:137): the engines ignore the caller's autocast region.  `--benchmark 2` additionally runs
-    the reference's own loader / model / pipeline throughput loops (eval.py:53-180, benchmark.py) over the B200 loaders and model."""
+needs_ref = pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "train.py")), reason="oracle/_ref not staged (oracle/make_ref.py)")
+
+
+def _dataset(tmp_path, rows=120):
     from rgb_no_more_b200 import synth
     data = tmp_path / "data"
     data.mkdir()
-    n_files, rows = 16, 120
+    n_files = 16
     for i in range(n_files):
         (data / f"img_{i}.JPEG").write_bytes(synth.synth_jpeg(i))
     for name in ("train", "val"):
@@ -38,11 +35,13 @@ def test_reference_train_py_runs_on_the_b200_backend(tmp_path, arch, batch, extr
             f.write("Filepath,Label\n")
             for r in range(rows if name == "train" else 40):
                 f.write(f"img_{r % n_files}.JPEG,{r % 8}\n")
-    save = tmp_path / "out" / "model.pth"
-    save.parent.mkdir()
+    return data
+
+
+def _launch(tmp_path, data, modes, arch, batch, extra, save, gpus=1):
     cmd = [sys.executable, "-m", "rgb_no_more_b200.compat.launch", "--ref", REF, "--backend", "b200", "--",
-           "--train", "--eval", "--domain", "dct", "--embed_type", "1", "--model_arch", arch, "--batch", str(batch), "--epochs", "1",
-           "--warmup_steps", "2", "--num_gpus", "1", "--num_cpus", "4", "--no_extract", "--no_resize", "--temp_datapath", str(data),
+           *modes, "--domain", "dct", "--embed_type", "1", "--model_arch", arch, "--batch", str(batch), "--epochs", "1",
+           "--warmup_steps", "2", "--num_gpus", str(gpus), "--num_cpus", "4", "--no_extract", "--no_resize", "--temp_datapath", str(data),
            "--indexpaths", f"{tmp_path / 'index_train.csv'},{tmp_path / 'index_val.csv'}", "--savepath", str(save), "--verbose", "1",
            "--port", str(_free_port()), "--num_ops", "2", "--ops_magnitude", "9"] + extra
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), RGBNM_CHILD_LOG="1")
@@ -51,9 +50,29 @@ def test_reference_train_py_runs_on_the_b200_backend(tmp_path, arch, batch, extr
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, env=env, cwd=str(tmp_path))
     log = r.stdout + r.stderr
     assert r.returncode == 0, log[-4000:]
+    return log
+
+
+def _test_line(log):
+    lines = [ln for ln in log.splitlines() if "[Test Acc:" in ln]
+    assert lines, log[-3000:]
+    return lines[-1][lines[-1].index("[Test Acc:"):]
+
+
+@needs_ref
+@pytest.mark.parametrize("arch,batch,extra", [("vits", 40, []), ("vits", 40, ["--amp", "1", "--ampdtype", "bf16"]), ("swinv2", 20, []),
+                                              ("vits", 40, ["--benchmark", "2"])])
+def test_reference_train_py_runs_on_the_b200_backend(tmp_path, arch, batch, extra):
+    """ViT-S with the reference's defaults (AMP off) and under its autocast + GradScaler loop (`--amp 1 --ampdtype bf16`), SwinV2-T
+    (AMP on by default, utils/configs.py:137): the engines ignore the caller's autocast region.  `--benchmark 2` additionally runs
+    the reference's own loader / model / pipeline throughput loops (eval.py:53-180, benchmark.py) over the B200 loaders and model."""
+    data = _dataset(tmp_path)
+    save = tmp_path / "out" / "model.pth"
+    save.parent.mkdir()
+    log = _launch(tmp_path, data, ["--train", "--eval"], arch, batch, extra, save)
     banner = "rgbnm B200 backend: ViT (vits)" if arch == "vits" else "rgbnm B200 backend: SwinTransformerV2 (swinv2)"
     assert banner in log, log[-3000:]                                           # the opt-in took effect in the spawned rank
-    assert "Test Acc" in log, log[-3000:]                                       # the reference's evaluation ran to the end
+    _test_line(log)                                                             # the reference's evaluation ran to the end
     if "--benchmark" in extra:
         for line in ("Train loader:", "Model F/B pass:", "Train pipeline:", "Test pipeline:"):
             assert line in log, log[-3000:]                                     # eval.py:171-177: its FPS table, from the B200 path
@@ -65,3 +84,30 @@ def test_reference_train_py_runs_on_the_b200_backend(tmp_path, arch, batch, extr
     assert all(torch.isfinite(v.float()).all() for v in sd.values() if v is not None)
     ckdir = save.parent / "checkpoints"                                         # per-epoch checkpoint written by the reference loop
     assert ckdir.is_dir() and os.listdir(ckdir), os.listdir(save.parent)
+
+
+@needs_ref
+def test_eval_only_from_the_saved_checkpoint_reproduces_the_test_metrics(tmp_path):
+    """`--eval --loadpath` (train.py:207-208, utils.load_model_and_report): the checkpoint the reference saved after training on the
+    B200 backend, loaded into a fresh B200 model by the reference's own loader code, gives the same test accuracy / loss line."""
+    data = _dataset(tmp_path)
+    save = tmp_path / "out" / "model.pth"
+    save.parent.mkdir()
+    first = _test_line(_launch(tmp_path, data, ["--train", "--eval"], "vits", 40, [], save))
+    again = _test_line(_launch(tmp_path, data, ["--eval"], "vits", 40, ["--loadpath", str(save)], tmp_path / "out" / "unused.pth"))
+    assert first == again, (first, again)
+
+
+@needs_ref
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_ranks_through_the_reference_launcher(tmp_path):
+    """`--num_gpus 2`: the reference spawns two ranks, wraps the B200 model in DistributedDataParallel (train.py:137) and shards the
+    index with its samplers' arithmetic; the run must finish and save finite weights.  (600 index rows: the reference's minival
+    split is 1 % of the index, and its evaluate_model needs at least one batch on every rank, eval.py:49.)"""
+    data = _dataset(tmp_path, rows=600)
+    save = tmp_path / "out" / "model.pth"
+    save.parent.mkdir()
+    log = _launch(tmp_path, data, ["--train", "--eval"], "vits", 40, [], save, gpus=2)
+    _test_line(log)
+    sd = torch.load(save, map_location="cpu")
+    assert len(sd) == 152 and all(torch.isfinite(v).all() for v in sd.values())
