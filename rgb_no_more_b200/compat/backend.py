@@ -48,7 +48,8 @@ def get_model(cfg, report=True):
 
 def get_dataset(cfg, temp_datapath, indexpaths):
     kw = dict(dataset=cfg.TRAIN.DATASET, basepath=temp_datapath, batch_size=cfg.TRAIN.BATCHPERGPU, num_workers=cfg.THREADS,
-              distributed=True, rank=cfg.RANK, world_size=cfg.WORLDSIZE, seed=cfg.SEED, device=cfg.RANK)
+              distributed=True, rank=cfg.RANK, world_size=cfg.WORLDSIZE, seed=cfg.SEED, device=cfg.RANK,
+              subblock=bool(cfg.MODEL.SUBBLOCK))
     trainloader = valloader = trainvalloader = None
     if cfg.TRAIN.SPLIT > 0:
         trainloader, valloader, trainvalloader = L.dataset_selector(

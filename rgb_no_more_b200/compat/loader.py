@@ -170,10 +170,11 @@ class B200Loader:
 
 def dataset_selector(dataset="imagenet_dct", type="train", indexpath="", basepath="", batch_size=128, num_workers=4, shuffle=False,
                      trainval_split=-1, return_indices=False, distributed=False, rank=-1, world_size=-1, seed=None, ops_list=None,
-                     num_ops=2, ops_magnitude=10, dtype=torch.bfloat16, device=None):
+                     num_ops=2, ops_magnitude=10, dtype=torch.bfloat16, device=None, subblock=True):
     """Same arguments and return structure as the reference's `datasets.dataset_selector` (datasets.py:445-582) for the DCT
     datasets.  `num_workers` becomes the number of host decode threads of this rank (the reference gives each rank
-    `num_cpus // world_size` DataLoader workers, pipeline_utils.py:125)."""
+    `num_cpus // world_size` DataLoader workers, pipeline_utils.py:125).  `subblock` (not a reference argument: there the sub-block
+    conversion lives in the model's patch embedding, plainvit.py:173-216) selects the operand K0 writes for `--no_subblock`."""
     if dataset[0:12] != "imagenet_dct":
         raise NotImplementedError(f"rgbnm: dataset '{dataset}' is outside the B200 hot path (SURVEY.md 8f)")
     dev = device if device is not None else max(rank, 0)
@@ -183,8 +184,9 @@ def dataset_selector(dataset="imagenet_dct", type="train", indexpath="", basepat
     def make(rows_, kind, shuf):
         # the reference's non-split branch does not forward ops_magnitude (datasets.py:568): kept, magnitude falls back to 10
         def tf(mag=ops_magnitude):
+            extra = {} if (subblock or dataset != "imagenet_dct") else {"subblock": False}      # SwinV2 always decomposes blocks
             return TF.get_transform(dataset, "train" if kind == "train" else "val", ops_list=ops_list if kind == "train" else None,
-                                    num_ops=num_ops, ops_magnitude=mag, dtype=dtype, device=dev)
+                                    num_ops=num_ops, ops_magnitude=mag, dtype=dtype, device=dev, **extra)
         return B200Loader(rows_, basepath, tf, batch_size, dev, train=(kind == "train"), shuffle=shuf, rank=r, world_size=w,
                           decode_threads=max(1, num_workers))
     if trainval_split > 0:

@@ -40,7 +40,8 @@ def _dataset(tmp_path, rows=120):
 
 def _launch(tmp_path, data, modes, arch, batch, extra, save, gpus=1):
     cmd = [sys.executable, "-m", "rgb_no_more_b200.compat.launch", "--ref", REF, "--backend", "b200", "--",
-           *modes, "--domain", "dct", "--embed_type", "1", "--model_arch", arch, "--batch", str(batch), "--epochs", "1",
+           *modes, "--domain", "dct", *([] if "--embed_type" in extra else ["--embed_type", "1"]), "--model_arch", arch,
+           "--batch", str(batch), "--epochs", "1",
            "--warmup_steps", "2", "--num_gpus", str(gpus), "--num_cpus", "4", "--no_extract", "--no_resize", "--temp_datapath", str(data),
            "--indexpaths", f"{tmp_path / 'index_train.csv'},{tmp_path / 'index_val.csv'}", "--savepath", str(save), "--verbose", "1",
            "--port", str(_free_port()), "--num_ops", "2", "--ops_magnitude", "9"] + extra
@@ -61,7 +62,8 @@ def _test_line(log):
 
 @needs_ref
 @pytest.mark.parametrize("arch,batch,extra", [("vits", 40, []), ("vits", 40, ["--amp", "1", "--ampdtype", "bf16"]), ("swinv2", 20, []),
-                                              ("vits", 40, ["--benchmark", "2"])])
+                                              ("vits", 40, ["--benchmark", "2"]), ("vits", 40, ["--embed_type", "2"]),
+                                              ("vits", 40, ["--embed_type", "2", "--no_subblock"]), ("vitti", 40, ["--embed_type", "1", "--no_subblock"])])
 def test_reference_train_py_runs_on_the_b200_backend(tmp_path, arch, batch, extra):
     """ViT-S with the reference's defaults (AMP off) and under its autocast + GradScaler loop (`--amp 1 --ampdtype bf16`), SwinV2-T
     (AMP on by default, utils/configs.py:137): the engines ignore the caller's autocast region.  `--benchmark 2` additionally runs
@@ -70,15 +72,21 @@ def test_reference_train_py_runs_on_the_b200_backend(tmp_path, arch, batch, extr
     save = tmp_path / "out" / "model.pth"
     save.parent.mkdir()
     log = _launch(tmp_path, data, ["--train", "--eval"], arch, batch, extra, save)
-    banner = "rgbnm B200 backend: ViT (vits)" if arch == "vits" else "rgbnm B200 backend: SwinTransformerV2 (swinv2)"
+    banner = f"rgbnm B200 backend: ViT ({arch})" if arch != "swinv2" else "rgbnm B200 backend: SwinTransformerV2 (swinv2)"
     assert banner in log, log[-3000:]                                           # the opt-in took effect in the spawned rank
     _test_line(log)                                                             # the reference's evaluation ran to the end
     if "--benchmark" in extra:
         for line in ("Train loader:", "Model F/B pass:", "Train pipeline:", "Test pipeline:"):
             assert line in log, log[-3000:]                                     # eval.py:171-177: its FPS table, from the B200 path
     sd = torch.load(save, map_location="cpu")
-    if arch == "vits":
-        assert len(sd) == 152 and sd["encoder.0.0.fn.eb_mha.qkv.weight"].shape == (1152, 384)     # reference key set (plainvit.py)
+    if arch != "swinv2":
+        from rgb_no_more_b200 import vit as V
+        emb, heads = (384, 6) if arch == "vits" else (192, 3)
+        ver = int(extra[extra.index("--embed_type") + 1]) if "--embed_type" in extra else 1
+        twin = V.ViT(patch_size=16, emb_size=emb, depth=12, n_classes=1000, drop_p=0.0, num_heads=heads, head_size=64, pixel_space="DCT",
+                     ver=ver, use_subblock="--no_subblock" not in extra)
+        assert sorted(sd.keys()) == sorted(twin.state_dict().keys())                 # = the reference's key set for this embedding
+        assert sd["encoder.0.0.fn.eb_mha.qkv.weight"].shape == (3 * emb, emb)
     else:
         assert len(sd) == 250 and sd["layers.0.blocks.0.attn.qkv.weight"].shape == (288, 96)      # reference key set (swinv2.py)
     assert all(torch.isfinite(v.float()).all() for v in sd.values() if v is not None)
