@@ -3,6 +3,7 @@
 // out-of-bounds access).  Prints one "<rc_info> <rc_read> <rc_batch>" line per file.
 #include <cstdint>
 #include <cstdio>
+#include <initializer_list>
 #include <vector>
 
 #include "../../include/rgbnm_b200.h"
@@ -33,6 +34,11 @@ int main(int argc, char** argv) {
             int32_t status[1] = {0};
             r2 = rgbnm_jpeg_decode_batch(ptrs, sizes, 1, 64, 64, y.data(), c.data(), q.data(), flags, status, 1);
             if (r2 == 0) r2 = status[0];
+            // plan-first variant: stop rows below, inside and beyond the image (and a negative one) must stay in bounds
+            for (int32_t last : {-5, 0, 17, 1000}) {
+                const int32_t rows[1] = {last};
+                (void)rgbnm_jpeg_decode_batch_rows(ptrs, sizes, 1, 64, 64, y.data(), c.data(), q.data(), flags, status, 1, rows);
+            }
         }
         std::printf("%d %d %d\n", r0, r1, r2);
         delete[] data;
